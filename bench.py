@@ -1,0 +1,263 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of proxtv_b200:  tv1_2d (DR2_TV) Mpixels/s on 4096 x 4096 float64 images, lambda = 0.2.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--size M] [--engine auto|seq|chunked]
+
+One "step" = one complete solve (35 Douglas-Rachford iterations + the final projection pair, 72 fiber passes) of one
+4096 x 4096 image per GPU (BASELINE.json configs[1]; synthetic piecewise-constant + Gaussian-noise input).
+N > 1 (launched by torchrun, one rank per GPU): every rank solves its own independent image -- the path has no data-path
+collective ("replicas only" for a single array), so scaling is weak and `value` aggregates all ranks.
+
+Rank 0 prints ONE JSON line.  Keys beyond the base contract:
+  roofline      dominant kernel class (by summed CUDA-event time inside the timed steps): algorithmic bytes per launch /
+                average launch duration, against MEASURED_PEAKS.json's hbm_gbs (fallback 6650 GB/s, flagged).
+  roofline_solve  the north-star figure: whole-solve algorithmic bytes (1728 B/pixel) / solve time.
+  e2e           same metric through the reference-facing C ABI call DR2_TV() with pinned HOST buffers (H2D + D2H inside).
+  cpu_baseline  the reference's own OpenMP DR2_TV (oracle/_ref, compiled from the unmodified sources) on this box's host
+                cores, N = 1 only, on a bounded sample.
+--impl reference times only that CPU implementation (rank 0 alone), same metric/config.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+B_PER_PIXEL_SOLVE = lambda b, maxit=35: b * (1 + 6 * maxit + 5)      # noqa: E731  SURVEY.md 8d: M*N*b*(1 + 6*maxit + 5)
+LAM = 0.2
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:  # noqa: BLE001
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index; self.proc = None; self.path = "/tmp/proxtv_clocks_%d_%d.csv" % (os.getpid(), index)
+
+    def start(self):
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        for line in open(self.path):
+            p = [q.strip() for q in line.split(",")]
+            if len(p) < 8:
+                continue
+            try:
+                sm.append(float(p[1])); mx.append(float(p[2]))
+            except ValueError:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], p[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        if sm:
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        return out
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation (OpenMP DR2_TV), all host cores, rank 0 only."""
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    try:
+        R = O.Ref(); kind = "reference"
+    except Exception:  # noqa: BLE001
+        R = O.Port(); kind = "port"
+    cores = os.cpu_count() or 1
+    M = args.size
+    Y = O.gen_cfg2(M, M, seed=0)
+    # bounded sample: a strip of full-length columns (fibers of the first pass keep their length M); pick the widest strip
+    # (number of columns) that keeps the whole run within ~2.5 minutes, from a quick probe.
+    probe_cols = max(M // 16, 8)
+    t0 = time.perf_counter(); R.dr2_tv(np.asfortranarray(Y[:, :probe_cols]), LAM, n_threads=cores); tp = time.perf_counter() - t0
+    budget = 150.0 / max(args.steps + args.warmup, 1)
+    cols = M
+    while cols > probe_cols and tp * (cols / probe_cols) > budget:
+        cols //= 2
+    S = np.asfortranarray(Y[:, :cols])
+    for _ in range(args.warmup):
+        R.dr2_tv(S, LAM, n_threads=cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        R.dr2_tv(S, LAM, n_threads=cores)
+    dt = (time.perf_counter() - t0) / max(args.steps, 1)
+    v = S.size / dt / 1e6
+    sample = "%dx%d strip of the %dx%d image per step (all %d columns)" % (M, cols, M, M, cols) if cols < M else "full %dx%d image per step" % (M, M)
+    print(json.dumps({
+        "impl": "reference", "metric": "tv1_2d Mpixels/s", "value": v, "unit": "Mpixels/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "tv1_2d DR2_TV %dx%d f64 lambda=%.1f, 35 iterations + final projection" % (M, M, LAM)},
+        "cpu_baseline": {"value": v, "unit": "Mpixels/s", "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": v, "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--size", type=int, default=4096)
+    ap.add_argument("--engine", default="auto")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import proxtv_b200 as ptv
+    from oracle import oracle as O          # input generators + the cpu_baseline leg only
+
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = ptv.require_device()
+    ptv.set_engine(args.engine)
+    M = args.size
+    Yh = O.gen_cfg2(M, M, seed=rank)                                     # F-ordered float64, one image per rank
+    Yd = torch.from_numpy(np.ascontiguousarray(Yh.T)).cuda()             # device copy, column-major image
+    out = torch.empty_like(Yd)
+    info = np.zeros(3)
+    st = torch.cuda.current_stream()
+    stp = C.c_void_p(st.cuda_stream)
+
+    def solve():
+        lib.proxtv_DR2_TV_dev_f64(M, M, 1, 0, C.c_void_p(Yd.data_ptr()), LAM, LAM, C.c_void_p(out.data_ptr()), 0,
+                                  C.c_void_p(info.ctypes.data), stp)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        solve()
+    barrier()
+    assert info[2] == 0, "DR2_TV reported an error: " + ptv._lib.last_error()
+    lib.proxtv_profile_reset(); lib.proxtv_profile_enable(1)
+    clocks = ClockSampler(local); clocks.start()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(st)
+    for _ in range(args.steps):
+        solve()
+    e1.record(st)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clk = clocks.stop()
+    lib.proxtv_profile_enable(0)
+    kms = (C.c_double * 3)(); kl = (C.c_longlong * 3)(); ks = (C.c_longlong * 3)()
+    lib.proxtv_profile_read(kms, kl, ks)
+    tmax = torch.tensor([ms], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms_step = float(tmax.item()) / args.steps
+    value = world * M * M / (ms_step * 1e-3) / 1e6
+
+    # ---- end to end through the reference-facing C ABI (host buffers, pinned; H2D + D2H inside the timed region) ----
+    nbytes = M * M * 8
+    hin = lib.proxtv_host_alloc(nbytes); hout = lib.proxtv_host_alloc(nbytes)
+    C.memmove(hin, Yh.ctypes.data, nbytes)
+    einfo = np.zeros(3)
+
+    def solve_host():
+        lib.DR2_TV(M, M, C.c_void_p(hin), LAM, LAM, 1.0, 1.0, C.c_void_p(hout), 1, 0, C.c_void_p(einfo.ctypes.data))
+
+    solve_host()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        solve_host()                       # synchronous: returns after the D2H copy completed
+    torch.cuda.synchronize()
+    et = torch.tensor([(time.perf_counter() - t0) * 1e3], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(et, op=dist.ReduceOp.MAX)
+    e2e_value = world * M * M / (float(et.item()) / args.steps * 1e-3) / 1e6
+    res = np.ctypeslib.as_array(C.cast(hout, C.POINTER(C.c_double)), shape=(M * M,))
+    same = bool(np.array_equal(res, out.cpu().numpy().ravel()))
+    lib.proxtv_host_free(hin); lib.proxtv_host_free(hout)
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        names = ["prox_contiguous_fibers", "prox_strided_fibers", "elementwise"]
+        # algorithmic bytes per launch of each kernel class for this workload (DESIGN.md "Kernels"): f64 sweeps of the image
+        # v0 (unfused) : contiguous prox 1R+1W ; strided prox 2R+1W ; elementwise helpers 2R+1W .. 4R+1W (avg listed)
+        fused = bool(int(kl[2]) < 10 * args.steps)
+        sweeps = {0: 2.0, 1: 4.0 if fused else 3.0, 2: 3.5}
+        dom = int(np.argmax([kms[i] for i in range(3)]))
+        avg_ms = kms[dom] / max(ks[dom], 1)
+        ach = sweeps[dom] * M * M * 8 / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
+        solve_bytes = B_PER_PIXEL_SOLVE(8) * M * M
+        line = {
+            "metric": "tv1_2d Mpixels/s", "value": value, "unit": "Mpixels/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "tv1_2d DR2_TV %dx%d f64 lambda=%.1f, 35 iterations + final projection, one image per GPU"
+                                   % (M, M, LAM), "engine": args.engine,
+                       "l2": "working set 4 x %d MiB > 126 MB L2 (inputs larger than L2, no flush)" % (nbytes >> 20)},
+            "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": ach, "peak": peak, "unit": "GB/s",
+                         "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                         "avg_launch_ms": avg_ms, "launches_timed": int(ks[dom]),
+                         "class_ms_per_step": {names[i]: kms[i] / args.steps for i in range(3)}},
+            "roofline_solve": {"algorithmic_bytes": solve_bytes, "achieved": solve_bytes / (ms_step * 1e-3) / 1e9,
+                               "peak": peak, "unit": "GB/s", "frac": solve_bytes / (ms_step * 1e-3) / 1e9 / peak},
+            "e2e": {"value": e2e_value, "unit": "Mpixels/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
+                    "api": "DR2_TV() C ABI, pinned host buffers", "matches_device_path": same},
+            "gpu_launches": int(sum(kl[i] for i in range(3))),
+            "clocks": clk,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                R = O.Ref(); kind = "reference"
+            except Exception:  # noqa: BLE001
+                R = O.Port(); kind = "port"
+            cores = os.cpu_count() or 1
+            cols = max(M // 4, 8)                     # bounded sample: a quarter-width strip, full-length first-pass fibers
+            S = np.asfortranarray(Yh[:, :cols])
+            t0 = time.perf_counter(); R.dr2_tv(S, LAM, n_threads=cores); dt = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": S.size / dt / 1e6, "unit": "Mpixels/s", "cores": cores, "kind": kind,
+                                    "sample": "one DR2_TV solve of a %dx%d strip of the image, %d OpenMP threads" % (M, cols, cores)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

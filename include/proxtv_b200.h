@@ -1,0 +1,137 @@
+/*
+ * proxtv_b200.h -- C ABI of libproxtv_b200.so, the B200-native TV-L1 proximity operators.
+ *
+ * Part 1 re-exports, with identical names, prototypes, argument meaning, return values and info[] contents, the hot-path
+ * subset of the reference's C interface (src/TVopt.h:88-141 == the cffi cdef in prox_tv/prox_tv_build.py:8-77), so the
+ * reference's Python wrapper (prox_tv/__init__.py) or MATLAB mex glue can bind this library instead of its own object
+ * code.  All pointers in Part 1 are HOST pointers, arrays are float64, 2D/ND arrays column-major;
+ * the caller owns every buffer; nothing is retained after return.  The computation runs on the current CUDA device
+ * (cuda:0 unless cudaSetDevice was called by the host process); there is no CPU fallback: without a usable device
+ * the calls print an error, set info[2] = RC_ERROR (3) where an info array exists and leave the output untouched.
+ *
+ * Part 2 adds what the BASELINE configurations need and the reference lacks: device-pointer variants (no PCIe traffic),
+ * a leading batch dimension, float32 instantiations and pinned-host helpers.
+ *
+ * Plain C: no C++/torch types cross this boundary.
+ */
+#ifndef PROXTV_B200_H
+#define PROXTV_B200_H
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* info[] slots and return codes -- reference: src/general.h:58-73 */
+#define PROXTV_INFO_ITERS 0
+#define PROXTV_INFO_GAP 1
+#define PROXTV_INFO_RC 2
+#define PROXTV_RC_OK 0
+#define PROXTV_RC_ITERS 1
+#define PROXTV_RC_STUCK 2
+#define PROXTV_RC_ERROR 3
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Part 1 -- drop-in symbols (host pointers, float64)
+ * ------------------------------------------------------------------------------------------------------------------ */
+
+/* replaces src/TVL1opt_hybridtautstring.cpp:237 (prototype src/TVopt.h:96).  x = argmin 0.5|x-y|^2 + lambda*sum|x_i-x_{i+1}|.
+ * Computed with the linearized taut-string scan; the reference's switch to the classic method after n^1.05 steps is an
+ * execution-time heuristic that changes results by <= 5e-11 abs and is not reproduced. */
+void hybridTautString_TV1(double *y, int n, double lambda, double *x);
+/* replaces src/TVL1opt_hybridtautstring.cpp:56 (src/TVopt.h:97); backtracksexp is accepted and ignored (see above). */
+void hybridTautString_TV1_custom(double *y, int n, double lambda, double *x, double backtracksexp);
+/* replaces src/TVL1opt_tautstring.cpp:355 (src/TVopt.h:95).  Returns 1.  lam <= 0 or n == 1: x = signal (:258-263). */
+int classicTautString_TV1(double *signal, int n, double lam, double *prox);
+/* replaces src/TVL1opt.cpp:359 (src/TVopt.h:94).  Returns 1.  Bit-identical to the reference. */
+int linearizedTautString_TV1(double *y, double lambda, double *x, int n);
+/* replaces src/condat_fast_tv.cpp:78 (src/condat_fast_tv.h).  In-place (output == input) allowed; width <= 0 or
+ * lambda < 0: nothing is done (:79). */
+void TV1D_denoise(double *input, double *output, const int width, const double lambda);
+/* replaces src/TVL1Wopt.cpp:364 (src/TVopt.h:103).  lambda has n-1 entries.  Returns 1.  Bit-identical to the reference. */
+int tautString_TV1_Weighted(double *y, double *lambda, double *x, int n);
+/* replaces src/TVgenopt.cpp:30 (src/TVopt.h:91) for p == 1 only (other norms: prints an error, RC_ERROR, returns 0).
+ * ws is ignored (the reference's Python wrapper always passes NULL). */
+int TV(double *y, double lambda, double *x, double *info, int n, double p, void *ws);
+/* replaces src/TV2Dopt.cpp:352 (src/TVopt.h:128).  M x N column-major; fixed maxit iterations (<= 0: 35) + final
+ * projection; info = {maxit, untouched, RC_OK}; returns 0 on success AND on error, like the reference (:440, :372).
+ * norm1, norm2 must be 1; nThreads is ignored. */
+int DR2_TV(size_t M, size_t N, double *unary, double W1, double W2, double norm1, double norm2, double *s, int nThreads,
+           int maxit, double *info);
+/* replaces src/TV2Dopt.cpp:59 (src/TVopt.h:126).  npen <= 2, norms must be 1, dims are 1-based; info = {iters, stop, RC};
+ * RC_ITERS is set when iters >= 35 regardless of maxIters (:289); returns 1 ok / 0 error. */
+int PD2_TV(double *y, double *lambdas, double *norms, double *dims, double *x, double *info, int *ns, int nds, int npen,
+           int ncores, int maxIters);
+/* replaces src/TVNDopt.cpp:48 (src/TVopt.h:137).  Like the reference it multiplies lambdas[] by npen IN PLACE (:100-101). */
+int PD_TV(double *y, double *lambdas, double *norms, double *dims, double *x, double *info, int *ns, int nds, int npen,
+          int ncores, int maxIters);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Part 2 -- extensions.  *_dev functions take DEVICE pointers and a cudaStream_t passed as void* (NULL = default
+ * stream); they enqueue work and return without synchronising unless stated.  Return value: 1 ok / 0 error, except the
+ * DR2 family which follows DR2_TV (always 0; check info[2]).
+ * ------------------------------------------------------------------------------------------------------------------ */
+
+int proxtv_device_count(void);                 /* usable CUDA devices (0 => every entry point fails loudly) */
+const char *proxtv_last_error(void);           /* last error text of the calling thread ("" if none) */
+const char *proxtv_version(void);
+
+/* kernel family: 0 auto, 1 sequential lane-per-fiber, 2 chunked speculative.  Returns the previous value. */
+int proxtv_set_engine(int engine);
+
+/* Batched 1D prox over the fibers of a column-major array: nf fibers of len samples, fiber j starting at
+ * (j / inc) * inc * len + (j % inc) with element stride inc (the reference's slicing rule, src/TVNDopt.cpp:184-188;
+ * inc == 1: nf contiguous signals back to back).  lamv == NULL: uniform weight lam, else per-edge weights laid out the
+ * same way with len-1 samples per fiber (batched tautString_TV1_Weighted). */
+int proxtv_prox_fibers_dev_f64(const double *in, double *out, long long nf, int len, long long inc, double lam,
+                               const double *lamv, void *stream);
+int proxtv_prox_fibers_dev_f32(const float *in, float *out, long long nf, int len, long long inc, float lam,
+                               const float *lamv, void *stream);
+/* host-pointer form of the above (pageable or pinned memory); synchronous. */
+int proxtv_prox_fibers_f64(const double *in, double *out, long long nf, int len, long long inc, double lam,
+                           const double *lamv);
+int proxtv_prox_fibers_f32(const float *in, float *out, long long nf, int len, long long inc, float lam,
+                           const float *lamv);
+
+/* DR2_TV on `batch` independent M x N images stored back to back.  info (host, 3 doubles, may be NULL).
+ * row_major = 0: column-major images (the reference's layout); 1: row-major (C order) images -- the pass order
+ * (axis 0 first, then axis 1) is the same, only the kernels' stride roles swap, so no transpose is ever made. */
+int proxtv_DR2_TV_dev_f64(size_t M, size_t N, int batch, int row_major, const double *Y, double W1, double W2, double *out, int maxit,
+                          double *info, void *stream);
+int proxtv_DR2_TV_dev_f32(size_t M, size_t N, int batch, int row_major, const float *Y, float W1, float W2, float *out, int maxit,
+                          double *info, void *stream);
+int proxtv_DR2_TV_batched_f64(size_t M, size_t N, int batch, const double *Y, double W1, double W2, double *out, int maxit,
+                              double *info);
+int proxtv_DR2_TV_batched_f32(size_t M, size_t N, int batch, const float *Y, float W1, float W2, float *out, int maxit,
+                              double *info);
+
+/* PD2_TV / PD_TV with device arrays y, x (lambdas, dims, ns, info stay on the host).  Synchronous (the stop test needs
+ * one 8-byte read-back per iteration).  proxtv_PD_TV_* scale lambdas in place like PD_TV. */
+int proxtv_PD2_TV_dev_f64(const double *y, double *lambdas, double *dims, double *x, double *info, int *ns, int nds,
+                          int npen, int maxIters, void *stream);
+int proxtv_PD2_TV_dev_f32(const float *y, double *lambdas, double *dims, float *x, double *info, int *ns, int nds, int npen,
+                          int maxIters, void *stream);
+int proxtv_PD_TV_dev_f64(const double *y, double *lambdas, double *dims, double *x, double *info, int *ns, int nds, int npen,
+                         int maxIters, void *stream);
+int proxtv_PD_TV_dev_f32(const float *y, double *lambdas, double *dims, float *x, double *info, int *ns, int nds, int npen,
+                         int maxIters, void *stream);
+int proxtv_PD_TV_f32(const float *y, double *lambdas, double *dims, float *x, double *info, int *ns, int nds, int npen,
+                     int maxIters);                                          /* host pointers, float32 */
+
+/* Launch accounting and optional CUDA-event timing per kernel class (0: prox over contiguous fibers, 1: prox over strided
+ * fibers, 2: elementwise/reduction helpers).  Launch counters always run; event timing only while enabled.  read():
+ * arrays of 3; ms = summed event time, launches = kernels launched, spans = timed brackets; synchronises the events. */
+void proxtv_profile_enable(int on);
+void proxtv_profile_reset(void);
+void proxtv_profile_read(double *ms, long long *launches, long long *spans);
+
+/* pinned host memory for the end-to-end path (cudaHostAlloc / cudaFreeHost) */
+void *proxtv_host_alloc(size_t bytes);
+void proxtv_host_free(void *p);
+/* release the cached device workspace */
+void proxtv_release_workspace(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PROXTV_B200_H */

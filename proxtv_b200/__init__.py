@@ -1,0 +1,291 @@
+"""proxtv_b200 -- B200-native Total-Variation (TV-L1) proximity operators behind proxTV's Python surface.
+
+Drop-in for the hot path of ``prox_tv`` (reference: prox_tv/__init__.py): ``tv1_1d`` (:124), ``tv1w_1d`` (:218),
+``tv1_2d`` (:355) and ``tvgen`` (:533) keep the reference's names, argument meaning, dtype/layout coercion, assertion
+behaviour and return conventions; the computation runs in hand-written sm_100a CUDA kernels reached through the C ABI of
+``libproxtv_b200.so`` (include/proxtv_b200.h).  There is NO CPU fallback: without the built extension or a CUDA
+device the calls raise.
+
+Extensions the reference lacks: a leading batch dimension (``tv1_1d_batched``,
+``tv1w_1d_batched``, ``tv1_2d_batched``), float32, and torch CUDA tensors as inputs (device-resident path: no PCIe
+traffic, no host transposes -- a C-ordered tensor is handled by swapping the kernels' stride roles).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import ProxTVError, load, require_device  # noqa: F401
+
+__all__ = ["tv1_1d", "tv1w_1d", "tv1_2d", "tvgen", "tv1_1d_batched", "tv1w_1d_batched", "tv1_2d_batched",
+           "set_engine", "ProxTVError"]
+
+_N_INFO = 3                      # prox_tv/__init__.py:67
+ENGINES = {"auto": 0, "seq": 1, "chunked": 2}
+
+
+def set_engine(name):
+    """Select the kernel family ('auto' | 'seq' | 'chunked'); returns the previous one."""
+    prev = load().proxtv_set_engine(ENGINES[name])
+    return [k for k, v in ENGINES.items() if v == prev][0]
+
+
+# ---- argument coercion, as the reference does it (prox_tv/__init__.py:80-121) ----
+def force_float_scalar(x):
+    return x if isinstance(x, float) else float(x)
+
+
+def force_float_matrix(x):
+    if not isinstance(x, np.ndarray):
+        try:
+            x = np.array(x)
+        except Exception:
+            raise TypeError("Input must be a numpy matrix or compatible object")
+    if x.dtype != np.dtype("float64"):
+        return x.astype("float")
+    return x
+
+
+def _ptr(a):
+    return C.c_void_p(a.ctypes.data)
+
+
+def _is_torch(x):
+    return type(x).__module__.startswith("torch") and hasattr(x, "data_ptr")
+
+
+def _check(ok, what):
+    if not ok:
+        raise ProxTVError("%s failed: %s" % (what, _lib.last_error()))
+
+
+# ======================================================================================================================
+# 1D
+# ======================================================================================================================
+_TV1_METHODS = ("classictautstring", "linearizedtautstring", "hybridtautstring", "pn", "condat", "dp",
+                "condattautstring", "kolmogorov")      # prox_tv/__init__.py:163-172
+
+
+def tv1_1d(x, w, method="hybridtautstring", sigma=0.05, maxbacktracks=None):
+    r"""1D TV-L1 prox: argmin_y 0.5||x-y||^2 + w sum_i |y_i - y_{i+1}|   (prox_tv/__init__.py:124-178).
+
+    Every ``method`` of the reference computes the same unique minimiser; here they all run the exact linearized
+    taut-string scan on the GPU (bit-identical to the reference's 'linearizedtautstring' and, whenever its backtracking
+    budget is not exhausted, to its default 'hybridtautstring').  ``sigma`` / ``maxbacktracks`` are accepted and ignored.
+    Returns a flat float64 array of ``np.size(x)`` elements, like the reference.
+    """
+    assert method in _TV1_METHODS
+    assert w >= 0
+    w = force_float_scalar(w)
+    x = force_float_matrix(x)
+    y = np.zeros(np.size(x))
+    if x.size:
+        lib = require_device()
+        xin = x if x.flags.c_contiguous or x.flags.f_contiguous else np.ascontiguousarray(x)
+        _check(lib.proxtv_prox_fibers_f64(_ptr(xin), _ptr(y), 1, int(np.size(x)), 1, w, None), "tv1_1d")
+    return y
+
+
+def tv1w_1d(x, w, method="tautstring", sigma=0.05):
+    r"""Weighted 1D TV-L1 prox: argmin_y 0.5||x-y||^2 + sum_i w_i |y_i - y_{i+1}|   (prox_tv/__init__.py:218-254).
+
+    Both reference methods ('tautstring', 'pn') compute the same minimiser; the GPU path is the weighted taut-string
+    scan, bit-identical to the reference's 'tautstring'.
+    """
+    assert np.all(w >= 0)
+    assert np.size(x) - 1 == np.size(w)
+    w = force_float_matrix(w)
+    x = force_float_matrix(x)
+    y = np.zeros(np.size(x))
+    n = int(np.size(x))
+    if n == 1:
+        y[0] = x.ravel()[0]
+    elif n > 1:
+        lib = require_device()
+        _check(lib.proxtv_prox_fibers_f64(_ptr(np.ascontiguousarray(x)), _ptr(y), 1, n, 1, 0.0,
+                                          _ptr(np.ascontiguousarray(w))), "tv1w_1d")
+    return y
+
+
+def _batched_1d(x, w, weights):
+    """x: (B, L) numpy array or torch CUDA tensor, row-contiguous signals."""
+    if _is_torch(x):
+        import torch
+        assert x.is_cuda and x.dim() == 2
+        xt = x.contiguous()
+        f32 = xt.dtype == torch.float32
+        if not f32 and xt.dtype != torch.float64:
+            xt = xt.double()
+        out = torch.empty_like(xt)
+        B, L = xt.shape
+        wt = None
+        if weights is not None:
+            wt = weights.to(dtype=xt.dtype, device=xt.device).contiguous()
+            assert tuple(wt.shape) == (B, L - 1)
+        lib = require_device()
+        st = C.c_void_p(torch.cuda.current_stream(xt.device).cuda_stream)
+        fn = lib.proxtv_prox_fibers_dev_f32 if f32 else lib.proxtv_prox_fibers_dev_f64
+        with torch.cuda.device(xt.device):
+            _check(fn(C.c_void_p(xt.data_ptr()), C.c_void_p(out.data_ptr()), B, L, 1, float(w),
+                      C.c_void_p(wt.data_ptr()) if wt is not None else None, st), "batched 1D prox")
+        return out
+    x = np.asarray(x)
+    assert x.ndim == 2
+    f32 = x.dtype == np.float32
+    x = np.ascontiguousarray(x, dtype=np.float32 if f32 else np.float64)
+    B, L = x.shape
+    out = np.empty_like(x)
+    wv = None
+    if weights is not None:
+        wv = np.ascontiguousarray(weights, dtype=x.dtype)
+        assert wv.shape == (B, L - 1)
+        assert np.all(wv >= 0)
+    if x.size:
+        lib = require_device()
+        fn = lib.proxtv_prox_fibers_f32 if f32 else lib.proxtv_prox_fibers_f64
+        _check(fn(_ptr(x), _ptr(out), B, L, 1, float(w), _ptr(wv) if wv is not None else None), "batched 1D prox")
+    return out
+
+
+def tv1_1d_batched(x, w):
+    """``tv1_1d`` on every row of a (B, L) array (numpy float64/float32, or a torch CUDA tensor)."""
+    assert w >= 0
+    return _batched_1d(x, float(w), None)
+
+
+def tv1w_1d_batched(x, w):
+    """``tv1w_1d`` on every row of x (B, L) with per-edge weights w (B, L-1)  -- BASELINE config 3."""
+    return _batched_1d(x, 0.0, w)
+
+
+# ======================================================================================================================
+# 2D
+# ======================================================================================================================
+_TV1_2D_METHODS = ("yang", "dr", "pd", "kolmogorov", "condat", "chambolle-pock", "chambolle-pock-acc")  # :391-399
+
+
+def tv1_2d(x, w, n_threads=1, max_iters=0, method="dr"):
+    r"""2D anisotropic TV-L1 prox (prox_tv/__init__.py:355-416).
+
+    ``method='dr'`` (default) reproduces the reference's DR2_TV iteration exactly (35 fixed iterations unless
+    ``max_iters`` > 0 -- NOT a converged solve); ``'pd'`` reproduces PD2_TV.  The other
+    reference methods are slower CPU baselines for the same problem and are not provided.  ``n_threads`` is ignored.
+    numpy input: returns a Fortran-ordered float64 array like the reference.  torch CUDA tensor input (2D, float64 or
+    float32): stays on the device and returns a tensor of the same dtype/layout.
+    """
+    assert w >= 0
+    assert method in _TV1_2D_METHODS
+    if method not in ("dr", "pd"):
+        raise NotImplementedError("proxtv_b200 implements the 'dr' and 'pd' 2D solvers (the GPU hot path); got %r" % method)
+    if _is_torch(x):
+        assert method == "dr", "torch path implements the DR solver"
+        return _dr2_torch(x, float(w), max_iters, batched=False)
+    x = np.asfortranarray(x, dtype="float64")
+    assert x.ndim == 2
+    w = force_float_scalar(w)
+    y = np.asfortranarray(np.zeros(x.shape))
+    info = np.zeros(_N_INFO)
+    lib = require_device()
+    if method == "dr":
+        lib.DR2_TV(x.shape[0], x.shape[1], _ptr(x), w, w, 1.0, 1.0, _ptr(y), int(n_threads), int(max_iters), _ptr(info))
+        _check(info[2] != 3, "DR2_TV")
+    else:
+        lam = np.array([w, w]); norms = np.array([1.0, 1.0]); dims = np.array([1.0, 2.0])
+        ns = np.array(x.shape, dtype=np.int32)
+        ok = lib.PD2_TV(_ptr(x), _ptr(lam), _ptr(norms), _ptr(dims), _ptr(y), _ptr(info), _ptr(ns), 2, 2,
+                        int(n_threads), int(max_iters))
+        _check(ok and info[2] != 3, "PD2_TV")
+    return y
+
+
+def _dr2_torch(x, w, max_iters, batched):
+    import torch
+    assert x.is_cuda and x.dtype in (torch.float64, torch.float32)
+    assert x.dim() == (3 if batched else 2)
+    M, N = int(x.shape[-2]), int(x.shape[-1])
+    batch = int(x.shape[0]) if batched else 1
+    # accept either memory order of the trailing two dims without copying
+    if x.stride(-1) == 1 and x.stride(-2) == N and (not batched or x.stride(0) == M * N):
+        row_major, xin = 1, x
+    elif x.stride(-2) == 1 and x.stride(-1) == M and (not batched or x.stride(0) == M * N):
+        row_major, xin = 0, x
+    else:
+        row_major, xin = 1, x.contiguous()
+    out = torch.empty_strided(xin.shape, xin.stride(), dtype=xin.dtype, device=xin.device)
+    info = np.zeros(_N_INFO)
+    lib = require_device()
+    st = C.c_void_p(torch.cuda.current_stream(xin.device).cuda_stream)
+    fn = lib.proxtv_DR2_TV_dev_f32 if xin.dtype == torch.float32 else lib.proxtv_DR2_TV_dev_f64
+    with torch.cuda.device(xin.device):
+        fn(M, N, batch, row_major, C.c_void_p(xin.data_ptr()), w, w, C.c_void_p(out.data_ptr()), int(max_iters),
+           _ptr(info), st)
+    _check(info[2] != 3, "DR2_TV (device)")
+    return out
+
+
+def tv1_2d_batched(x, w, max_iters=0):
+    """``tv1_2d(method='dr')`` on every image of x (B, H, W)  -- BASELINE config 5.
+
+    numpy: float64 or float32, C-ordered (B, H, W); torch: CUDA tensor (B, H, W).  Each image is solved independently with
+    exactly the single-image iteration (its own 2*mean initialisation).
+    """
+    assert w >= 0
+    if _is_torch(x):
+        return _dr2_torch(x, float(w), max_iters, batched=True)
+    x = np.asarray(x)
+    assert x.ndim == 3
+    f32 = x.dtype == np.float32
+    B, H, W = x.shape
+    # device layout: column-major images back to back == C-ordered (B, W, H) array of transposed images
+    xt = np.ascontiguousarray(np.transpose(x, (0, 2, 1)), dtype=np.float32 if f32 else np.float64)
+    out = np.empty_like(xt)
+    info = np.zeros(_N_INFO)
+    lib = require_device()
+    fn = lib.proxtv_DR2_TV_batched_f32 if f32 else lib.proxtv_DR2_TV_batched_f64
+    fn(H, W, B, _ptr(xt), float(w), float(w), _ptr(out), int(max_iters), _ptr(info))
+    _check(info[2] != 3, "DR2_TV (batched)")
+    return np.transpose(out, (0, 2, 1))
+
+
+# ======================================================================================================================
+# ND
+# ======================================================================================================================
+def tvgen(x, ws, ds, ps, n_threads=1, max_iters=0):
+    r"""General ND TV prox with one 1D TV-L1 term per entry of (ws, ds, ps)   (prox_tv/__init__.py:533-600).
+
+    Dispatch follows the reference, including its quirks: the DR2_TV branch of the reference is dead code
+    (``len(ds) == 2 & ds[0] == 1 & ds[1] == 2`` is always False, :585), so two terms go to PD2_TV and anything else to
+    PD_TV.  PD_TV scales the caller's ``ws`` by ``len(ws)`` IN PLACE when ``ws`` is a float64 ndarray (:576 does not
+    copy in that case; src/TVNDopt.cpp:100-101).  Only p = 1 norms are implemented on the GPU path.
+    Extension: a float32 ``x`` is solved in float32 (the reference would upcast) when ``len(ws) != 2``.
+    """
+    assert len(ws) == len(ds)
+    assert len(ws) == len(ps)
+    assert n_threads >= 1
+    assert max_iters >= 0
+    info = np.zeros(_N_INFO)
+    f32 = isinstance(x, np.ndarray) and x.dtype == np.float32 and len(ws) != 2
+    x = np.asfortranarray(x, dtype="float32" if f32 else "float64")
+    ws = force_float_matrix(ws)
+    ps = force_float_matrix(ps)
+    y = np.zeros(np.shape(x), order="F", dtype=x.dtype)
+    if np.any(ps != 1):
+        raise NotImplementedError("proxtv_b200 implements TV-L1 (p = 1) penalty terms only")
+    lib = require_device()
+    dsa = np.array(ds, dtype=np.float64)
+    ns = np.array(x.shape, dtype=np.int32)
+    if len(ws) == 2:
+        ok = lib.PD2_TV(_ptr(x), _ptr(ws), _ptr(ps), _ptr(dsa), _ptr(y), _ptr(info), _ptr(ns), x.ndim, 2,
+                        int(n_threads), int(max_iters))
+    elif f32:
+        ok = lib.proxtv_PD_TV_f32(_ptr(x), _ptr(ws), _ptr(dsa), _ptr(y), _ptr(info), _ptr(ns), x.ndim, len(ws),
+                                  int(max_iters))
+    else:
+        ok = lib.PD_TV(_ptr(x), _ptr(ws), _ptr(ps), _ptr(dsa), _ptr(y), _ptr(info), _ptr(ns), x.ndim, len(ws),
+                       int(n_threads), int(max_iters))
+    _check(ok and info[2] != 3, "tvgen")
+    tvgen.last_info = info
+    return y
+
+
+tvgen.last_info = None

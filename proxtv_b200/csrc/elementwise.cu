@@ -1,0 +1,179 @@
+// elementwise.cu -- streaming helpers of the outer loops (unfused forms; the chunked kernels fuse most of these).
+//
+// Arithmetic is written in the reference's operation order so that, given identical prox outputs, every intermediate is
+// bit-identical to the reference's (src/TV2Dopt.cpp:390-430, :212-277; src/TVNDopt.cpp:212-227).  The only exception is
+// the two sums (image mean, stop criterion), which are tree reductions with a fixed, deterministic order instead of the
+// reference's serial / OpenMP-reduction order.
+#include "ptv_internal.h"
+
+namespace ptv {
+
+static inline unsigned grid_for(long long n, int threads, int per_thread = 4) {
+    long long b = (n + (long long)threads * per_thread - 1) / ((long long)threads * per_thread);
+    if (b < 1) b = 1;
+    if (b > 148LL * 32) b = 148LL * 32;
+    return (unsigned)b;
+}
+
+__device__ __forceinline__ double block_sum(double v) {
+    __shared__ double sm[32];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) sm[w] = v;
+    __syncthreads();
+    int nw = (blockDim.x + 31) >> 5;
+    v = (threadIdx.x < nw) ? sm[threadIdx.x] : 0.0;
+    if (w == 0) for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    __syncthreads();
+    return v;   // valid in thread 0
+}
+
+// ---- per-image 2*mean (DR initialisation, src/TV2Dopt.cpp:390-395) ----
+template <typename T>
+__global__ void k_image_partial(const T* __restrict__ Y, long long per_image, double* __restrict__ partial) {
+    const T* img = Y + (long long)blockIdx.y * per_image;
+    double acc = 0;
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < per_image; q += (long long)gridDim.x * blockDim.x)
+        acc += (double)img[q];
+    acc = block_sum(acc);
+    if (threadIdx.x == 0) partial[(long long)blockIdx.y * gridDim.x + blockIdx.x] = acc;
+}
+template <typename T>
+__global__ void k_image_fill(T* __restrict__ t, long long per_image, const double* __restrict__ partial, int nblk) {
+    __shared__ double mean2;
+    double acc = 0;
+    for (int q = threadIdx.x; q < nblk; q += blockDim.x) acc += partial[(long long)blockIdx.y * nblk + q];
+    acc = block_sum(acc);
+    if (threadIdx.x == 0) mean2 = 2 * acc / (double)per_image;
+    __syncthreads();
+    T v = (T)mean2;
+    T* img = t + (long long)blockIdx.y * per_image;
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < per_image; q += (long long)gridDim.x * blockDim.x)
+        img[q] = v;
+}
+template <typename T>
+cudaError_t ew_image_means_x2(const T* Y, long long per_image, int batch, T* t, double* scratch, cudaStream_t st) {
+    KernelSpan span(KC_ELEMENTWISE, 2 * ((batch + 0) > 0 ? 1 : 0), st);
+    int nblk = (int)grid_for(per_image, 256, 8);
+    if (nblk > REDUCE_BLOCKS) nblk = REDUCE_BLOCKS;
+    // scratch holds REDUCE_BLOCKS doubles: split them between the images of one launch
+    int share = REDUCE_BLOCKS / (batch < REDUCE_BLOCKS ? batch : REDUCE_BLOCKS);
+    if (nblk > share) nblk = share < 1 ? 1 : share;
+    int per_launch = REDUCE_BLOCKS / nblk; if (per_launch < 1) per_launch = 1;
+    for (int b0 = 0; b0 < batch; b0 += per_launch) {
+        int nb = batch - b0 < per_launch ? batch - b0 : per_launch;
+        dim3 g(nblk, nb);
+        k_image_partial<T><<<g, 256, 0, st>>>(Y + (long long)b0 * per_image, per_image, scratch);
+        k_image_fill<T><<<g, 256, 0, st>>>(t + (long long)b0 * per_image, per_image, scratch, nblk);
+    }
+    return cudaGetLastError();
+}
+
+// ---- Douglas-Rachford elementwise steps ----
+template <typename T> __global__ void k_dr_reflect_cols(const T* __restrict__ t, const T* __restrict__ x, T* __restrict__ s, long long n) {
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (long long)gridDim.x * blockDim.x) {
+        T d = t[q] - x[q];                 // DR_proxDiff: in - prox(in)            (:545-546)
+        s[q] = T(2) * d - t[q];            // reflection                            (:411)
+    }
+}
+template <typename T> __global__ void k_dr_combine_rows(const T* __restrict__ Y, const T* __restrict__ s, const T* __restrict__ x,
+                                                       T* __restrict__ t, long long n) {
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (long long)gridDim.x * blockDim.x) {
+        T in = Y[q] - s[q];                // :515
+        T tb = Y[q] - (in - x[q]);         // :520 with :546
+        tb = T(2) * tb - s[q];             // :419
+        t[q] = T(0.5) * (t[q] + tb);       // :422
+    }
+}
+template <typename T> __global__ void k_dr_final_cols(const T* __restrict__ t, const T* __restrict__ x, T* __restrict__ s, long long n) {
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (long long)gridDim.x * blockDim.x)
+        s[q] = t[q] - x[q];                // :427
+}
+template <typename T> __global__ void k_dr_final_rows(const T* __restrict__ Y, const T* __restrict__ s, const T* __restrict__ x,
+                                                     T* __restrict__ out, long long n) {
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (long long)gridDim.x * blockDim.x) {
+        T in = Y[q] - s[q];
+        T tb = Y[q] - (in - x[q]);         // :429
+        out[q] = tb - s[q];                // :430
+    }
+}
+template <typename T> __global__ void k_dual_update(T* __restrict__ p, const T* __restrict__ a, const T* __restrict__ b, long long n) {
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (long long)gridDim.x * blockDim.x)
+        p[q] += a[q] - b[q];               // src/TV2Dopt.cpp:213,:263
+}
+
+template <typename T> cudaError_t ew_dr_reflect_cols(const T* t, const T* x, T* s, long long n, cudaStream_t st) {
+    KernelSpan span(KC_ELEMENTWISE, 1, st);
+    k_dr_reflect_cols<T><<<grid_for(n, 256), 256, 0, st>>>(t, x, s, n); return cudaGetLastError(); }
+template <typename T> cudaError_t ew_dr_combine_rows(const T* Y, const T* s, const T* x, T* t, long long n, cudaStream_t st) {
+    KernelSpan span(KC_ELEMENTWISE, 1, st);
+    k_dr_combine_rows<T><<<grid_for(n, 256), 256, 0, st>>>(Y, s, x, t, n); return cudaGetLastError(); }
+template <typename T> cudaError_t ew_dr_final_cols(const T* t, const T* x, T* s, long long n, cudaStream_t st) {
+    KernelSpan span(KC_ELEMENTWISE, 1, st);
+    k_dr_final_cols<T><<<grid_for(n, 256), 256, 0, st>>>(t, x, s, n); return cudaGetLastError(); }
+template <typename T> cudaError_t ew_dr_final_rows(const T* Y, const T* s, const T* x, T* out, long long n, cudaStream_t st) {
+    KernelSpan span(KC_ELEMENTWISE, 1, st);
+    k_dr_final_rows<T><<<grid_for(n, 256), 256, 0, st>>>(Y, s, x, out, n); return cudaGetLastError(); }
+template <typename T> cudaError_t ew_dual_update(T* p, const T* a, const T* b, long long n, cudaStream_t st) {
+    KernelSpan span(KC_ELEMENTWISE, 1, st);
+    k_dual_update<T><<<grid_for(n, 256), 256, 0, st>>>(p, a, b, n); return cudaGetLastError(); }
+
+// ---- stop criterion: mean |a - b|  (src/TV2Dopt.cpp:273-277) ----
+template <typename T> __global__ void k_absdiff_partial(const T* __restrict__ a, const T* __restrict__ b, long long n, double* __restrict__ partial) {
+    double acc = 0;
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (long long)gridDim.x * blockDim.x)
+        acc += fabs((double)a[q] - (double)b[q]);
+    acc = block_sum(acc);
+    if (threadIdx.x == 0) partial[blockIdx.x] = acc;
+}
+__global__ void k_final_mean(const double* __restrict__ partial, int nblk, long long n, double* __restrict__ result) {
+    double acc = 0;
+    for (int q = threadIdx.x; q < nblk; q += blockDim.x) acc += partial[q];
+    acc = block_sum(acc);
+    if (threadIdx.x == 0) *result = acc / (double)n;
+}
+template <typename T> cudaError_t ew_mean_abs_diff(const T* a, const T* b, long long n, double* scratch, double* result, cudaStream_t st) {
+    KernelSpan span(KC_ELEMENTWISE, 2, st);
+    int nblk = (int)grid_for(n, 256, 8); if (nblk > REDUCE_BLOCKS) nblk = REDUCE_BLOCKS;
+    k_absdiff_partial<T><<<nblk, 256, 0, st>>>(a, b, n, scratch);
+    k_final_mean<<<1, 256, 0, st>>>(scratch, nblk, n, result);
+    return cudaGetLastError();
+}
+
+// ---- parallel proximal Dykstra combine (src/TVNDopt.cpp:212-227): x = sum_i p_i/k ; z_i += x - p_i ; stop = mean|x - x_old| ----
+template <typename T> __global__ void k_pd_combine(T* const* __restrict__ p, T* const* __restrict__ z, int k, T* __restrict__ x,
+                                                  long long n, double* __restrict__ partial) {
+    double acc = 0;
+    const T kk = (T)k;
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (long long)gridDim.x * blockDim.x) {
+        T xo = x[q], xn = T(0);
+        for (int i = 0; i < k; i++) xn += p[i][q] / kk;
+        for (int i = 0; i < k; i++) z[i][q] += xn - p[i][q];
+        x[q] = xn;
+        acc += fabs((double)xn - (double)xo);
+    }
+    acc = block_sum(acc);
+    if (threadIdx.x == 0) partial[blockIdx.x] = acc;
+}
+template <typename T> cudaError_t ew_pd_combine(T* const* p, T* const* z, int k, T* x, long long n, double* scratch, double* result,
+                                                cudaStream_t st) {
+    KernelSpan span(KC_ELEMENTWISE, 2, st);
+    int nblk = (int)grid_for(n, 256, 4); if (nblk > REDUCE_BLOCKS) nblk = REDUCE_BLOCKS;
+    k_pd_combine<T><<<nblk, 256, 0, st>>>(p, z, k, x, n, scratch);
+    k_final_mean<<<1, 256, 0, st>>>(scratch, nblk, n, result);
+    return cudaGetLastError();
+}
+
+#define INST(T) \
+    template cudaError_t ew_image_means_x2<T>(const T*, long long, int, T*, double*, cudaStream_t); \
+    template cudaError_t ew_dr_reflect_cols<T>(const T*, const T*, T*, long long, cudaStream_t); \
+    template cudaError_t ew_dr_combine_rows<T>(const T*, const T*, const T*, T*, long long, cudaStream_t); \
+    template cudaError_t ew_dr_final_cols<T>(const T*, const T*, T*, long long, cudaStream_t); \
+    template cudaError_t ew_dr_final_rows<T>(const T*, const T*, const T*, T*, long long, cudaStream_t); \
+    template cudaError_t ew_dual_update<T>(T*, const T*, const T*, long long, cudaStream_t); \
+    template cudaError_t ew_mean_abs_diff<T>(const T*, const T*, long long, double*, double*, cudaStream_t); \
+    template cudaError_t ew_pd_combine<T>(T* const*, T* const*, int, T*, long long, double*, double*, cudaStream_t);
+INST(double)
+INST(float)
+
+}  // namespace ptv

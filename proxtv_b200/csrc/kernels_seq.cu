@@ -1,0 +1,65 @@
+// kernels_seq.cu -- robust baseline: one lane runs the whole sequential scan of one fiber.
+//
+// Works for any fiber length, stride and weight; used for tiny problems, as the repair path for fibers the chunked
+// kernels flag, and as the on-device cross-check of the fast kernels.  With adjacent lanes on adjacent fibers the
+// strided direction (inc > 1) is naturally coalesced; contiguous fibers rely on L1 (each lane streams its own lines).
+// Reference behaviour: TV() with p == 1 applied to each fiber (src/TVgenopt.cpp:41-47, src/TVNDopt.cpp:182-207).
+#include "ptv_internal.h"
+#include "taut_scan.cuh"
+
+namespace ptv {
+
+template <typename T, bool WEIGHTED>
+__global__ void __launch_bounds__(32) k_prox_seq(const T* __restrict__ A, const T* __restrict__ B, int op, T* __restrict__ X,
+                                                 FiberGeom g, T lam, const T* __restrict__ lamv,
+                                                 const int* __restrict__ list, long long nlist) {
+    long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (list) { if (j >= nlist) return; j = list[j]; }
+    else if (j >= g.nf) return;
+    const int n = g.len;
+    const long long inc = g.inc;
+    const long long base = (j / inc) * inc * n + (j % inc);
+    const long long wbase = (j / inc) * inc * (n - 1) + (j % inc);
+    auto y = [&](int i) -> T {
+        long long o = base + (long long)i * inc;
+        T a = A[o];
+        return op == IN_A ? a : (op == IN_A_MINUS_B ? a - B[o] : a + B[o]);
+    };
+    auto run = [&](auto lamf) {
+        Scan<T> s;
+        s.begin(0, y, lamf);
+        int f, l; T v;
+        while (s.i < n) {
+            int k = s.step(n, y, lamf, f, l, v);
+            if (k != K_NONE)
+                for (int q = f; q <= l; q++) X[base + (long long)q * inc] = v;
+        }
+        for (int q = s.last + 1; q < n; q++) X[base + (long long)q * inc] = s.lo;
+    };
+    if (n <= 0) return;
+    if (WEIGHTED) {
+        if (n == 1) { X[base] = y(0); return; }     // the reference reads lambda[0] out of bounds here; identity is the limit
+        auto ld = [&](int i) -> T { return lamv[wbase + (long long)i * inc]; };
+        run(ArrayLam<T, decltype(ld)>{ld});
+    } else {
+        run(UniformLam<T>{lam});
+    }
+}
+
+template <typename T>
+cudaError_t prox_fibers_seq(const T* A, const T* B, InOp op, T* X, FiberGeom g, T lam, const T* lamv, const int* list,
+                            long long nlist, cudaStream_t st) {
+    long long cnt = list ? nlist : g.nf;
+    if (cnt <= 0 || g.len <= 0) return cudaSuccess;
+    unsigned blocks = (unsigned)((cnt + 31) / 32);
+    if (lamv) k_prox_seq<T, true><<<blocks, 32, 0, st>>>(A, B, (int)op, X, g, lam, lamv, list, nlist);
+    else      k_prox_seq<T, false><<<blocks, 32, 0, st>>>(A, B, (int)op, X, g, lam, lamv, list, nlist);
+    return cudaGetLastError();
+}
+
+template cudaError_t prox_fibers_seq<double>(const double*, const double*, InOp, double*, FiberGeom, double, const double*,
+                                             const int*, long long, cudaStream_t);
+template cudaError_t prox_fibers_seq<float>(const float*, const float*, InOp, float*, FiberGeom, float, const float*,
+                                            const int*, long long, cudaStream_t);
+
+}  // namespace ptv

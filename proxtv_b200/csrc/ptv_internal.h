@@ -1,0 +1,76 @@
+// ptv_internal.h -- internal host-side declarations shared by the CUDA translation units of libproxtv_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace ptv {
+
+// Return codes and info slots of the reference (src/general.h:58-73).
+enum { INFO_ITERS = 0, INFO_GAP = 1, INFO_RC = 2 };
+enum { RC_OK = 0, RC_ITERS = 1, RC_STUCK = 2, RC_ERROR = 3 };
+constexpr double STOP_PD = 1e-6;       // src/TVopt.h:71
+constexpr int MAX_ITERS_PD = 35;       // src/TVopt.h:73
+constexpr int MAX_ITERS_DR = 35;       // src/TVopt.h:83
+
+// The set of 1D fibers of a column-major array along one dimension (src/TVNDopt.cpp:133-138,184-188):
+// fiber j starts at (j / inc) * inc * len + (j % inc) and its elements are `inc` apart.  A leading batch of arrays is
+// simply one more (slowest) dimension.
+struct FiberGeom {
+    long long nf;    // number of fibers
+    int len;         // samples per fiber
+    long long inc;   // element stride inside a fiber (1 = contiguous fibers)
+};
+
+// How a fiber's input is formed from up to two arrays, and what is written back (fused DR / Dykstra arithmetic).
+enum InOp { IN_A = 0, IN_A_MINUS_B = 1, IN_A_PLUS_B = 2 };
+
+// Which kernel family prox_fibers() may use.
+enum Engine { ENGINE_AUTO = 0, ENGINE_SEQ = 1, ENGINE_CHUNKED = 2 };
+
+struct ProxStats {           // filled asynchronously on the device; optional
+    unsigned long long fallback_fibers;
+};
+
+// x = prox_{lam * TV}(in) for every fiber.  lamv == nullptr: uniform weight lam; else per-edge weights, laid out like the
+// fibers but with len-1 samples per fiber.  All pointers are device pointers.  Returns cudaGetLastError().
+template <typename T>
+cudaError_t prox_fibers(const T* A, const T* B, InOp op, T* X, FiberGeom g, T lam, const T* lamv, Engine eng,
+                        cudaStream_t st);
+
+// ---- launch accounting / event timing (profile.cu) ----
+enum KernelClass { KC_PROX_CONTIG = 0, KC_PROX_STRIDED = 1, KC_ELEMENTWISE = 2, KC_COUNT = 3 };
+struct KernelSpan {          // RAII: counts `nkernels` launches of class cls; when profiling is on, brackets them with events
+    int cls; cudaStream_t st; cudaEvent_t a;
+    KernelSpan(int cls, int nkernels, cudaStream_t st);
+    ~KernelSpan();
+};
+void profile_enable(int on);
+void profile_reset();
+void profile_read(double* ms, long long* launches, long long* spans);   // arrays of KC_COUNT
+
+// ---- elementwise helpers (elementwise.cu) ----
+template <typename T> cudaError_t ew_image_means_x2(const T* Y, long long per_image, int batch, T* t, double* scratch,
+                                                    cudaStream_t st);                 // t[b,:] = 2*mean(Y[b,:])
+template <typename T> cudaError_t ew_dr_reflect_cols(const T* t, const T* x, T* s, long long n, cudaStream_t st);
+template <typename T> cudaError_t ew_dr_combine_rows(const T* Y, const T* s, const T* x, T* t, long long n, cudaStream_t st);
+template <typename T> cudaError_t ew_dr_final_cols(const T* t, const T* x, T* s, long long n, cudaStream_t st);
+template <typename T> cudaError_t ew_dr_final_rows(const T* Y, const T* s, const T* x, T* out, long long n, cudaStream_t st);
+template <typename T> cudaError_t ew_dual_update(T* p, const T* a, const T* b, long long n, cudaStream_t st);  // p += a - b
+template <typename T> cudaError_t ew_mean_abs_diff(const T* a, const T* b, long long n, double* scratch, double* result,
+                                                   cudaStream_t st);                  // *result = mean|a-b| (device)
+template <typename T> cudaError_t ew_pd_combine(T* const* p, T* const* z, int k, T* x, long long n, double* scratch,
+                                                double* result, cudaStream_t st);
+constexpr int REDUCE_BLOCKS = 1184;    // 148 SMs x 8; partial sums are combined in a fixed order (deterministic)
+
+// ---- device-resident solvers (solver.cu).  All arrays are device pointers; `ws` must hold ws_bytes_*() bytes. ----
+template <typename T> size_t ws_bytes_dr2(size_t M, size_t N, int batch);
+template <typename T> int dr2_device(size_t M, size_t N, int batch, int row_major, const T* Y, T w1, T w2, T* out, int maxit, double* info,
+                                     void* ws, Engine eng, cudaStream_t st);
+template <typename T> size_t ws_bytes_pd(long long n, int npen);
+template <typename T> int pd2_device(const T* y, const double* lambdas, const double* dims, T* x, double* info, const int* ns,
+                                     int nds, int npen, int maxIters, void* ws, Engine eng, cudaStream_t st);
+template <typename T> int pd_device(const T* y, const double* lambdas_scaled, const double* dims, T* x, double* info,
+                                    const int* ns, int nds, int npen, int maxIters, void* ws, Engine eng, cudaStream_t st);
+
+}  // namespace ptv

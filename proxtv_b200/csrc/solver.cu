@@ -1,0 +1,163 @@
+// solver.cu -- device-resident outer loops: Douglas-Rachford (DR2_TV) and proximal Dykstra (PD2_TV, PD_TV).
+//
+// Semantics follow the reference exactly (same initialisation, pass order, iteration structure, stop test and info[]):
+//   DR2_TV  src/TV2Dopt.cpp:352-444     PD2_TV  src/TV2Dopt.cpp:59-302     PD_TV  src/TVNDopt.cpp:48-252
+// The reference's fixed 35 DR iterations are NOT a converged solve and the result depends on the pass order, so nothing
+// here may be "improved" (SURVEY.md section 0.3).  All arrays stay in HBM for the whole solve; the only host round trip
+// is the 8-byte stop criterion of the Dykstra loops, once per iteration.
+#include "ptv_internal.h"
+#include <float.h>
+#include <stdio.h>
+
+namespace ptv {
+
+static inline size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
+static constexpr size_t SCRATCH_BYTES = (REDUCE_BLOCKS + 8) * sizeof(double);
+
+#define PTV_TRY(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { \
+    fprintf(stderr, "proxtv_b200: CUDA error %s at %s:%d\n", cudaGetErrorString(e__), __FILE__, __LINE__); \
+    if (info) info[INFO_RC] = RC_ERROR; return 0; } } while (0)
+
+// ------------------------------------------------------------------------------------------------------------------
+template <typename T> size_t ws_bytes_dr2(size_t M, size_t N, int batch) {
+    size_t n = M * N * (size_t)batch;
+    return 3 * align256(n * sizeof(T)) + SCRATCH_BYTES;
+}
+
+template <typename T>
+int dr2_device(size_t M, size_t N, int batch, int row_major, const T* Y, T w1, T w2, T* out, int maxit, double* info, void* ws,
+               Engine eng, cudaStream_t st) {
+    const long long n = (long long)M * (long long)N * batch;
+    if (n == 0) { if (info) { info[INFO_ITERS] = 0; info[INFO_RC] = RC_OK; } return 0; }
+    char* w = (char*)ws;
+    T* t = (T*)w; w += align256(n * sizeof(T));
+    T* s = (T*)w; w += align256(n * sizeof(T));
+    T* x = (T*)w; w += align256(n * sizeof(T));
+    double* scratch = (double*)w;
+    if (maxit <= 0) maxit = MAX_ITERS_DR;                                     // TV2Dopt.cpp:387
+    // first pass: fibers along axis 0 (length M); second pass: along axis 1 (length N) -- the order is part of the contract.
+    // column-major: axis-0 fibers are contiguous, axis-1 fibers have stride M; row-major storage swaps the two roles.
+    const FiberGeom gc = row_major ? FiberGeom{(long long)N * batch, (int)M, (long long)N} : FiberGeom{(long long)N * batch, (int)M, 1};
+    const FiberGeom gr = row_major ? FiberGeom{(long long)M * batch, (int)N, 1} : FiberGeom{(long long)M * batch, (int)N, (long long)M};
+    PTV_TRY(ew_image_means_x2<T>(Y, (long long)M * N, batch, t, scratch, st));        // :390-395
+    for (int it = 0; it < maxit; it++) {                                      // :403-423
+        PTV_TRY(prox_fibers<T>(t, nullptr, IN_A, x, gc, w1, nullptr, eng, st));
+        PTV_TRY(ew_dr_reflect_cols<T>(t, x, s, n, st));
+        PTV_TRY(prox_fibers<T>(Y, s, IN_A_MINUS_B, x, gr, w2, nullptr, eng, st));
+        PTV_TRY(ew_dr_combine_rows<T>(Y, s, x, t, n, st));
+    }
+    PTV_TRY(prox_fibers<T>(t, nullptr, IN_A, x, gc, w1, nullptr, eng, st));   // :427-430
+    PTV_TRY(ew_dr_final_cols<T>(t, x, s, n, st));
+    PTV_TRY(prox_fibers<T>(Y, s, IN_A_MINUS_B, x, gr, w2, nullptr, eng, st));
+    PTV_TRY(ew_dr_final_rows<T>(Y, s, x, out, n, st));
+    if (info) { info[INFO_ITERS] = maxit; info[INFO_RC] = RC_OK; }            // :433-436 (INFO_GAP is left untouched)
+    return 0;                                                                 // :440 (the reference returns 0 on success)
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+template <typename T> size_t ws_bytes_pd(long long n, int npen) {
+    int arrays = 2 * npen + 2;   // PD_TV: p_i, z_i ; PD2_TV (npen <= 2): p, q, z, xl  -> 4 <= 2*2+2
+    if (arrays < 4) arrays = 4;
+    return (size_t)arrays * align256((size_t)n * sizeof(T)) + SCRATCH_BYTES + align256(2 * 64 * sizeof(void*));
+}
+
+static bool geom_of(const int* ns, int nds, double dim, long long n, FiberGeom* g) {
+    int d = (int)(dim - 1);                                                   // TV2Dopt.cpp:171, TVNDopt.cpp:175
+    if (d < 0 || d >= nds) return false;
+    long long inc = 1;
+    for (int i = 0; i < d; i++) inc *= ns[i];                                 // TVNDopt.cpp:133-138
+    g->len = ns[d]; g->inc = inc; g->nf = ns[d] ? n / ns[d] : 0;
+    return true;
+}
+
+static int read_stop(const double* dres, double* stop, cudaStream_t st) {
+    cudaError_t e = cudaMemcpyAsync(stop, dres, sizeof(double), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    return e == cudaSuccess;
+}
+
+template <typename T>
+int pd2_device(const T* y, const double* lambdas, const double* dims, T* x, double* info, const int* ns, int nds, int npen,
+               int maxIters, void* ws, Engine eng, cudaStream_t st) {
+    if (npen > 2) { printf("PD2_TV: this algorithm can not work with more than 2 penalties\n");      // :95-96
+                    if (info) info[INFO_RC] = RC_ERROR; return 0; }
+    long long n = 1; for (int i = 0; i < nds; i++) n *= ns[i];
+    if (maxIters <= 0) maxIters = MAX_ITERS_PD;
+    FiberGeom g0{0, 0, 1}, g1{0, 0, 1};
+    if (npen < 1 || !geom_of(ns, nds, dims[0], n, &g0) || (npen >= 2 && !geom_of(ns, nds, dims[1], n, &g1))) {
+        printf("PD2_TV: invalid penalty dimensions\n"); if (info) info[INFO_RC] = RC_ERROR; return 0; }
+    double stop = DBL_MAX; int iters = 0;
+    if (n > 0) {
+        char* w = (char*)ws; const size_t ab = align256((size_t)n * sizeof(T));
+        T* p = (T*)w; w += ab; T* q = (T*)w; w += ab; T* z = (T*)w; w += ab; T* xl = (T*)w; w += ab;
+        double* scratch = (double*)w; double* dres = scratch + REDUCE_BLOCKS;
+        PTV_TRY(cudaMemcpyAsync(x, y, (size_t)n * sizeof(T), cudaMemcpyDeviceToDevice, st));          // :132-137
+        PTV_TRY(cudaMemsetAsync(p, 0, (size_t)n * sizeof(T), st));
+        PTV_TRY(cudaMemsetAsync(q, 0, (size_t)n * sizeof(T), st));
+        while (stop > STOP_PD && (npen > 1 || !iters) && iters < maxIters) {                           // :157
+            PTV_TRY(cudaMemcpyAsync(xl, x, (size_t)n * sizeof(T), cudaMemcpyDeviceToDevice, st));
+            PTV_TRY(prox_fibers<T>(x, p, IN_A_PLUS_B, z, g0, (T)lambdas[0], nullptr, eng, st));       // :171-208
+            PTV_TRY(ew_dual_update<T>(p, x, z, n, st));                                               // :211-213
+            if (npen >= 2) {
+                PTV_TRY(prox_fibers<T>(z, q, IN_A_PLUS_B, x, g1, (T)lambdas[1], nullptr, eng, st));   // :216-258
+                PTV_TRY(ew_dual_update<T>(q, z, x, n, st));                                           // :261-263
+            } else {
+                PTV_TRY(cudaMemcpyAsync(x, z, (size_t)n * sizeof(T), cudaMemcpyDeviceToDevice, st));  // :266-269
+            }
+            PTV_TRY(ew_mean_abs_diff<T>(x, xl, n, scratch, dres, st));                                // :273-277
+            if (!read_stop(dres, &stop, st)) { PTV_TRY(cudaGetLastError()); PTV_TRY(cudaErrorUnknown); }
+            iters++;
+        }
+    }
+    if (info) { info[INFO_ITERS] = iters; info[INFO_GAP] = stop;
+                info[INFO_RC] = iters >= MAX_ITERS_PD ? RC_ITERS : RC_OK; }                           // :283-295
+    return 1;
+}
+
+template <typename T>
+int pd_device(const T* y, const double* lam, const double* dims, T* x, double* info, const int* ns, int nds, int npen,
+              int maxIters, void* ws, Engine eng, cudaStream_t st) {
+    long long n = 1; for (int i = 0; i < nds; i++) n *= ns[i];
+    if (maxIters <= 0) maxIters = MAX_ITERS_PD;
+    if (npen > 64) { printf("PD_TV: more than 64 penalty terms are not supported\n"); if (info) info[INFO_RC] = RC_ERROR; return 0; }
+    FiberGeom g[64];
+    for (int i = 0; i < npen; i++)
+        if (!geom_of(ns, nds, dims[i], n, &g[i])) { printf("PD_TV: invalid penalty dimensions\n");
+                                                     if (info) info[INFO_RC] = RC_ERROR; return 0; }
+    double stop = DBL_MAX; int iters = 0;
+    if (n > 0 && npen > 0) {
+        char* w = (char*)ws; const size_t ab = align256((size_t)n * sizeof(T));
+        T* hp[64]; T* hz[64];
+        for (int i = 0; i < npen; i++) { hp[i] = (T*)w; w += ab; hz[i] = (T*)w; w += ab; }
+        double* scratch = (double*)w; double* dres = scratch + REDUCE_BLOCKS; w += SCRATCH_BYTES;
+        T** dp = (T**)w; T** dz = dp + 64;
+        PTV_TRY(cudaMemcpyAsync(dp, hp, sizeof(T*) * npen, cudaMemcpyHostToDevice, st));
+        PTV_TRY(cudaMemcpyAsync(dz, hz, sizeof(T*) * npen, cudaMemcpyHostToDevice, st));
+        PTV_TRY(cudaStreamSynchronize(st));    // hp/hz are stack arrays
+        PTV_TRY(cudaMemsetAsync(x, 0, (size_t)n * sizeof(T), st));                                    // :125-130
+        for (int i = 0; i < npen; i++) PTV_TRY(cudaMemcpyAsync(hz[i], y, (size_t)n * sizeof(T), cudaMemcpyDeviceToDevice, st));
+        while (stop > STOP_PD && iters < maxIters) {                                                  // :151
+            for (int i = 0; i < npen; i++)
+                PTV_TRY(prox_fibers<T>(hz[i], nullptr, IN_A, hp[i], g[i], (T)lam[i], nullptr, eng, st));  // :171-208
+            PTV_TRY(ew_pd_combine<T>(dp, dz, npen, x, n, scratch, dres, st));                         // :212-227
+            if (!read_stop(dres, &stop, st)) { PTV_TRY(cudaGetLastError()); PTV_TRY(cudaErrorUnknown); }
+            iters++;
+        }
+    } else if (n > 0) {
+        PTV_TRY(cudaMemsetAsync(x, 0, (size_t)n * sizeof(T), st));
+    }
+    if (info) { info[INFO_ITERS] = iters; info[INFO_GAP] = stop;
+                info[INFO_RC] = iters >= MAX_ITERS_PD ? RC_ITERS : RC_OK; }                           // :233-245
+    return 1;
+}
+
+#define INST(T) \
+    template size_t ws_bytes_dr2<T>(size_t, size_t, int); \
+    template int dr2_device<T>(size_t, size_t, int, int, const T*, T, T, T*, int, double*, void*, Engine, cudaStream_t); \
+    template size_t ws_bytes_pd<T>(long long, int); \
+    template int pd2_device<T>(const T*, const double*, const double*, T*, double*, const int*, int, int, int, void*, Engine, cudaStream_t); \
+    template int pd_device<T>(const T*, const double*, const double*, T*, double*, const int*, int, int, int, void*, Engine, cudaStream_t);
+INST(double)
+INST(float)
+
+}  // namespace ptv
