@@ -63,13 +63,14 @@ int host_prox_fibers(const char* fn, const T* in, T* out, long long nf, int len,
     std::lock_guard<std::mutex> lk(g_mu);
     const size_t n = (size_t)nf * len, nw = lamv ? (size_t)nf * (len - 1) : 0;
     char* d = (char*)g_io.get(2 * al(n * sizeof(T)) + al(nw * sizeof(T) + 8));
+    T* scr = (inc != 1) ? (T*)g_ws.get(2 * al(n * sizeof(T))) : nullptr;
     if (!d) return fail(fn, "out of device memory", nullptr) ? 1 : 0;
     T* din = (T*)d; T* dout = (T*)(d + al(n * sizeof(T))); T* dw = (T*)(d + 2 * al(n * sizeof(T)));
     cudaStream_t st = 0;
     if (!cuda_ok(fn, cudaMemcpyAsync(din, in, n * sizeof(T), cudaMemcpyHostToDevice, st), nullptr)) return 0;
     if (nw && !cuda_ok(fn, cudaMemcpyAsync(dw, lamv, nw * sizeof(T), cudaMemcpyHostToDevice, st), nullptr)) return 0;
     FiberGeom g{nf, len, inc};
-    if (!cuda_ok(fn, prox_fibers<T>(din, nullptr, IN_A, dout, g, lam, lamv ? dw : nullptr, (Engine)g_engine, st), nullptr)) return 0;
+    if (!cuda_ok(fn, prox_fibers<T>(din, nullptr, IN_A, dout, 0, g, lam, lamv ? dw : nullptr, (Engine)g_engine, scr, st), nullptr)) return 0;
     if (!cuda_ok(fn, cudaMemcpyAsync(out, dout, n * sizeof(T), cudaMemcpyDeviceToHost, st), nullptr)) return 0;
     if (!cuda_ok(fn, cudaStreamSynchronize(st), nullptr)) return 0;
     return 1;
@@ -122,6 +123,12 @@ int run_pd(const char* fn, int mode, bool host_io, const T* y, double* lambdas, 
         if (!cuda_ok(fn, cudaStreamSynchronize(st), info)) return 0;
     }
     return 1;
+}
+
+template <typename T> static T* dev_scratch(long long nf, int len, long long inc) {
+    if (inc == 1 || nf <= 0 || len <= 0) return nullptr;
+    std::lock_guard<std::mutex> lk(g_mu);
+    return (T*)g_ws.get(2 * al((size_t)nf * len * sizeof(T)));
 }
 
 template <typename T>
@@ -197,11 +204,11 @@ int PD_TV(double* y, double* lambdas, double* norms, double* dims, double* x, do
 // ---- Part 2: extensions ----
 int proxtv_prox_fibers_dev_f64(const double* in, double* out, long long nf, int len, long long inc, double lam, const double* lamv, void* stream) {
     if (!have_device("proxtv_prox_fibers_dev_f64", nullptr)) return 0;
-    return cuda_ok("proxtv_prox_fibers_dev_f64", prox_fibers<double>(in, nullptr, IN_A, out, FiberGeom{nf, len, inc}, lam, lamv, (Engine)g_engine, (cudaStream_t)stream), nullptr);
+    return cuda_ok("proxtv_prox_fibers_dev_f64", prox_fibers<double>(in, nullptr, IN_A, out, 0, FiberGeom{nf, len, inc}, lam, lamv, (Engine)g_engine, dev_scratch<double>(nf, len, inc), (cudaStream_t)stream), nullptr);
 }
 int proxtv_prox_fibers_dev_f32(const float* in, float* out, long long nf, int len, long long inc, float lam, const float* lamv, void* stream) {
     if (!have_device("proxtv_prox_fibers_dev_f32", nullptr)) return 0;
-    return cuda_ok("proxtv_prox_fibers_dev_f32", prox_fibers<float>(in, nullptr, IN_A, out, FiberGeom{nf, len, inc}, lam, lamv, (Engine)g_engine, (cudaStream_t)stream), nullptr);
+    return cuda_ok("proxtv_prox_fibers_dev_f32", prox_fibers<float>(in, nullptr, IN_A, out, 0, FiberGeom{nf, len, inc}, lam, lamv, (Engine)g_engine, dev_scratch<float>(nf, len, inc), (cudaStream_t)stream), nullptr);
 }
 int proxtv_prox_fibers_f64(const double* in, double* out, long long nf, int len, long long inc, double lam, const double* lamv) {
     return host_prox_fibers<double>("proxtv_prox_fibers_f64", in, out, nf, len, inc, lam, lamv);

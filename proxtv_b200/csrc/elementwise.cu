@@ -118,6 +118,21 @@ template <typename T> cudaError_t ew_dual_update(T* p, const T* a, const T* b, l
     KernelSpan span(KC_ELEMENTWISE, 1, st);
     k_dual_update<T><<<grid_for(n, 256), 256, 0, st>>>(p, a, b, n); return cudaGetLastError(); }
 
+// ---- first DR pass on a constant image: s = 2 (t - x1[image][k]) - t, k = position of the sample along its axis-0 fiber ----
+template <typename T> __global__ void k_dr_reflect_bcast(const T* __restrict__ t, const T* __restrict__ x1, T* __restrict__ s, long long n,
+                                                        long long per_image, int len, long long inc) {
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (long long)gridDim.x * blockDim.x) {
+        const long long b = q / per_image, r = q - b * per_image;
+        const int k = (int)((r / inc) % len);
+        const T d = t[q] - x1[b * len + k];
+        s[q] = T(2) * d - t[q];
+    }
+}
+template <typename T> cudaError_t ew_dr_reflect_bcast(const T* t, const T* x1, T* s, long long n, long long per_image, int len,
+                                                      long long inc, cudaStream_t st) {
+    KernelSpan span(KC_ELEMENTWISE, 1, st);
+    k_dr_reflect_bcast<T><<<grid_for(n, 256), 256, 0, st>>>(t, x1, s, n, per_image, len, inc); return cudaGetLastError(); }
+
 // ---- stop criterion: mean |a - b|  (src/TV2Dopt.cpp:273-277) ----
 template <typename T> __global__ void k_absdiff_partial(const T* __restrict__ a, const T* __restrict__ b, long long n, double* __restrict__ partial) {
     double acc = 0;
@@ -171,6 +186,7 @@ template <typename T> cudaError_t ew_pd_combine(T* const* p, T* const* z, int k,
     template cudaError_t ew_dr_final_cols<T>(const T*, const T*, T*, long long, cudaStream_t); \
     template cudaError_t ew_dr_final_rows<T>(const T*, const T*, const T*, T*, long long, cudaStream_t); \
     template cudaError_t ew_dual_update<T>(T*, const T*, const T*, long long, cudaStream_t); \
+    template cudaError_t ew_dr_reflect_bcast<T>(const T*, const T*, T*, long long, long long, int, long long, cudaStream_t); \
     template cudaError_t ew_mean_abs_diff<T>(const T*, const T*, long long, double*, double*, cudaStream_t); \
     template cudaError_t ew_pd_combine<T>(T* const*, T* const*, int, T*, long long, double*, double*, cudaStream_t);
 INST(double)

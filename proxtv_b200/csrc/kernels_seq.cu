@@ -5,13 +5,13 @@
 // strided direction (inc > 1) is naturally coalesced; contiguous fibers rely on L1 (each lane streams its own lines).
 // Reference behaviour: TV() with p == 1 applied to each fiber (src/TVgenopt.cpp:41-47, src/TVNDopt.cpp:182-207).
 #include "ptv_internal.h"
-#include "taut_scan.cuh"
+#include "chunk_core.cuh"
 
 namespace ptv {
 
 template <typename T, bool WEIGHTED>
 __global__ void __launch_bounds__(32) k_prox_seq(const T* __restrict__ A, const T* __restrict__ B, int op, T* __restrict__ X,
-                                                 FiberGeom g, T lam, const T* __restrict__ lamv,
+                                                 int out_op, FiberGeom g, T lam, const T* __restrict__ lamv,
                                                  const int* __restrict__ list, long long nlist) {
     long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (list) { if (j >= nlist) return; j = list[j]; }
@@ -32,13 +32,13 @@ __global__ void __launch_bounds__(32) k_prox_seq(const T* __restrict__ A, const 
         while (s.i < n) {
             int k = s.step(n, y, lamf, f, l, v);
             if (k != K_NONE)
-                for (int q = f; q <= l; q++) X[base + (long long)q * inc] = v;
+                for (int q = f; q <= l; q++) X[base + (long long)q * inc] = out_op ? apply_out<T>(out_op, y(q), v) : v;
         }
-        for (int q = s.last + 1; q < n; q++) X[base + (long long)q * inc] = s.lo;
+        for (int q = s.last + 1; q < n; q++) X[base + (long long)q * inc] = out_op ? apply_out<T>(out_op, y(q), s.lo) : s.lo;
     };
     if (n <= 0) return;
     if (WEIGHTED) {
-        if (n == 1) { X[base] = y(0); return; }     // the reference reads lambda[0] out of bounds here; identity is the limit
+        if (n == 1) { X[base] = apply_out<T>(out_op, y(0), y(0)); return; }     // the reference reads lambda[0] out of bounds here; identity is the limit
         auto ld = [&](int i) -> T { return lamv[wbase + (long long)i * inc]; };
         run(ArrayLam<T, decltype(ld)>{ld});
     } else {
@@ -46,20 +46,48 @@ __global__ void __launch_bounds__(32) k_prox_seq(const T* __restrict__ A, const 
     }
 }
 
+// prox of a CONSTANT fiber (all samples equal c[b]) of length n, one thread per fiber, everything in registers.
+// Used for the first Douglas-Rachford pass, whose input is the constant image 2*mean (src/TV2Dopt.cpp:390-395): all fibers
+// of an image are then identical, so one fiber per image is solved and broadcast.  x1: [batch][n].
 template <typename T>
-cudaError_t prox_fibers_seq(const T* A, const T* B, InOp op, T* X, FiberGeom g, T lam, const T* lamv, const int* list,
+__global__ void k_prox_const_fiber(const T* __restrict__ c, long long c_stride, int n, T lam, T* __restrict__ x1) {
+    const long long b = blockIdx.x;
+    const T cv = c[b * c_stride];
+    auto y = [cv](int) -> T { return cv; };
+    UniformLam<T> lamf{lam};
+    T* out = x1 + b * (long long)n;
+    Scan<T> s;
+    s.begin(0, y, lamf);
+    int f, l; T v;
+    while (s.i < n) {
+        int k = s.step(n, y, lamf, f, l, v);
+        if (k != K_NONE) for (int q = f; q <= l; q++) out[q] = v;
+    }
+    for (int q = s.last + 1; q < n; q++) out[q] = s.lo;
+}
+template <typename T>
+cudaError_t prox_const_fibers(const T* c, long long c_stride, int batch, int n, T lam, T* x1, cudaStream_t st) {
+    if (batch <= 0 || n <= 0) return cudaSuccess;
+    k_prox_const_fiber<T><<<batch, 1, 0, st>>>(c, c_stride, n, lam, x1);
+    return cudaGetLastError();
+}
+template cudaError_t prox_const_fibers<double>(const double*, long long, int, int, double, double*, cudaStream_t);
+template cudaError_t prox_const_fibers<float>(const float*, long long, int, int, float, float*, cudaStream_t);
+
+template <typename T>
+cudaError_t prox_fibers_seq(const T* A, const T* B, InOp op, T* X, int out_op, FiberGeom g, T lam, const T* lamv, const int* list,
                             long long nlist, cudaStream_t st) {
     long long cnt = list ? nlist : g.nf;
     if (cnt <= 0 || g.len <= 0) return cudaSuccess;
     unsigned blocks = (unsigned)((cnt + 31) / 32);
-    if (lamv) k_prox_seq<T, true><<<blocks, 32, 0, st>>>(A, B, (int)op, X, g, lam, lamv, list, nlist);
-    else      k_prox_seq<T, false><<<blocks, 32, 0, st>>>(A, B, (int)op, X, g, lam, lamv, list, nlist);
+    if (lamv) k_prox_seq<T, true><<<blocks, 32, 0, st>>>(A, B, (int)op, X, out_op, g, lam, lamv, list, nlist);
+    else      k_prox_seq<T, false><<<blocks, 32, 0, st>>>(A, B, (int)op, X, out_op, g, lam, lamv, list, nlist);
     return cudaGetLastError();
 }
 
-template cudaError_t prox_fibers_seq<double>(const double*, const double*, InOp, double*, FiberGeom, double, const double*,
+template cudaError_t prox_fibers_seq<double>(const double*, const double*, InOp, double*, int, FiberGeom, double, const double*,
                                              const int*, long long, cudaStream_t);
-template cudaError_t prox_fibers_seq<float>(const float*, const float*, InOp, float*, FiberGeom, float, const float*,
+template cudaError_t prox_fibers_seq<float>(const float*, const float*, InOp, float*, int, FiberGeom, float, const float*,
                                             const int*, long long, cudaStream_t);
 
 }  // namespace ptv

@@ -34,9 +34,10 @@ struct ProxStats {           // filled asynchronously on the device; optional
 
 // x = prox_{lam * TV}(in) for every fiber.  lamv == nullptr: uniform weight lam; else per-edge weights, laid out like the
 // fibers but with len-1 samples per fiber.  All pointers are device pointers.  Returns cudaGetLastError().
+// out_op (OutOp in chunk_core.cuh): 0 X = prox ; 1 X = 2*(in - prox) - in (DR reflection) ; 2 X = in - prox.
 template <typename T>
-cudaError_t prox_fibers(const T* A, const T* B, InOp op, T* X, FiberGeom g, T lam, const T* lamv, Engine eng,
-                        cudaStream_t st);
+cudaError_t prox_fibers(const T* A, const T* B, InOp op, T* X, int out_op, FiberGeom g, T lam, const T* lamv, Engine eng,
+                        T* scratch /* 2 * nf * len elements, or nullptr */, cudaStream_t st);
 
 // ---- launch accounting / event timing (profile.cu) ----
 enum KernelClass { KC_PROX_CONTIG = 0, KC_PROX_STRIDED = 1, KC_ELEMENTWISE = 2, KC_COUNT = 3 };
@@ -56,6 +57,9 @@ template <typename T> cudaError_t ew_dr_reflect_cols(const T* t, const T* x, T* 
 template <typename T> cudaError_t ew_dr_combine_rows(const T* Y, const T* s, const T* x, T* t, long long n, cudaStream_t st);
 template <typename T> cudaError_t ew_dr_final_cols(const T* t, const T* x, T* s, long long n, cudaStream_t st);
 template <typename T> cudaError_t ew_dr_final_rows(const T* Y, const T* s, const T* x, T* out, long long n, cudaStream_t st);
+template <typename T> cudaError_t ew_dr_reflect_bcast(const T* t, const T* x1, T* s, long long n, long long per_image, int len,
+                                                      long long inc, cudaStream_t st);
+template <typename T> cudaError_t prox_const_fibers(const T* c, long long c_stride, int batch, int n, T lam, T* x1, cudaStream_t st);
 template <typename T> cudaError_t ew_dual_update(T* p, const T* a, const T* b, long long n, cudaStream_t st);  // p += a - b
 template <typename T> cudaError_t ew_mean_abs_diff(const T* a, const T* b, long long n, double* scratch, double* result,
                                                    cudaStream_t st);                  // *result = mean|a-b| (device)

@@ -21,7 +21,7 @@ static constexpr size_t SCRATCH_BYTES = (REDUCE_BLOCKS + 8) * sizeof(double);
 // ------------------------------------------------------------------------------------------------------------------
 template <typename T> size_t ws_bytes_dr2(size_t M, size_t N, int batch) {
     size_t n = M * N * (size_t)batch;
-    return 3 * align256(n * sizeof(T)) + SCRATCH_BYTES;
+    return 5 * align256(n * sizeof(T)) + SCRATCH_BYTES;
 }
 
 template <typename T>
@@ -33,6 +33,7 @@ int dr2_device(size_t M, size_t N, int batch, int row_major, const T* Y, T w1, T
     T* t = (T*)w; w += align256(n * sizeof(T));
     T* s = (T*)w; w += align256(n * sizeof(T));
     T* x = (T*)w; w += align256(n * sizeof(T));
+    T* scr = (T*)w; w += 2 * align256(n * sizeof(T));      // gather/scatter staging of the strided pass
     double* scratch = (double*)w;
     if (maxit <= 0) maxit = MAX_ITERS_DR;                                     // TV2Dopt.cpp:387
     // first pass: fibers along axis 0 (length M); second pass: along axis 1 (length N) -- the order is part of the contract.
@@ -41,14 +42,19 @@ int dr2_device(size_t M, size_t N, int batch, int row_major, const T* Y, T w1, T
     const FiberGeom gr = row_major ? FiberGeom{(long long)M * batch, (int)N, 1} : FiberGeom{(long long)M * batch, (int)N, (long long)M};
     PTV_TRY(ew_image_means_x2<T>(Y, (long long)M * N, batch, t, scratch, st));        // :390-395
     for (int it = 0; it < maxit; it++) {                                      // :403-423
-        PTV_TRY(prox_fibers<T>(t, nullptr, IN_A, x, gc, w1, nullptr, eng, st));
-        PTV_TRY(ew_dr_reflect_cols<T>(t, x, s, n, st));
-        PTV_TRY(prox_fibers<T>(Y, s, IN_A_MINUS_B, x, gr, w2, nullptr, eng, st));
+        if (it == 0 && eng != ENGINE_SEQ) {
+            // the first input is the constant image 2*mean: every axis-0 fiber of an image is the same constant vector, so
+            // one fiber per image is solved (same arithmetic, registers only) and broadcast -- identical result, and it
+            // spares the chunked kernel its worst case (a fiber without a single break).
+            PTV_TRY(prox_const_fibers<T>(t, (long long)M * N, batch, (int)M, w1, x, st));
+            PTV_TRY(ew_dr_reflect_bcast<T>(t, x, s, n, (long long)M * N, gc.len, gc.inc, st));
+        } else
+        PTV_TRY(prox_fibers<T>(t, nullptr, IN_A, s, 1 /*reflect: s = 2(t - prox) - t*/, gc, w1, nullptr, eng, scr, st));
+        PTV_TRY(prox_fibers<T>(Y, s, IN_A_MINUS_B, x, 0, gr, w2, nullptr, eng, scr, st));
         PTV_TRY(ew_dr_combine_rows<T>(Y, s, x, t, n, st));
     }
-    PTV_TRY(prox_fibers<T>(t, nullptr, IN_A, x, gc, w1, nullptr, eng, st));   // :427-430
-    PTV_TRY(ew_dr_final_cols<T>(t, x, s, n, st));
-    PTV_TRY(prox_fibers<T>(Y, s, IN_A_MINUS_B, x, gr, w2, nullptr, eng, st));
+    PTV_TRY(prox_fibers<T>(t, nullptr, IN_A, s, 2 /*s = t - prox*/, gc, w1, nullptr, eng, scr, st));   // :427-430
+    PTV_TRY(prox_fibers<T>(Y, s, IN_A_MINUS_B, x, 0, gr, w2, nullptr, eng, scr, st));
     PTV_TRY(ew_dr_final_rows<T>(Y, s, x, out, n, st));
     if (info) { info[INFO_ITERS] = maxit; info[INFO_RC] = RC_OK; }            // :433-436 (INFO_GAP is left untouched)
     return 0;                                                                 // :440 (the reference returns 0 on success)
@@ -56,8 +62,8 @@ int dr2_device(size_t M, size_t N, int batch, int row_major, const T* Y, T w1, T
 
 // ------------------------------------------------------------------------------------------------------------------
 template <typename T> size_t ws_bytes_pd(long long n, int npen) {
-    int arrays = 2 * npen + 2;   // PD_TV: p_i, z_i ; PD2_TV (npen <= 2): p, q, z, xl  -> 4 <= 2*2+2
-    if (arrays < 4) arrays = 4;
+    int arrays = 2 * npen + 4;   // PD_TV: p_i, z_i ; PD2_TV (npen <= 2): p, q, z, xl  -> 4 <= 2*2+2
+    if (arrays < 6) arrays = 6;
     return (size_t)arrays * align256((size_t)n * sizeof(T)) + SCRATCH_BYTES + align256(2 * 64 * sizeof(void*));
 }
 
@@ -90,16 +96,17 @@ int pd2_device(const T* y, const double* lambdas, const double* dims, T* x, doub
     if (n > 0) {
         char* w = (char*)ws; const size_t ab = align256((size_t)n * sizeof(T));
         T* p = (T*)w; w += ab; T* q = (T*)w; w += ab; T* z = (T*)w; w += ab; T* xl = (T*)w; w += ab;
+        T* scr = (T*)w; w += 2 * ab;
         double* scratch = (double*)w; double* dres = scratch + REDUCE_BLOCKS;
         PTV_TRY(cudaMemcpyAsync(x, y, (size_t)n * sizeof(T), cudaMemcpyDeviceToDevice, st));          // :132-137
         PTV_TRY(cudaMemsetAsync(p, 0, (size_t)n * sizeof(T), st));
         PTV_TRY(cudaMemsetAsync(q, 0, (size_t)n * sizeof(T), st));
         while (stop > STOP_PD && (npen > 1 || !iters) && iters < maxIters) {                           // :157
             PTV_TRY(cudaMemcpyAsync(xl, x, (size_t)n * sizeof(T), cudaMemcpyDeviceToDevice, st));
-            PTV_TRY(prox_fibers<T>(x, p, IN_A_PLUS_B, z, g0, (T)lambdas[0], nullptr, eng, st));       // :171-208
+            PTV_TRY(prox_fibers<T>(x, p, IN_A_PLUS_B, z, 0, g0, (T)lambdas[0], nullptr, eng, scr, st));       // :171-208
             PTV_TRY(ew_dual_update<T>(p, x, z, n, st));                                               // :211-213
             if (npen >= 2) {
-                PTV_TRY(prox_fibers<T>(z, q, IN_A_PLUS_B, x, g1, (T)lambdas[1], nullptr, eng, st));   // :216-258
+                PTV_TRY(prox_fibers<T>(z, q, IN_A_PLUS_B, x, 0, g1, (T)lambdas[1], nullptr, eng, scr, st));   // :216-258
                 PTV_TRY(ew_dual_update<T>(q, z, x, n, st));                                           // :261-263
             } else {
                 PTV_TRY(cudaMemcpyAsync(x, z, (size_t)n * sizeof(T), cudaMemcpyDeviceToDevice, st));  // :266-269
@@ -129,6 +136,7 @@ int pd_device(const T* y, const double* lam, const double* dims, T* x, double* i
         char* w = (char*)ws; const size_t ab = align256((size_t)n * sizeof(T));
         T* hp[64]; T* hz[64];
         for (int i = 0; i < npen; i++) { hp[i] = (T*)w; w += ab; hz[i] = (T*)w; w += ab; }
+        T* scr = (T*)w; w += 2 * ab;
         double* scratch = (double*)w; double* dres = scratch + REDUCE_BLOCKS; w += SCRATCH_BYTES;
         T** dp = (T**)w; T** dz = dp + 64;
         PTV_TRY(cudaMemcpyAsync(dp, hp, sizeof(T*) * npen, cudaMemcpyHostToDevice, st));
@@ -138,7 +146,7 @@ int pd_device(const T* y, const double* lam, const double* dims, T* x, double* i
         for (int i = 0; i < npen; i++) PTV_TRY(cudaMemcpyAsync(hz[i], y, (size_t)n * sizeof(T), cudaMemcpyDeviceToDevice, st));
         while (stop > STOP_PD && iters < maxIters) {                                                  // :151
             for (int i = 0; i < npen; i++)
-                PTV_TRY(prox_fibers<T>(hz[i], nullptr, IN_A, hp[i], g[i], (T)lam[i], nullptr, eng, st));  // :171-208
+                PTV_TRY(prox_fibers<T>(hz[i], nullptr, IN_A, hp[i], 0, g[i], (T)lam[i], nullptr, eng, scr, st));  // :171-208
             PTV_TRY(ew_pd_combine<T>(dp, dz, npen, x, n, scratch, dres, st));                         // :212-227
             if (!read_stop(dres, &stop, st)) { PTV_TRY(cudaGetLastError()); PTV_TRY(cudaErrorUnknown); }
             iters++;

@@ -15,6 +15,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#define PTV_HD __host__ __device__ __forceinline__
+
 namespace ptv {
 
 // Kind of a segment start (how the scan state at that position was created).
@@ -28,19 +30,19 @@ enum : int {
 };
 
 template <typename T> struct Eps { };
-template <> struct Eps<double> { static __device__ __forceinline__ double v() { return 1e-10; } };   // general.h:64
-template <> struct Eps<float>  { static __device__ __forceinline__ float  v() { return 1e-10f; } };
+template <> struct Eps<double> { static PTV_HD double v() { return 1e-10; } };   // general.h:64
+template <> struct Eps<float>  { static PTV_HD float  v() { return 1e-10f; } };
 
 // Per-edge weight access: uniform lambda or a per-fiber array lam[0..n-2] (strided like the fiber itself).
 template <typename T> struct UniformLam {
     T lam;
     static constexpr bool weighted = false;
-    __device__ __forceinline__ T operator()(int) const { return lam; }
+    PTV_HD T operator()(int) const { return lam; }
 };
 template <typename T, class Ld> struct ArrayLam {
     Ld ld;      // ld(i) -> lam[i]
     static constexpr bool weighted = true;
-    __device__ __forceinline__ T operator()(int i) const { return ld(i); }
+    PTV_HD T operator()(int i) const { return ld(i); }
 };
 
 template <typename T> struct Scan {
@@ -52,7 +54,7 @@ template <typename T> struct Scan {
 
     // State at the beginning of a fiber (or of a speculative cold start at position p).
     template <class LdY, class Lam>
-    __device__ __forceinline__ void begin(int p, LdY y, Lam lam) {
+    PTV_HD void begin(int p, LdY y, Lam lam) {
         T l0 = lam(p);
         T y0 = y(p);
         hlo = hhi = T(0);
@@ -65,7 +67,7 @@ template <typename T> struct Scan {
 
     // Renewal state: a segment of the given kind starts at position p (0 < p < n).
     template <class LdY, class Lam>
-    __device__ __forceinline__ void renew(int p, int kind, int n, LdY y, Lam lam) {
+    PTV_HD void renew(int p, int kind, int n, LdY y, Lam lam) {
         T yp = y(p);
         last = p - 1;
         blo = bhi = p;
@@ -96,7 +98,7 @@ template <typename T> struct Scan {
     // afterwards), otherwise the kind of the segment start that was just created; in that case the finished segment
     // is [seg_first, seg_last] with value seg_val, and the state has been renewed at position seg_last + 1.
     template <class LdY, class Lam>
-    __device__ __forceinline__ int step(int n, LdY y, Lam lam, int& seg_first, int& seg_last, T& seg_val) {
+    PTV_HD int step(int n, LdY y, Lam lam, int& seg_first, int& seg_last, T& seg_val) {
         const T yi = y(i);
         if (i < n - 1) {
             const T li = lam(i);

@@ -1,0 +1,86 @@
+// transpose.cu -- tiled gather/scatter between strided fibers and contiguous fibers.
+//
+// The fibers of a column-major array along a dimension d >= 1 have element stride inc = prod(ns[0..d-1]) and adjacent
+// fibers are adjacent in memory: the array is [outer][len][inc] with `inc` fastest.  gather_fibers() writes the
+// transposed slab [outer][inc][len] (every fiber contiguous), fusing the input op (A, A-B, A+B); scatter_fibers() is the
+// inverse.  32 x 32 tiles through padded shared memory: both the read and the write side move 256-byte (f64) rows.
+// This is the simple route for the strided direction while the scan itself is compute-bound; the tile kernel that stages
+// strided fibers directly (DESIGN.md "next") removes these two extra sweeps.
+#include "ptv_internal.h"
+
+namespace ptv {
+
+template <typename T>
+__global__ void k_gather(const T* __restrict__ A, const T* __restrict__ B, int op, T* __restrict__ out, int len, long long inc) {
+    __shared__ T tile[32][33];
+    const long long o = blockIdx.z;
+    const long long slab = (long long)len * inc;
+    const long long r0 = (long long)blockIdx.x * 32;     // along inc (fiber index inside the slab)
+    const int k0 = blockIdx.y * 32;                      // along the fiber
+    const int tx = threadIdx.x, ty = threadIdx.y;        // 32 x 8
+    for (int dy = ty; dy < 32; dy += 8) {
+        const int k = k0 + dy; const long long r = r0 + tx;
+        if (k < len && r < inc) {
+            const long long idx = o * slab + (long long)k * inc + r;
+            T a = A[idx];
+            if (op == IN_A_MINUS_B) a = a - B[idx]; else if (op == IN_A_PLUS_B) a = a + B[idx];
+            tile[dy][tx] = a;
+        }
+    }
+    __syncthreads();
+    for (int dy = ty; dy < 32; dy += 8) {
+        const long long r = r0 + dy; const int k = k0 + tx;
+        if (k < len && r < inc) out[o * slab + r * len + k] = tile[tx][dy];
+    }
+}
+
+template <typename T>
+__global__ void k_scatter(const T* __restrict__ in, T* __restrict__ X, int len, long long inc) {
+    __shared__ T tile[32][33];
+    const long long o = blockIdx.z;
+    const long long slab = (long long)len * inc;
+    const long long r0 = (long long)blockIdx.x * 32;
+    const int k0 = blockIdx.y * 32;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    for (int dy = ty; dy < 32; dy += 8) {
+        const long long r = r0 + dy; const int k = k0 + tx;
+        if (k < len && r < inc) tile[dy][tx] = in[o * slab + r * len + k];
+    }
+    __syncthreads();
+    for (int dy = ty; dy < 32; dy += 8) {
+        const int k = k0 + dy; const long long r = r0 + tx;
+        if (k < len && r < inc) X[o * slab + (long long)k * inc + r] = tile[tx][dy];
+    }
+}
+
+template <typename T>
+cudaError_t gather_fibers(const T* A, const T* B, InOp op, T* out, FiberGeom g, cudaStream_t st) {
+    if (g.nf <= 0 || g.len <= 0) return cudaSuccess;
+    const long long outer = g.nf / g.inc;
+    dim3 grid((unsigned)((g.inc + 31) / 32), (unsigned)((g.len + 31) / 32), 1), block(32, 8);
+    for (long long o0 = 0; o0 < outer; o0 += 65535) {                // gridDim.z limit
+        grid.z = (unsigned)((outer - o0) < 65535 ? (outer - o0) : 65535);
+        const long long off = o0 * (long long)g.len * g.inc;
+        k_gather<T><<<grid, block, 0, st>>>(A + off, B ? B + off : nullptr, (int)op, out + off, g.len, g.inc);
+    }
+    return cudaGetLastError();
+}
+template <typename T>
+cudaError_t scatter_fibers(const T* in, T* X, FiberGeom g, cudaStream_t st) {
+    if (g.nf <= 0 || g.len <= 0) return cudaSuccess;
+    const long long outer = g.nf / g.inc;
+    dim3 grid((unsigned)((g.inc + 31) / 32), (unsigned)((g.len + 31) / 32), 1), block(32, 8);
+    for (long long o0 = 0; o0 < outer; o0 += 65535) {
+        grid.z = (unsigned)((outer - o0) < 65535 ? (outer - o0) : 65535);
+        const long long off = o0 * (long long)g.len * g.inc;
+        k_scatter<T><<<grid, block, 0, st>>>(in + off, X + off, g.len, g.inc);
+    }
+    return cudaGetLastError();
+}
+
+template cudaError_t gather_fibers<double>(const double*, const double*, InOp, double*, FiberGeom, cudaStream_t);
+template cudaError_t gather_fibers<float>(const float*, const float*, InOp, float*, FiberGeom, cudaStream_t);
+template cudaError_t scatter_fibers<double>(const double*, double*, FiberGeom, cudaStream_t);
+template cudaError_t scatter_fibers<float>(const float*, float*, FiberGeom, cudaStream_t);
+
+}  // namespace ptv

@@ -1,0 +1,72 @@
+// emu_chunked.cu -- TEST INFRASTRUCTURE: runs the per-lane phases of proxtv_b200/csrc/chunk_core.cuh on the CPU, lane by
+// lane and phase by phase, exactly as one CTA of kernels_chunked.cu executes them (lanes interact only across barriers,
+// so a sequential sweep over lanes per phase is an exact emulation; the one-writer-per-chunk-per-round discipline that
+// makes this true is asserted, not assumed).  Lets the stitching logic be checked against the oracle without a GPU.
+// Not part of the product; built by tests/test_chunk_emulation.py with nvcc (host code only).
+#include "../../proxtv_b200/csrc/chunk_core.cuh"
+#include <vector>
+#include <string.h>
+
+using namespace ptv;
+
+template <typename T> struct PtrLd { const T* p; PTV_HD T operator()(int i) const { return p[i]; } };
+// value store that records which chunk each round writes, to assert the write discipline
+template <typename T> struct ChkSt {
+    T* p; int* owner_round; int* owner_lane; int* cur_round; int* cur_lane; int* bad;
+    PTV_HD void operator()(int j, T v) const {
+        int c = j / CH;
+        if (owner_round[c] == *cur_round && owner_lane[c] != *cur_lane) *bad = 1;     // two lanes wrote one chunk in a round
+        owner_round[c] = *cur_round; owner_lane[c] = *cur_lane;
+        p[j] = v;
+    }
+};
+
+template <typename T>
+static int emu(const T* yin, int n, T lam, const T* lamv, T* x, int out_op, int* rounds_out) {
+    if (n <= 0) return 0;
+    const int nchunks = (n + CH - 1) / CH;
+    std::vector<T> ys(yin, yin + n), vs(n, T(-12345)), ws(n, T(0)), rcp(RCP_N, T(0));
+    for (int d = 1; d < RCP_N; d++) rcp[d] = T(1) / T(d);
+    if (lamv) memcpy(ws.data(), lamv, sizeof(T) * (size_t)(n - 1));
+    std::vector<uint32_t> P(nchunks), K0(nchunks), K1(nchunks);
+    ChunkMasks m{P.data(), K0.data(), K1.data()};
+    std::vector<LaneState<T>> st(nchunks);
+    std::vector<int> orr(nchunks, -1), orl(nchunks, -1), carry(nchunks);
+    int cur_round = 0, cur_lane = 0, bad = 0;
+    PtrLd<T> y{ys.data()};
+    ChkSt<T> stv{vs.data(), orr.data(), orl.data(), &cur_round, &cur_lane, &bad};
+    RcpDiv<T> div{rcp.data()};
+    auto run = [&](auto lamf) -> int {
+        int r = 0;
+        for (;; r++) {
+            cur_round = r;
+            std::vector<uint32_t> sP(P), sK0(K0), sK1(K1);
+            bool any = false;
+            for (int q = 0; q < nchunks; q++) {
+                cur_lane = q;
+                int c = q + r;          // the chunk lane q reads/writes this round must still hold its pre-round masks
+                if (r > 0 && st[q].active && c < nchunks && (P[c] != sP[c] || K0[c] != sK0[c] || K1[c] != sK1[c])) return -1;
+                if (r == 0) { st[q].active = false; st[q].finished = false; st[q].pend_a = -1; st[q].pend_k = K_NONE; }
+                any |= walk_chunk<T>(q, r, nchunks, n, y, stv, lamf, div, st[q], m);
+            }
+            if (bad) return -2;
+            if (!any) break;
+        }
+        if (rounds_out) *rounds_out = r;
+        fill_carry_seq(nchunks, m, carry.data());
+        for (int j = 0; j < n; j++) {
+            int a = seg_start_of(j, m, carry.data());
+            x[j] = apply_out<T>(out_op, ys[j], vs[a]);
+        }
+        return 0;
+    };
+    if (lamv) return run(ArrayLam<T, PtrLd<T>>{PtrLd<T>{ws.data()}});
+    return run(UniformLam<T>{lam});
+}
+
+extern "C" int emu_chunked_f64(const double* y, int n, double lam, const double* lamv, double* x, int out_op, int* rounds) {
+    return emu<double>(y, n, lam, lamv, x, out_op, rounds);
+}
+extern "C" int emu_chunked_f32(const float* y, int n, float lam, const float* lamv, float* x, int out_op, int* rounds) {
+    return emu<float>(y, n, lam, lamv, x, out_op, rounds);
+}
