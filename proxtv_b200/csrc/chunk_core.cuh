@@ -1,8 +1,11 @@
 // chunk_core.cuh -- per-lane phases of the chunked speculative TV-L1 prox (host+device so a CTA can be emulated on CPU).
 //
-// One fiber is cut into chunks of CH = 32 samples; one lane owns one chunk.  Shared state per fiber: the staged input y,
-// a SPARSE value array vs (vs[a] = value of the segment that starts at a, valid only where a start is recorded), and one
-// (present, kind-bit-0, kind-bit-1) mask word triple per chunk.  Phases, with a CTA barrier between consecutive ones:
+// One fiber is cut into chunks of CH = 32 samples; one lane owns one chunk.  State per fiber: the staged input y (shared
+// memory), one (present, kind-bit-0, kind-bit-1) mask word triple per chunk (shared memory), and a SPARSE value store
+// vs (vs[a] = value of the segment that starts at a, meaningful only where a start is recorded) for which the kernel uses
+// the fiber's own OUTPUT row in global memory (it lives in L2 for the few microseconds between the scan and the fill),
+// so shared memory holds 8 bytes per sample and twice as many fibers are resident per SM.
+// Phases, with a CTA barrier between consecutive ones:
 //
 //   walk own chunk (round 0)  every lane runs the exact scan (taut_scan.cuh) from a COLD START at its chunk's first sample
 //              (lane 0: the true start of the fiber) until its first segment start at or beyond the chunk end, recording
@@ -17,12 +20,14 @@
 //              samples); a fiber without breaks degrades to one lane's sequential scan, never to a wrong
 //              answer.
 //   fill       the final masks are the exact segmentation and vs holds the exact segment values: every output sample is
-//              f(y[j], vs[start(j)]), computed cooperatively with coalesced stores.
+//              f(y[j], vs[start(j)]).  Done one 32-sample window at a time (all reads of vs inside the window, then all
+//              writes), with the value of the segment entering each window gathered beforehand, because vs IS the output.
 //
 // Every number produced is bit-identical to the sequential scan: the same operations in the same order per segment.  The
-// scan loop is FLAT: one scan step per iteration for every lane (breaks are handled by predicated code in the same
-// iteration), so lanes of a warp only diverge in their trip counts.  Divisions by the small integer (i - last) use a
-// correctly rounded reciprocal table + two FMAs (Markstein): q = a*r, q' = fma(fma(-q, d, a), r, q) == RN(a / d).
+// scan loop is FLAT: one scan step per iteration for every lane (a break is handled inside the same iteration), so lanes
+// of a warp only diverge in their trip counts.  Divisions by the small integer (i - last) use a correctly rounded
+// reciprocal table + two FMAs (Markstein): q = a*r, q' = fma(fma(-q, d, a), r, q) == RN(a / d); verified exhaustively
+// against IEEE division for all table divisors (tests/test_chunk_emulation.py::test_table_division_is_exact).
 #pragma once
 #include "taut_scan.cuh"
 #include <math.h>
@@ -34,14 +39,16 @@ constexpr int RCP_N = 64;                   // reciprocal table covers divisors 
 
 struct ChunkMasks { uint32_t* P; uint32_t* K0; uint32_t* K1; };     // one word per chunk of one fiber
 
+template <typename T> struct alignas(2 * sizeof(T)) RcpPair { T r, d; };     // (1/d correctly rounded, d)
+
 // exact a / d for integer d >= 1
 template <typename T> struct RcpDiv {
-    const T* tbl;
+    const RcpPair<T>* tbl;
     PTV_HD T operator()(T a, int d) const {
         if (d < RCP_N) {
-            const T r = tbl[d], dd = T(d);
-            const T q = a * r;
-            return fma(fma(-q, dd, a), r, q);
+            const RcpPair<T> e = tbl[d];
+            const T q = a * e.r;
+            return fma(fma(-q, e.d, a), e.r, q);
         }
         return a / T(d);
     }
@@ -54,13 +61,6 @@ template <typename T> struct LaneState {
     bool active;            // still has chunks to walk through
 };
 
-PTV_HD int low_bit(uint32_t m) {
-#ifdef __CUDA_ARCH__
-    return __ffs((int)m) - 1;
-#else
-    return __builtin_ctz(m);
-#endif
-}
 PTV_HD int high_bit(uint32_t m) {          // m != 0
 #ifdef __CUDA_ARCH__
     return 31 - __clz((int)m);
@@ -69,90 +69,94 @@ PTV_HD int high_bit(uint32_t m) {          // m != 0
 #endif
 }
 
-// One regular scan step (requires s.i < n - 1), written so that it compiles to straight-line predicated code.
-// Returns K_NONE / K_CEIL / K_FLOOR; on a break the finished segment is [f, s.last] (s.last already updated) with value v.
-template <typename T, class LdY, class Lam>
-PTV_HD int fast_step(Scan<T>& s, LdY y, Lam lam, RcpDiv<T> div, int& f, T& v) {
-    const int i = s.i;
-    const T yi = y(i);
-    const T li = lam(i);
-    const T hlo = s.hlo + (s.lo - yi);
-    const T hhi = s.hhi + (s.hi - yi);
-    const bool cb = li < hlo;
-    const bool fb = !cb && (-li > hhi);
-    if (cb | fb) {
-        const int p = (cb ? s.blo : s.bhi) + 1;
-        f = s.last + 1;
-        v = cb ? s.lo : s.hi;
-        const T yp = y(p);
-        if (!Lam::weighted) {
-            const T l2 = T(2) * li, nl2 = T(2) * (-li);
-            s.lo = cb ? yp : nl2 + yp;
-            s.hi = cb ? l2 + yp : yp;
-            s.hhi = li; s.hlo = -li;
-        } else {
-            const T lp = lam(p - 1), lq = lam(p);
-            if (cb) { s.lo = yp + lp - lq; s.hi = yp + lp + lq; }
-            else    { s.hi = yp - lp + lq; s.lo = yp - lp - lq; }
-            s.hhi = lq; s.hlo = -lq;
-        }
-        s.last = p - 1; s.blo = s.bhi = p; s.i = p + 1;
-        return cb ? K_CEIL : K_FLOOR;
-    }
-    const int d = i - s.last;
-    T hh = hhi, hl = hlo;
-    if (hhi >= li)  { s.hi = s.hi + div(li - hhi, d);  hh = li;  s.bhi = i; }
-    if (hlo <= -li) { s.lo = s.lo + div(-li - hlo, d); hl = -li; s.blo = i; }
-    s.hhi = hh; s.hlo = hl; s.i = i + 1;
-    return K_NONE;
-}
-
-// Walk through chunk c.  round == 0: the lane's own chunk, entered with a cold start (no merging possible: the chunk's
-// masks are not written yet).  round >= 1: a chunk to the right, entered with the lane's scan state and pending start.
-// StV(j, v): store into the sparse value array.  Returns true if the lane is still active afterwards.
-template <typename T, class LdY, class StV, class Lam>
+// Walk through chunk c = q + round.  ROUND0: the lane's own chunk, entered with a cold start (no merging possible: the
+// chunk's masks are not written yet).  Otherwise a chunk to the right, entered with the lane's scan state and pending
+// start.  StV(j, v): store into the sparse value store.  Returns true if the lane is still active afterwards.
+template <typename T, bool ROUND0, class LdY, class StV, class Lam>
 PTV_HD bool walk_chunk(int q, int round, int nchunks, int n, LdY y, StV stv, Lam lam, RcpDiv<T> div, LaneState<T>& st,
                        ChunkMasks m) {
     const int c = q + round;
-    if (round > 0) {
+    uint32_t oP = 0, oK0 = 0, oK1 = 0, P = 0, K0 = 0, K1 = 0;
+    const int cb = c * CH, ce = (cb + CH < n) ? cb + CH : n;
+    if (ROUND0) {
+        st.s.begin(cb, y, lam);            // q == 0: the true start; q > 0: speculative cold start
+        st.finished = false; st.pend_a = -1; st.pend_k = K_NONE;
+    } else {
         if (!st.active) return false;
         if (c >= nchunks) { st.active = false; return false; }
-        if (st.finished) {                 // the lane's scan ended further left: it passed over this chunk without a start
-            m.P[c] = 0; m.K0[c] = 0; m.K1[c] = 0;
+        if (st.finished || st.pend_a >= ce) {      // nothing of this lane's scan starts inside this chunk: it is covered
+            m.P[c] = 0; m.K0[c] = 0; m.K1[c] = 0;  // by the lane's open segment -> override with "no starts"
             st.active = (c + 1 < nchunks);
             return st.active;
         }
-    }
-    const int cb = c * CH, ce = (cb + CH < n) ? cb + CH : n;
-    uint32_t oP = 0, oK0 = 0, oK1 = 0;
-    if (round > 0) { oP = m.P[c]; oK0 = m.K0[c]; oK1 = m.K1[c]; }
-    else {
-        st.s.begin(cb, y, lam);            // q == 0: the true start; q > 0: speculative cold start
-        st.finished = false; st.pend_a = -1; st.pend_k = K_NONE;
-    }
-    uint32_t P = 0, K0 = 0, K1 = 0;
-    bool merged = false; int mbit = 0;
-    // a start found in an earlier phase that lies inside this chunk is handled first, then one scan step per iteration
-    bool have = (st.pend_a >= 0);
-    for (;;) {
-        if (have) {
-            if (st.pend_a >= ce) break;                                   // beyond this chunk: keep it pending
-            const int bit = st.pend_a - cb, kk = st.pend_k - 1;
-            if (((oP >> bit) & 1u) && (int)((oK0 >> bit) & 1u) == (kk & 1) && (int)((oK1 >> bit) & 1u) == (kk >> 1)) {
-                merged = true; mbit = bit; break;
-            }
-            P |= 1u << bit; K0 |= (uint32_t)(kk & 1) << bit; K1 |= (uint32_t)(kk >> 1) << bit;
-            have = false;
+        oP = m.P[c]; oK0 = m.K0[c]; oK1 = m.K1[c];
+        // the pending start lies inside this chunk (pend_a >= cb holds: the previous round consumed everything before)
+        const int bit = st.pend_a - cb, kk = st.pend_k - 1;
+        if (((oP >> bit) & 1u) && (int)((oK0 >> bit) & 1u) == (kk & 1) && (int)((oK1 >> bit) & 1u) == (kk >> 1)) {
+            const uint32_t keep = ~0u << bit;      // merged right away: drop the chunk's starts that lie inside the lane's
+            m.P[c] = oP & keep; m.K0[c] = oK0 & keep; m.K1[c] = oK1 & keep;      // open segment, keep the rest
+            st.active = false;
+            return false;
         }
-        int k, f; T v;
-        if (st.s.i < n - 1) k = fast_step<T>(st.s, y, lam, div, f, v);
-        else if (st.s.i == n - 1) { int l; k = st.s.step(n, y, lam, f, l, v); }     // closing sample: rare, generic code
-        else {                                                                     // the fiber ended: last open segment
+        P = 1u << bit; K0 = (uint32_t)(kk & 1) << bit; K1 = (uint32_t)(kk >> 1) << bit;
+    }
+    bool merged = false; int mbit = 0;
+    for (;;) {
+        int k, f, a; T v;
+        if (st.s.i < n - 1) {
+            // ---- regular step (taut_scan.cuh Scan::step, i < n-1 branch) with the break handled in place ----
+            Scan<T>& s = st.s;
+            const int i = s.i;
+            const T yi = y(i);
+            const T li = lam(i);
+            const T hlo = s.hlo + (s.lo - yi);
+            const T hhi = s.hhi + (s.hi - yi);
+            const bool cbk = li < hlo;
+            const bool fbk = !cbk && (-li > hhi);
+            if (!(cbk | fbk)) {
+                const int d = i - s.last;
+                T hh = hhi, hl = hlo;
+                if (hhi >= li)  { s.hi = s.hi + div(li - hhi, d);  hh = li;  s.bhi = i; }
+                if (hlo <= -li) { s.lo = s.lo + div(-li - hlo, d); hl = -li; s.blo = i; }
+                s.hhi = hh; s.hlo = hl; s.i = i + 1;
+                continue;
+            }
+            a = (cbk ? s.blo : s.bhi) + 1;
+            f = s.last + 1;
+            v = cbk ? s.lo : s.hi;
+            const T yp = y(a);
+            if (!Lam::weighted) {
+                const T l2 = T(2) * li, nl2 = T(2) * (-li);
+                s.lo = cbk ? yp : nl2 + yp;
+                s.hi = cbk ? l2 + yp : yp;
+                s.hhi = li; s.hlo = -li;
+            } else {
+                const T lp = lam(a - 1), lq = lam(a);
+                if (cbk) { s.lo = yp + lp - lq; s.hi = yp + lp + lq; }
+                else     { s.hi = yp - lp + lq; s.lo = yp - lp - lq; }
+                s.hhi = lq; s.hlo = -lq;
+            }
+            s.last = a - 1; s.blo = s.bhi = a; s.i = a + 1;
+            k = cbk ? K_CEIL : K_FLOOR;
+        } else if (st.s.i == n - 1) {              // closing sample: rare, generic code
+            int l;
+            k = st.s.step(n, y, lam, f, l, v);
+            if (k == K_NONE) continue;             // i == n now: handled by the next iteration
+            a = l + 1;
+        } else {                                   // the fiber ended: value of the last open segment
             stv(st.s.last + 1, st.s.lo);
             st.finished = true; st.pend_a = -1;
             break;
         }
-        if (k != K_NONE) { stv(f, v); st.pend_a = st.s.last + 1; st.pend_k = k; have = true; }
+        // ---- a segment [f, a-1] with value v was finished and a new one starts at a with kind k ----
+        stv(f, v);
+        if (a >= ce) { st.pend_a = a; st.pend_k = k; break; }
+        const int bit = a - cb, kk = k - 1;
+        if (!ROUND0 && ((oP >> bit) & 1u) && (int)((oK0 >> bit) & 1u) == (kk & 1) && (int)((oK1 >> bit) & 1u) == (kk >> 1)) {
+            merged = true; mbit = bit; break;
+        }
+        const uint32_t mb = 1u << bit;
+        P |= mb; K0 |= (kk & 1) ? mb : 0u; K1 |= (kk >> 1) ? mb : 0u;
     }
     if (merged) {
         const uint32_t keep = ~0u << mbit;
@@ -174,22 +178,18 @@ template <typename T> PTV_HD T apply_out(int op, T yin, T x) {
     return d;                                                 // final projection      (:427)
 }
 
-// carry[c] = position of the last segment start strictly before chunk c's first sample that is <= that sample's segment,
-// i.e. the start of the segment covering sample c*CH when the chunk's own bit 0 is not set.  Sequential reference
-// implementation (the kernel computes the same thing with a warp scan).
-PTV_HD void fill_carry_seq(int nchunks, ChunkMasks m, int* carry) {
-    int lastpos = 0;                                         // sample 0 always starts a segment
-    for (int c = 0; c < nchunks; c++) {
-        carry[c] = lastpos;
-        if (m.P[c]) lastpos = c * CH + high_bit(m.P[c]);
-    }
+// carry[c] = start of the segment that covers sample c*CH when the chunk's own bit 0 is not set: the last recorded start
+// before the chunk (sample 0 always starts a segment).  Lane-parallel form: each lane looks left for a non-empty chunk.
+PTV_HD int carry_of(int c, ChunkMasks m) {
+    int c2 = c - 1;
+    while (c2 >= 0 && m.P[c2] == 0) c2--;
+    return (c2 >= 0) ? c2 * CH + high_bit(m.P[c2]) : 0;
 }
 
-// start position of the segment covering sample j
-PTV_HD int seg_start_of(int j, ChunkMasks m, const int* carry) {
-    const int c = j >> 5, b = j & 31;
+// start of the segment covering sample j = c*CH + b, or -1 if that segment starts before the chunk (use the carry)
+PTV_HD int seg_start_in_chunk(int c, int b, ChunkMasks m) {
     const uint32_t w = m.P[c] & (0xffffffffu >> (31 - b));
-    return w ? (c << 5) + high_bit(w) : carry[c];
+    return w ? (c << 5) + high_bit(w) : -1;
 }
 
 }  // namespace ptv

@@ -20,27 +20,68 @@ template <typename T> struct SmemSt {
     PTV_HD void operator()(int j, T v) const { p[j + (j >> 5) * PadCfg<T>::PADE] = v; }
 };
 
+// ---- TMA (bulk async copy) staging: cp.async.bulk global -> shared, completion counted on an mbarrier ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <typename T> struct GlobSt {            // sparse value store = the fiber's own output row (see chunk_core.cuh)
+    T* p;
+    __device__ __forceinline__ void operator()(int j, T v) const { p[j] = v; }
+};
+
 template <typename T, bool WEIGHTED>
 __global__ void k_prox_chunked_contig(const T* __restrict__ A, const T* __restrict__ B, int in_op, T* __restrict__ X, int out_op,
-                                      long long nf, int n, T lam, const T* __restrict__ lamv, int lpf, int fpb, int npad) {
+                                      long long nf, int n, T lam, const T* __restrict__ lamv, int lpf, int fpb, int npad, int use_tma) {
+    __shared__ uint64_t mbar;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    T* ys = reinterpret_cast<T*>(smem_raw);                       // staged input            [fpb][npad]
-    T* vs = ys + (size_t)fpb * npad;                              // sparse segment values   [fpb][npad]
-    T* wsm = vs + (size_t)fpb * npad;                             // per-edge weights        [fpb][npad] (weighted only)
-    T* rcp = wsm + (WEIGHTED ? (size_t)fpb * npad : 0);           // reciprocal table        [RCP_N]
-    uint32_t* mk = reinterpret_cast<uint32_t*>(rcp + RCP_N);      // masks P, K0, K1         [3][fpb][lpf]
-    int* carry = reinterpret_cast<int*>(mk + (size_t)3 * fpb * lpf);   // [fpb][lpf]
+    RcpPair<T>* rcp = reinterpret_cast<RcpPair<T>*>(smem_raw);    // reciprocal table        [RCP_N]   (16-byte aligned)
+    T* ys = reinterpret_cast<T*>(rcp + RCP_N);                    // staged input            [fpb][npad] (npad*sizeof(T) % 16 == 0)
+    T* wsm = ys + (size_t)fpb * npad;                             // per-edge weights        [fpb][npad] (weighted only)
+    T* cval = wsm + (WEIGHTED ? (size_t)fpb * npad : 0);          // value entering each chunk [fpb][lpf]
+    uint32_t* mk = reinterpret_cast<uint32_t*>(cval + (size_t)fpb * lpf);      // masks P, K0, K1 [3][fpb][lpf]
     constexpr int PADE = PadCfg<T>::PADE;
     const int tid = threadIdx.x;
     const long long f0 = (long long)blockIdx.x * fpb;
     const int nfib = (int)((nf - f0) < fpb ? (nf - f0) : fpb);
+    const int nchunks = (n + CH - 1) / CH;
 
-    // ---- stage the fibers: coalesced reads, input op applied on the fly ----
-    if (tid < RCP_N) rcp[tid] = tid ? T(1) / T(tid) : T(0);
+    // ---- stage the fibers ----
+    if (tid < RCP_N) { rcp[tid].r = tid ? T(1) / T(tid) : T(0); rcp[tid].d = T(tid); }
+    if (use_tma) {
+        // one bulk copy per 32-sample chunk row (rows are padded in shared memory), all in flight at once
+        if (tid == 0) mbar_init(&mbar, 1);
+        __syncthreads();
+        if (tid == 0) mbar_arrive_expect_tx(&mbar, (uint32_t)((size_t)nfib * n * sizeof(T)));
+        for (int e = tid; e < nfib * nchunks; e += blockDim.x) {
+            const int fb = e / nchunks, c = e - fb * nchunks;
+            const int cnt = (c * CH + CH <= n) ? CH : n - c * CH;
+            tma_bulk_g2s(ys + (size_t)fb * npad + (size_t)c * (CH + PADE), A + (f0 + fb) * (long long)n + (long long)c * CH,
+                         (uint32_t)(cnt * sizeof(T)), &mbar);
+        }
+    }
     for (int fb = 0; fb < nfib; fb++) {
         const long long base = (f0 + fb) * (long long)n;
         T* row = ys + (size_t)fb * npad;
-        for (int j = tid; j < n; j += blockDim.x) {
+        if (!use_tma) for (int j = tid; j < n; j += blockDim.x) {       // coalesced reads, input op applied on the fly
             T a = A[base + j];
             if (in_op == IN_A_MINUS_B) a = a - B[base + j];
             else if (in_op == IN_A_PLUS_B) a = a + B[base + j];
@@ -52,48 +93,47 @@ __global__ void k_prox_chunked_contig(const T* __restrict__ A, const T* __restri
             for (int j = tid; j < n; j += blockDim.x) wrow[j + (j >> 5) * PADE] = (j < n - 1) ? lamv[wbase + j] : T(0);
         }
     }
+    if (use_tma) mbar_wait(&mbar, 0);
     __syncthreads();
 
-    const int nchunks = (n + CH - 1) / CH;
+    // ---- scan: own chunk, then rounds until every lane has merged ----
     const int fb = tid / lpf, q = tid - fb * lpf;
     const bool lane_ok = fb < nfib && q < nchunks;
     const int fbc = lane_ok ? fb : 0;
     ChunkMasks m{mk + (size_t)fbc * lpf, mk + (size_t)(fpb + fbc) * lpf, mk + (size_t)(2 * fpb + fbc) * lpf};
     SmemLd<T> y{ys + (size_t)fbc * npad};
-    SmemSt<T> stv{vs + (size_t)fbc * npad};
+    T* xrow = X + (f0 + fbc) * (long long)n;
+    GlobSt<T> stv{xrow};
     RcpDiv<T> div{rcp};
     LaneState<T> st;
     st.active = false; st.finished = false; st.pend_a = -1; st.pend_k = K_NONE;
 
     auto phases = [&](auto lamf) {
-        bool act = lane_ok ? walk_chunk<T>(q, 0, nchunks, n, y, stv, lamf, div, st, m) : false;
+        bool act = lane_ok ? walk_chunk<T, true>(q, 0, nchunks, n, y, stv, lamf, div, st, m) : false;
         for (int r = 1; __syncthreads_or(act ? 1 : 0); r++)
-            act = lane_ok ? walk_chunk<T>(q, r, nchunks, n, y, stv, lamf, div, st, m) : false;
+            act = lane_ok ? walk_chunk<T, false>(q, r, nchunks, n, y, stv, lamf, div, st, m) : false;
     };
     if (WEIGHTED) phases(ArrayLam<T, SmemLd<T>>{SmemLd<T>{wsm + (size_t)fbc * npad}});
     else phases(UniformLam<T>{lam});
 
-    // ---- carry: start of the segment that covers each chunk's first sample ----
-    int* cr = carry + (size_t)fbc * lpf;
-    if (lane_ok) {
-        int c2 = q - 1;
-        while (c2 >= 0 && m.P[c2] == 0) c2--;
-        cr[q] = (c2 >= 0) ? c2 * CH + high_bit(m.P[c2]) : 0;
-    }
+    // ---- value of the segment entering each chunk (gathered before any output is written: the store is the output) ----
+    if (lane_ok) cval[(size_t)fbc * lpf + q] = __ldcg(xrow + carry_of(q, m));
     __syncthreads();
 
-    // ---- fill + stream the result back: out[j] = f(y[j], value of the segment covering j), coalesced ----
-    for (int fb2 = 0; fb2 < nfib; fb2++) {
-        const long long base = (f0 + fb2) * (long long)n;
-        const T* yrow = ys + (size_t)fb2 * npad;
-        const T* vrow = vs + (size_t)fb2 * npad;
+    // ---- fill: one 32-sample window per warp iteration; all sparse reads of the window, then its (coalesced) writes ----
+    const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+    for (int w = warp; w < nfib * nchunks; w += nwarps) {
+        const int fb2 = w / nchunks, c = w - fb2 * nchunks;
+        const int j = c * CH + lane;
+        T* xr = X + (f0 + fb2) * (long long)n;
         ChunkMasks m2{mk + (size_t)fb2 * lpf, nullptr, nullptr};
-        const int* cr2 = carry + (size_t)fb2 * lpf;
-        for (int j = tid; j < n; j += blockDim.x) {
-            const int a = seg_start_of(j, m2, cr2);
-            const T x = vrow[a + (a >> 5) * PADE];
-            X[base + j] = apply_out<T>(out_op, yrow[j + (j >> 5) * PADE], x);
+        T v = T(0);
+        if (j < n) {
+            const int sa = seg_start_in_chunk(c, lane, m2);
+            v = (sa >= 0) ? __ldcg(xr + sa) : cval[(size_t)fb2 * lpf + c];
         }
+        __syncwarp();
+        if (j < n) xr[j] = apply_out<T>(out_op, ys[(size_t)fb2 * npad + j + (j >> 5) * PADE], v);
     }
 }
 
@@ -106,11 +146,11 @@ cudaError_t prox_fibers_chunked_contig(const T* A, const T* B, InOp op, T* X, in
     const int n = g.len;
     const int lpf = (n + CH - 1) / CH;
     if (lpf > 1024) return cudaErrorInvalidConfiguration;
-    const int npad = n + (lpf + 1) * PadCfg<T>::PADE;
-    const size_t per_fiber = (size_t)npad * sizeof(T) * (lamv ? 3 : 2) + (size_t)lpf * 16;
+    const int npad = (n + (lpf + 1) * PadCfg<T>::PADE + PadCfg<T>::PADE - 1) / PadCfg<T>::PADE * PadCfg<T>::PADE;
+    const size_t per_fiber = (size_t)npad * sizeof(T) * (lamv ? 2 : 1) + (size_t)lpf * (12 + sizeof(T));
     int fpb = 128 / lpf; if (fpb < 1) fpb = 1;
     if ((long long)fpb > g.nf) fpb = (int)g.nf;
-    const size_t smem = per_fiber * fpb + RCP_N * sizeof(T) + 16;
+    const size_t smem = per_fiber * fpb + RCP_N * 2 * sizeof(T) + 16;
     if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;
     int threads = ((fpb * lpf + 31) / 32) * 32;
     if (threads < RCP_N) threads = RCP_N;
@@ -119,7 +159,9 @@ cudaError_t prox_fibers_chunked_contig(const T* A, const T* B, InOp op, T* X, in
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    kern<<<blocks, threads, smem, st>>>(A, B, (int)op, X, out_op, g.nf, n, lam, lamv, lpf, fpb, npad);
+    // TMA staging needs 16-byte aligned rows: aligned base, row pitch a multiple of 16 bytes, single input array
+    const int use_tma = (op == IN_A) && (((uintptr_t)A & 15) == 0) && (((size_t)n * sizeof(T)) % 16 == 0);
+    kern<<<blocks, threads, smem, st>>>(A, B, (int)op, X, out_op, g.nf, n, lam, lamv, lpf, fpb, npad, use_tma);
     return cudaGetLastError();
 }
 

@@ -1,7 +1,7 @@
 // emu_chunked.cu -- TEST INFRASTRUCTURE: runs the per-lane phases of proxtv_b200/csrc/chunk_core.cuh on the CPU, lane by
 // lane and phase by phase, exactly as one CTA of kernels_chunked.cu executes them (lanes interact only across barriers,
 // so a sequential sweep over lanes per phase is an exact emulation; the one-writer-per-chunk-per-round discipline that
-// makes this true is asserted, not assumed).  Lets the stitching logic be checked against the oracle without a GPU.
+// makes this true is asserted, not assumed).  The output array doubles as the sparse value store, as in the kernel.
 // Not part of the product; built by tests/test_chunk_emulation.py with nvcc (host code only).
 #include "../../proxtv_b200/csrc/chunk_core.cuh"
 #include <vector>
@@ -25,16 +25,18 @@ template <typename T>
 static int emu(const T* yin, int n, T lam, const T* lamv, T* x, int out_op, int* rounds_out) {
     if (n <= 0) return 0;
     const int nchunks = (n + CH - 1) / CH;
-    std::vector<T> ys(yin, yin + n), vs(n, T(-12345)), ws(n, T(0)), rcp(RCP_N, T(0));
-    for (int d = 1; d < RCP_N; d++) rcp[d] = T(1) / T(d);
+    std::vector<T> ys(yin, yin + n), ws(n, T(0)), cval(nchunks);
+    std::vector<RcpPair<T>> rcp(RCP_N);
+    for (int d = 0; d < RCP_N; d++) { rcp[d].r = d ? T(1) / T(d) : T(0); rcp[d].d = T(d); }
     if (lamv) memcpy(ws.data(), lamv, sizeof(T) * (size_t)(n - 1));
+    for (int j = 0; j < n; j++) x[j] = T(-12345);                 // the output row doubles as the sparse value store
     std::vector<uint32_t> P(nchunks), K0(nchunks), K1(nchunks);
     ChunkMasks m{P.data(), K0.data(), K1.data()};
     std::vector<LaneState<T>> st(nchunks);
-    std::vector<int> orr(nchunks, -1), orl(nchunks, -1), carry(nchunks);
+    std::vector<int> orr(nchunks, -1), orl(nchunks, -1);
     int cur_round = 0, cur_lane = 0, bad = 0;
     PtrLd<T> y{ys.data()};
-    ChkSt<T> stv{vs.data(), orr.data(), orl.data(), &cur_round, &cur_lane, &bad};
+    ChkSt<T> stv{x, orr.data(), orl.data(), &cur_round, &cur_lane, &bad};
     RcpDiv<T> div{rcp.data()};
     auto run = [&](auto lamf) -> int {
         int r = 0;
@@ -46,17 +48,23 @@ static int emu(const T* yin, int n, T lam, const T* lamv, T* x, int out_op, int*
                 cur_lane = q;
                 int c = q + r;          // the chunk lane q reads/writes this round must still hold its pre-round masks
                 if (r > 0 && st[q].active && c < nchunks && (P[c] != sP[c] || K0[c] != sK0[c] || K1[c] != sK1[c])) return -1;
-                if (r == 0) { st[q].active = false; st[q].finished = false; st[q].pend_a = -1; st[q].pend_k = K_NONE; }
-                any |= walk_chunk<T>(q, r, nchunks, n, y, stv, lamf, div, st[q], m);
+                if (r == 0) { st[q].active = false; st[q].finished = false; st[q].pend_a = -1; st[q].pend_k = K_NONE;
+                              any |= walk_chunk<T, true>(q, 0, nchunks, n, y, stv, lamf, div, st[q], m); }
+                else any |= walk_chunk<T, false>(q, r, nchunks, n, y, stv, lamf, div, st[q], m);
             }
             if (bad) return -2;
             if (!any) break;
         }
         if (rounds_out) *rounds_out = r;
-        fill_carry_seq(nchunks, m, carry.data());
-        for (int j = 0; j < n; j++) {
-            int a = seg_start_of(j, m, carry.data());
-            x[j] = apply_out<T>(out_op, ys[j], vs[a]);
+        for (int c = 0; c < nchunks; c++) cval[c] = x[carry_of(c, m)];           // gather phase (barrier after it)
+        for (int c = 0; c < nchunks; c++) {                                        // fill, one window at a time
+            T v[CH];
+            for (int b = 0; b < CH && c * CH + b < n; b++) {                       // all reads of the window ...
+                int sa = seg_start_in_chunk(c, b, m);
+                if (sa >= 0 && sa / CH != c) return -3;                            // ... stay inside the window
+                v[b] = sa >= 0 ? x[sa] : cval[c];
+            }
+            for (int b = 0; b < CH && c * CH + b < n; b++) x[c * CH + b] = apply_out<T>(out_op, ys[c * CH + b], v[b]);
         }
         return 0;
     };
@@ -69,4 +77,23 @@ extern "C" int emu_chunked_f64(const double* y, int n, double lam, const double*
 }
 extern "C" int emu_chunked_f32(const float* y, int n, float lam, const float* lamv, float* x, int out_op, int* rounds) {
     return emu<float>(y, n, lam, lamv, x, out_op, rounds);
+}
+// exactness of the reciprocal-table division against IEEE division: returns the number of mismatches
+extern "C" long emu_check_table_division(long reps_per_divisor, unsigned long long seed) {
+    std::vector<RcpPair<double>> rd(RCP_N); std::vector<RcpPair<float>> rf(RCP_N);
+    for (int d = 0; d < RCP_N; d++) { rd[d].r = d ? 1.0 / d : 0.0; rd[d].d = d; rf[d].r = d ? 1.0f / d : 0.0f; rf[d].d = (float)d; }
+    RcpDiv<double> dd{rd.data()}; RcpDiv<float> df{rf.data()};
+    unsigned long long s = seed ? seed : 88172645463325252ULL; long bad = 0;
+    for (int d = 1; d < RCP_N; d++)
+        for (long k = 0; k < reps_per_divisor; k++) {
+            s ^= s << 13; s ^= s >> 7; s ^= s << 17;
+            double a; unsigned long long mant = (s & 0xFFFFFFFFFFFFFULL) | ((unsigned long long)(1023 - 40 + (s >> 58) * 2) << 52);
+            memcpy(&a, &mant, 8); if (s & (1ULL << 57)) a = -a;
+            if (k % 3 == 1) { a = (double)(long long)(s >> 24) * d; if (k & 4) a = nextafter(a, (k & 8) ? 1e300 : -1e300); }
+            if (dd(a, d) != a / d) bad++;
+            float af = (float)a;
+            if (k % 3 == 1) af = (float)((s >> 44) * (unsigned long long)d);
+            if (df(af, d) != af / (float)d) bad++;
+        }
+    return bad;
 }

@@ -27,6 +27,7 @@ def emu():
                                "-Xcompiler", "-fPIC,-ffp-contract=off", "-shared", "-x", "cu", src, "-o", so])
     lib = C.CDLL(so)
     lib.emu_chunked_f64.argtypes = [dp, C.c_int, C.c_double, dp, dp, C.c_int, C.POINTER(C.c_int)]
+    lib.emu_check_table_division.argtypes = [C.c_long, C.c_ulonglong]; lib.emu_check_table_division.restype = C.c_long
 
     def run(y, lam, w=None, out_op=0):
         y = np.ascontiguousarray(y, dtype=np.float64); x = np.empty_like(y); r = C.c_int(0)
@@ -34,8 +35,9 @@ def emu():
         if w is not None:
             w = np.ascontiguousarray(w, dtype=np.float64); wp = w.ctypes.data_as(dp)
         rc = lib.emu_chunked_f64(y.ctypes.data_as(dp), y.size, float(lam), wp, x.ctypes.data_as(dp), out_op, C.byref(r))
-        assert rc == 0, "emulated round read a mask written in the same round (race)"
+        assert rc == 0, "emulated CTA broke the barrier discipline (rc=%d)" % rc
         return x, r.value
+    run.lib = lib
     return run
 
 
@@ -87,3 +89,8 @@ def test_typical_data_needs_one_round(emu):
     y = O.gen_cfg2(4096, 4, seed=1)[:, 0]
     _, r = emu(y, 0.2)
     assert r <= 3
+
+
+def test_table_division_is_exact(emu):
+    """q = a*r ; q' = fma(fma(-q, d, a), r, q) with r = RN(1/d) must equal IEEE a/d for every table divisor (f64 and f32)."""
+    assert emu.lib.emu_check_table_division(200000, 12345) == 0
