@@ -41,6 +41,10 @@ struct ChunkMasks { uint32_t* P; uint32_t* K0; uint32_t* K1; };     // one word 
 
 template <typename T> struct alignas(2 * sizeof(T)) RcpPair { T r, d; };     // (1/d correctly rounded, d)
 
+// out-of-line IEEE division for divisors beyond the table (rare: a segment longer than RCP_N samples is being built);
+// must not be inlined or the compiler evaluates it speculatively on the hot path
+template <typename T> __host__ __device__ __noinline__ T slow_div(T a, int d) { return a / T(d); }
+
 // exact a / d for integer d >= 1
 template <typename T> struct RcpDiv {
     const RcpPair<T>* tbl;
@@ -50,7 +54,7 @@ template <typename T> struct RcpDiv {
             const T q = a * e.r;
             return fma(fma(-q, e.d, a), e.r, q);
         }
-        return a / T(d);
+        return slow_div<T>(a, d);
     }
 };
 
@@ -103,22 +107,28 @@ PTV_HD bool walk_chunk(int q, int round, int nchunks, int n, LdY y, StV stv, Lam
     bool merged = false; int mbit = 0;
     for (;;) {
         int k, f, a; T v;
-        if (st.s.i < n - 1) {
-            // ---- regular step (taut_scan.cuh Scan::step, i < n-1 branch) with the break handled in place ----
-            Scan<T>& s = st.s;
-            const int i = s.i;
+        Scan<T>& s = st.s;
+        const int i = s.i;
+        const int d = i - s.last;
+        if (i < n - 1 && d < RCP_N) {
+            // ---- hot path: regular step (taut_scan.cuh Scan::step, i < n-1 branch), straight-line, break handled in place.
+            //      Both touch updates are computed unconditionally with the exact table division and selected. ----
             const T yi = y(i);
             const T li = lam(i);
+            const RcpPair<T> e = div.tbl[d];
             const T hlo = s.hlo + (s.lo - yi);
             const T hhi = s.hhi + (s.hi - yi);
             const bool cbk = li < hlo;
             const bool fbk = !cbk && (-li > hhi);
             if (!(cbk | fbk)) {
-                const int d = i - s.last;
-                T hh = hhi, hl = hlo;
-                if (hhi >= li)  { s.hi = s.hi + div(li - hhi, d);  hh = li;  s.bhi = i; }
-                if (hlo <= -li) { s.lo = s.lo + div(-li - hlo, d); hl = -li; s.blo = i; }
-                s.hhi = hh; s.hlo = hl; s.i = i + 1;
+                const T nh = li - hhi, nl = -li - hlo;
+                const T qh0 = nh * e.r, ql0 = nl * e.r;
+                const T qh = fma(fma(-qh0, e.d, nh), e.r, qh0);      // == nh / d, correctly rounded
+                const T ql = fma(fma(-ql0, e.d, nl), e.r, ql0);      // == nl / d
+                const bool thi = hhi >= li, tlo = hlo <= -li;
+                s.hi = thi ? s.hi + qh : s.hi;  s.hhi = thi ? li : hhi;   s.bhi = thi ? i : s.bhi;
+                s.lo = tlo ? s.lo + ql : s.lo;  s.hlo = tlo ? -li : hlo;  s.blo = tlo ? i : s.blo;
+                s.i = i + 1;
                 continue;
             }
             a = (cbk ? s.blo : s.bhi) + 1;
@@ -138,13 +148,13 @@ PTV_HD bool walk_chunk(int q, int round, int nchunks, int n, LdY y, StV stv, Lam
             }
             s.last = a - 1; s.blo = s.bhi = a; s.i = a + 1;
             k = cbk ? K_CEIL : K_FLOOR;
-        } else if (st.s.i == n - 1) {              // closing sample: rare, generic code
+        } else if (i < n) {                        // closing sample, or a segment longer than the table: rare, generic code
             int l;
-            k = st.s.step(n, y, lam, f, l, v);
-            if (k == K_NONE) continue;             // i == n now: handled by the next iteration
+            k = s.step(n, y, lam, f, l, v);
+            if (k == K_NONE) continue;
             a = l + 1;
         } else {                                   // the fiber ended: value of the last open segment
-            stv(st.s.last + 1, st.s.lo);
+            stv(s.last + 1, s.lo);
             st.finished = true; st.pend_a = -1;
             break;
         }
@@ -156,7 +166,7 @@ PTV_HD bool walk_chunk(int q, int round, int nchunks, int n, LdY y, StV stv, Lam
             merged = true; mbit = bit; break;
         }
         const uint32_t mb = 1u << bit;
-        P |= mb; K0 |= (kk & 1) ? mb : 0u; K1 |= (kk >> 1) ? mb : 0u;
+        P |= mb; K0 |= (uint32_t)(kk & 1) << bit; K1 |= (uint32_t)(kk >> 1) << bit;
     }
     if (merged) {
         const uint32_t keep = ~0u << mbit;

@@ -43,6 +43,18 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// shared-memory sample load through a 32-bit shared-window address held in a register
+template <typename T> struct SmemLd32 {
+    uint32_t base;
+    __device__ __forceinline__ T operator()(int j) const;
+};
+template <> __device__ __forceinline__ double SmemLd32<double>::operator()(int j) const {
+    double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(base + (uint32_t)((j + ((j >> 5) << 1)) << 3)) : "memory"); return v;
+}
+template <> __device__ __forceinline__ float SmemLd32<float>::operator()(int j) const {
+    float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(base + (uint32_t)((j + ((j >> 5) << 2)) << 2)) : "memory"); return v;
+}
+
 template <typename T> struct GlobSt {            // sparse value store = the fiber's own output row (see chunk_core.cuh)
     T* p;
     __device__ __forceinline__ void operator()(int j, T v) const { p[j] = v; }
@@ -101,7 +113,7 @@ __global__ void k_prox_chunked_contig(const T* __restrict__ A, const T* __restri
     const bool lane_ok = fb < nfib && q < nchunks;
     const int fbc = lane_ok ? fb : 0;
     ChunkMasks m{mk + (size_t)fbc * lpf, mk + (size_t)(fpb + fbc) * lpf, mk + (size_t)(2 * fpb + fbc) * lpf};
-    SmemLd<T> y{ys + (size_t)fbc * npad};
+    SmemLd32<T> y{smem_u32(ys + (size_t)fbc * npad)};
     T* xrow = X + (f0 + fbc) * (long long)n;
     GlobSt<T> stv{xrow};
     RcpDiv<T> div{rcp};
@@ -113,27 +125,41 @@ __global__ void k_prox_chunked_contig(const T* __restrict__ A, const T* __restri
         for (int r = 1; __syncthreads_or(act ? 1 : 0); r++)
             act = lane_ok ? walk_chunk<T, false>(q, r, nchunks, n, y, stv, lamf, div, st, m) : false;
     };
-    if (WEIGHTED) phases(ArrayLam<T, SmemLd<T>>{SmemLd<T>{wsm + (size_t)fbc * npad}});
+    if (WEIGHTED) phases(ArrayLam<T, SmemLd32<T>>{SmemLd32<T>{smem_u32(wsm + (size_t)fbc * npad)}});
     else phases(UniformLam<T>{lam});
 
     // ---- value of the segment entering each chunk (gathered before any output is written: the store is the output) ----
     if (lane_ok) cval[(size_t)fbc * lpf + q] = __ldcg(xrow + carry_of(q, m));
     __syncthreads();
 
-    // ---- fill: one 32-sample window per warp iteration; all sparse reads of the window, then its (coalesced) writes ----
+    // ---- fill: 32-sample windows, FW per warp at a time: all sparse reads of the batch (L2 round trips overlap), then its
+    //      coalesced writes.  Reads of a window only touch that window, so batching windows is hazard free. ----
+    constexpr int FW = 4;
     const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
-    for (int w = warp; w < nfib * nchunks; w += nwarps) {
-        const int fb2 = w / nchunks, c = w - fb2 * nchunks;
-        const int j = c * CH + lane;
+    const uint32_t below = 0xffffffffu >> (31 - lane);
+    for (int fb2 = 0; fb2 < nfib; fb2++) {
         T* xr = X + (f0 + fb2) * (long long)n;
-        ChunkMasks m2{mk + (size_t)fb2 * lpf, nullptr, nullptr};
-        T v = T(0);
-        if (j < n) {
-            const int sa = seg_start_in_chunk(c, lane, m2);
-            v = (sa >= 0) ? __ldcg(xr + sa) : cval[(size_t)fb2 * lpf + c];
+        const uint32_t* Pm = mk + (size_t)fb2 * lpf;
+        const T* cv = cval + (size_t)fb2 * lpf;
+        const T* yr = ys + (size_t)fb2 * npad;
+        for (int c0 = warp * FW; c0 < nchunks; c0 += nwarps * FW) {
+            T v[FW];
+#pragma unroll
+            for (int u = 0; u < FW; u++) {
+                const int c = c0 + u, j = (c << 5) + lane;
+                v[u] = T(0);
+                if (c < nchunks && j < n) {
+                    const uint32_t w = Pm[c] & below;
+                    v[u] = w ? __ldcg(xr + (c << 5) + high_bit(w)) : cv[c];
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int u = 0; u < FW; u++) {
+                const int c = c0 + u, j = (c << 5) + lane;
+                if (c < nchunks && j < n) xr[j] = apply_out<T>(out_op, yr[j + c * PADE], v[u]);
+            }
         }
-        __syncwarp();
-        if (j < n) xr[j] = apply_out<T>(out_op, ys[(size_t)fb2 * npad + j + (j >> 5) * PADE], v);
     }
 }
 
