@@ -76,7 +76,8 @@ int proxtv_device_count(void);                 /* usable CUDA devices (0 => ever
 const char *proxtv_last_error(void);           /* last error text of the calling thread ("" if none) */
 const char *proxtv_version(void);
 
-/* kernel family: 0 auto, 1 sequential lane-per-fiber, 2 chunked speculative.  Returns the previous value. */
+/* kernel family: 0 auto, 1 sequential lane-per-fiber, 2 chunked speculative, 3 chunked with direct strided staging.
+ * Returns the previous value. */
 int proxtv_set_engine(int engine);
 
 /* Batched 1D prox over the fibers of a column-major array: nf fibers of len samples, fiber j starting at

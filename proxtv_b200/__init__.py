@@ -21,11 +21,11 @@ __all__ = ["tv1_1d", "tv1w_1d", "tv1_2d", "tvgen", "tv1_1d_batched", "tv1w_1d_ba
            "set_engine", "ProxTVError"]
 
 _N_INFO = 3                      # prox_tv/__init__.py:67
-ENGINES = {"auto": 0, "seq": 1, "chunked": 2}
+ENGINES = {"auto": 0, "seq": 1, "chunked": 2, "chunked-strided": 3}
 
 
 def set_engine(name):
-    """Select the kernel family ('auto' | 'seq' | 'chunked'); returns the previous one."""
+    """Select the kernel family ('auto' | 'seq' | 'chunked' | 'chunked-strided'); returns the previous one."""
     prev = load().proxtv_set_engine(ENGINES[name])
     return [k for k, v in ENGINES.items() if v == prev][0]
 

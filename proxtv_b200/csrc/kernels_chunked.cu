@@ -61,7 +61,8 @@ template <typename T> struct GlobSt {            // sparse value store = the fib
 };
 
 template <typename T, bool WEIGHTED>
-__global__ void k_prox_chunked_contig(const T* __restrict__ A, const T* __restrict__ B, int in_op, T* __restrict__ X, int out_op,
+__global__ void k_prox_chunked_contig(const T* __restrict__ A, const T* __restrict__ B, const T* __restrict__ C, int in_op,
+                                      T* __restrict__ X, int out_op,
                                       long long nf, int n, T lam, const T* __restrict__ lamv, int lpf, int fpb, int npad, int use_tma) {
     __shared__ uint64_t mbar;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -138,7 +139,8 @@ __global__ void k_prox_chunked_contig(const T* __restrict__ A, const T* __restri
     const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
     const uint32_t below = 0xffffffffu >> (31 - lane);
     for (int fb2 = 0; fb2 < nfib; fb2++) {
-        T* xr = X + (f0 + fb2) * (long long)n;
+        const long long gb = (f0 + fb2) * (long long)n;
+        T* xr = X + gb;
         const uint32_t* Pm = mk + (size_t)fb2 * lpf;
         const T* cv = cval + (size_t)fb2 * lpf;
         const T* yr = ys + (size_t)fb2 * npad;
@@ -157,7 +159,7 @@ __global__ void k_prox_chunked_contig(const T* __restrict__ A, const T* __restri
 #pragma unroll
             for (int u = 0; u < FW; u++) {
                 const int c = c0 + u, j = (c << 5) + lane;
-                if (c < nchunks && j < n) xr[j] = apply_out<T>(out_op, yr[j + c * PADE], v[u]);
+                if (c < nchunks && j < n) xr[j] = apply_out_ex<T>(out_op, yr[j + c * PADE], v[u], A, B, C, gb + j);
             }
         }
     }
@@ -165,8 +167,8 @@ __global__ void k_prox_chunked_contig(const T* __restrict__ A, const T* __restri
 
 // Returns cudaErrorInvalidConfiguration if the fibers do not fit in shared memory (caller falls back to the sequential kernel).
 template <typename T>
-cudaError_t prox_fibers_chunked_contig(const T* A, const T* B, InOp op, T* X, int out_op, FiberGeom g, T lam, const T* lamv,
-                                       cudaStream_t st) {
+cudaError_t prox_fibers_chunked_contig(const T* A, const T* B, const T* C, InOp op, T* X, int out_op, FiberGeom g, T lam,
+                                       const T* lamv, cudaStream_t st) {
     if (g.inc != 1) return cudaErrorInvalidConfiguration;
     if (g.nf <= 0 || g.len <= 0) return cudaSuccess;
     const int n = g.len;
@@ -187,13 +189,163 @@ cudaError_t prox_fibers_chunked_contig(const T* A, const T* B, InOp op, T* X, in
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     // TMA staging needs 16-byte aligned rows: aligned base, row pitch a multiple of 16 bytes, single input array
     const int use_tma = (op == IN_A) && (((uintptr_t)A & 15) == 0) && (((size_t)n * sizeof(T)) % 16 == 0);
-    kern<<<blocks, threads, smem, st>>>(A, B, (int)op, X, out_op, g.nf, n, lam, lamv, lpf, fpb, npad, use_tma);
+    kern<<<blocks, threads, smem, st>>>(A, B, C, (int)op, X, out_op, g.nf, n, lam, lamv, lpf, fpb, npad, use_tma);
     return cudaGetLastError();
 }
 
-template cudaError_t prox_fibers_chunked_contig<double>(const double*, const double*, InOp, double*, int, FiberGeom, double,
-                                                        const double*, cudaStream_t);
-template cudaError_t prox_fibers_chunked_contig<float>(const float*, const float*, InOp, float*, int, FiberGeom, float,
-                                                       const float*, cudaStream_t);
+template cudaError_t prox_fibers_chunked_contig<double>(const double*, const double*, const double*, InOp, double*, int, FiberGeom,
+                                                        double, const double*, cudaStream_t);
+template cudaError_t prox_fibers_chunked_contig<float>(const float*, const float*, const float*, InOp, float*, int, FiberGeom,
+                                                       float, const float*, cudaStream_t);
+
+// ------------------------------------------------------------------------------------------------------------------
+// k_prox_chunked_strided: fibers with element stride `inc` whose neighbours are adjacent in memory (every dimension but
+// the first of a column-major array).  A CTA takes FPB adjacent fibers: every global access then moves FPB*sizeof(T)
+// contiguous bytes per sample position (32 B = one DRAM sector for FPB = 4 doubles / 8 floats), and the staging loop
+// transposes on the fly into the same per-fiber padded rows the contiguous kernel uses, so the scan phases are shared.
+// No transposed copy of the array is ever made.  The fill can fuse the second half of a Douglas-Rachford iteration
+// (OUT_DR_ROWS*): it re-reads Y, s, t at the positions it writes; those lines were staged by this CTA moments ago and
+// the working set of all resident CTAs (< 60 MB) sits in the 126 MB L2.
+template <typename T> struct GlobStStrided {
+    T* p; long long inc;
+    __device__ __forceinline__ void operator()(int j, T v) const { p[(long long)j * inc] = v; }
+};
+
+template <typename T, int FPB>
+__global__ void __launch_bounds__(1024) k_prox_chunked_strided(const T* __restrict__ A, const T* __restrict__ B, const T* __restrict__ C,
+                                                           int in_op, T* __restrict__ X, int out_op, long long nf, int n, long long inc,
+                                                           T lam, int lpf, int npad, T* __restrict__ V) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    RcpPair<T>* rcp = reinterpret_cast<RcpPair<T>*>(smem_raw);
+    T* ys = reinterpret_cast<T*>(rcp + RCP_N);                    // [FPB][npad]
+    T* cval = ys + (size_t)FPB * npad;                            // [FPB][lpf]
+    uint32_t* mk = reinterpret_cast<uint32_t*>(cval + (size_t)FPB * lpf);      // [3][FPB][lpf]
+    constexpr int PADE = PadCfg<T>::PADE;
+    constexpr int CPW = 32 / FPB;                                 // sample positions one warp covers per access
+    const int tid = threadIdx.x;
+    const long long f0 = (long long)blockIdx.x * FPB;             // first fiber of the group (inc % FPB == 0: one slab)
+    const long long base0 = (f0 / inc) * inc * n + (f0 % inc);
+    const int nchunks = (n + CH - 1) / CH;
+
+    // ---- stage: thread (r, cc) reads fiber r at positions cc, cc + step, ...; FPB lanes share one sector ----
+    if (tid < RCP_N) { rcp[tid].r = tid ? T(1) / T(tid) : T(0); rcp[tid].d = T(tid); }
+    {
+        const int r = tid % FPB, cc = tid / FPB, step = blockDim.x / FPB;
+        T* row = ys + (size_t)r * npad;
+        constexpr int U = 8;                                      // loads in flight per thread and array
+        for (int k0 = cc; k0 < n; k0 += step * U) {
+            T a[U], b[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const int k = k0 + u * step;
+                const long long g = base0 + (long long)k * inc + r;
+                a[u] = (k < n) ? A[g] : T(0);
+                b[u] = (k < n && in_op != IN_A) ? B[g] : T(0);
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const int k = k0 + u * step;
+                T v = a[u];
+                if (in_op == IN_A_MINUS_B) v = v - b[u]; else if (in_op == IN_A_PLUS_B) v = v + b[u];
+                if (k < n) row[k + (k >> 5) * PADE] = v;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- scan (shared with the contiguous kernel) ----
+    const int fb = tid / lpf, q = tid - fb * lpf;
+    const bool lane_ok = fb < FPB && q < nchunks;
+    const int fbc = lane_ok ? fb : 0;
+    ChunkMasks m{mk + (size_t)fbc * lpf, mk + (size_t)(FPB + fbc) * lpf, mk + (size_t)(2 * FPB + fbc) * lpf};
+    SmemLd32<T> y{smem_u32(ys + (size_t)fbc * npad)};
+    // sparse value store: a contiguous scratch row per fiber (V, [fiber][n]) when the caller provides one -- the values are
+    // written and read back by this CTA only, so a dense row keeps them in a handful of L2 lines -- else the output itself
+    T* xfib = V ? V + (f0 + fbc) * (long long)n : X + base0 + fbc;
+    const long long vinc = V ? 1 : inc;
+    GlobStStrided<T> stv{xfib, vinc};
+    RcpDiv<T> div{rcp};
+    LaneState<T> st;
+    st.active = false; st.finished = false; st.pend_a = -1; st.pend_k = K_NONE;
+    UniformLam<T> lamf{lam};
+    {
+        bool act = lane_ok ? walk_chunk<T, true>(q, 0, nchunks, n, y, stv, lamf, div, st, m) : false;
+        for (int r = 1; __syncthreads_or(act ? 1 : 0); r++)
+            act = lane_ok ? walk_chunk<T, false>(q, r, nchunks, n, y, stv, lamf, div, st, m) : false;
+    }
+    if (lane_ok) cval[(size_t)fbc * lpf + q] = __ldcg(xfib + (long long)carry_of(q, m) * vinc);
+    __syncthreads();
+
+    // ---- fill: a warp takes one 32-sample window of all FPB fibers: FPB accesses of CPW positions x FPB fibers each; all
+    //      sparse reads of the window first, then its writes (FPB*sizeof(T)-byte pieces, sector aligned) ----
+    const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+    const int r = lane % FPB, jj = lane / FPB;
+    const uint32_t* Pm = mk + (size_t)r * lpf;
+    const T* cv = cval + (size_t)r * lpf;
+    const T* yr = ys + (size_t)r * npad;
+    const T* vr = V ? V + (f0 + r) * (long long)n : X + base0 + r;
+    for (int c = warp; c < nchunks; c += nwarps) {
+        T v[FPB];
+        const uint32_t pw = Pm[c];
+#pragma unroll
+        for (int u = 0; u < FPB; u++) {
+            const int b = u * CPW + jj, k = (c << 5) + b;
+            v[u] = T(0);
+            if (k < n) {
+                const uint32_t w = pw & (0xffffffffu >> (31 - b));
+                v[u] = w ? __ldcg(vr + (long long)((c << 5) + high_bit(w)) * vinc) : cv[c];
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int u = 0; u < FPB; u++) {
+            const int b = u * CPW + jj, k = (c << 5) + b;
+            if (k < n) {
+                const long long g = base0 + (long long)k * inc + r;
+                X[g] = apply_out_ex<T>(out_op, yr[k + c * PADE], v[u], A, B, C, g);
+            }
+        }
+    }
+}
+
+template <typename T, int FPB>
+static cudaError_t launch_strided(const T* A, const T* B, const T* C, InOp op, T* X, int out_op, FiberGeom g, T lam, T* V, cudaStream_t st) {
+    const int n = g.len;
+    const int lpf = (n + CH - 1) / CH;
+    const int npad = (n + (lpf + 1) * PadCfg<T>::PADE + PadCfg<T>::PADE - 1) / PadCfg<T>::PADE * PadCfg<T>::PADE;
+    const size_t smem = (size_t)FPB * ((size_t)npad * sizeof(T) + (size_t)lpf * (12 + sizeof(T))) + RCP_N * 2 * sizeof(T) + 16;
+    const int threads = ((FPB * lpf + 31) / 32) * 32;
+    if (smem > 220 * 1024 || threads > 1024 || g.inc % FPB != 0 || g.nf % FPB != 0) return cudaErrorInvalidConfiguration;
+    auto kern = k_prox_chunked_strided<T, FPB>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    kern<<<(unsigned)(g.nf / FPB), threads < RCP_N ? RCP_N : threads, smem, st>>>(A, B, C, (int)op, X, out_op, g.nf, n, g.inc, lam, lpf, npad, V);
+    return cudaGetLastError();
+}
+
+// Returns cudaErrorInvalidConfiguration when the shape does not suit this kernel (caller falls back).
+template <typename T>
+cudaError_t prox_fibers_chunked_strided(const T* A, const T* B, const T* C, InOp op, T* X, int out_op, FiberGeom g, T lam, T* V,
+                                        cudaStream_t st) {
+    if (g.inc <= 1) return cudaErrorInvalidConfiguration;
+    if (g.nf <= 0 || g.len <= 0) return cudaSuccess;
+    constexpr int SECT = 32 / (int)sizeof(T);        // fibers per 32-byte sector: 4 doubles, 8 floats
+    // Group width: as wide as possible while at least three CTAs stay resident per SM (the kernel is latency/issue bound,
+    // not bandwidth bound, so occupancy beats access width); half a sector per access is the floor -- the neighbouring CTA
+    // takes the other half at the same time and finds it in L2.
+    const int lpf = (g.len + CH - 1) / CH;
+    const size_t per_fiber = (size_t)(g.len + (lpf + 2) * PadCfg<T>::PADE) * sizeof(T) + (size_t)lpf * (12 + sizeof(T));
+    const size_t budget = 72 * 1024;
+    cudaError_t e = cudaErrorInvalidConfiguration;
+    if (per_fiber * 4 * SECT <= budget) e = launch_strided<T, 4 * SECT>(A, B, C, op, X, out_op, g, lam, V, st);
+    if (e == cudaErrorInvalidConfiguration && per_fiber * 2 * SECT <= budget) { cudaGetLastError(); e = launch_strided<T, 2 * SECT>(A, B, C, op, X, out_op, g, lam, V, st); }
+    if (e == cudaErrorInvalidConfiguration && per_fiber * SECT <= budget) { cudaGetLastError(); e = launch_strided<T, SECT>(A, B, C, op, X, out_op, g, lam, V, st); }
+    if (e == cudaErrorInvalidConfiguration) { cudaGetLastError(); e = launch_strided<T, SECT / 2>(A, B, C, op, X, out_op, g, lam, V, st); }
+    if (e == cudaErrorInvalidConfiguration) { cudaGetLastError(); e = launch_strided<T, SECT>(A, B, C, op, X, out_op, g, lam, V, st); }
+    return e;
+}
+template cudaError_t prox_fibers_chunked_strided<double>(const double*, const double*, const double*, InOp, double*, int, FiberGeom, double, double*, cudaStream_t);
+template cudaError_t prox_fibers_chunked_strided<float>(const float*, const float*, const float*, InOp, float*, int, FiberGeom, float, float*, cudaStream_t);
 
 }  // namespace ptv

@@ -10,7 +10,7 @@
 namespace ptv {
 
 template <typename T, bool WEIGHTED>
-__global__ void __launch_bounds__(32) k_prox_seq(const T* __restrict__ A, const T* __restrict__ B, int op, T* __restrict__ X,
+__global__ void __launch_bounds__(32) k_prox_seq(const T* __restrict__ A, const T* __restrict__ B, const T* __restrict__ C, int op, T* __restrict__ X,
                                                  int out_op, FiberGeom g, T lam, const T* __restrict__ lamv,
                                                  const int* __restrict__ list, long long nlist) {
     long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -32,13 +32,13 @@ __global__ void __launch_bounds__(32) k_prox_seq(const T* __restrict__ A, const 
         while (s.i < n) {
             int k = s.step(n, y, lamf, f, l, v);
             if (k != K_NONE)
-                for (int q = f; q <= l; q++) X[base + (long long)q * inc] = out_op ? apply_out<T>(out_op, y(q), v) : v;
+                for (int q = f; q <= l; q++) { const long long g2 = base + (long long)q * inc; X[g2] = out_op ? apply_out_ex<T>(out_op, y(q), v, A, B, C, g2) : v; }
         }
-        for (int q = s.last + 1; q < n; q++) X[base + (long long)q * inc] = out_op ? apply_out<T>(out_op, y(q), s.lo) : s.lo;
+        for (int q = s.last + 1; q < n; q++) { const long long g2 = base + (long long)q * inc; X[g2] = out_op ? apply_out_ex<T>(out_op, y(q), s.lo, A, B, C, g2) : s.lo; }
     };
     if (n <= 0) return;
     if (WEIGHTED) {
-        if (n == 1) { X[base] = apply_out<T>(out_op, y(0), y(0)); return; }     // the reference reads lambda[0] out of bounds here; identity is the limit
+        if (n == 1) { X[base] = apply_out_ex<T>(out_op, y(0), y(0), A, B, C, base); return; }     // the reference reads lambda[0] out of bounds here; identity is the limit
         auto ld = [&](int i) -> T { return lamv[wbase + (long long)i * inc]; };
         run(ArrayLam<T, decltype(ld)>{ld});
     } else {
@@ -75,19 +75,19 @@ template cudaError_t prox_const_fibers<double>(const double*, long long, int, in
 template cudaError_t prox_const_fibers<float>(const float*, long long, int, int, float, float*, cudaStream_t);
 
 template <typename T>
-cudaError_t prox_fibers_seq(const T* A, const T* B, InOp op, T* X, int out_op, FiberGeom g, T lam, const T* lamv, const int* list,
-                            long long nlist, cudaStream_t st) {
+cudaError_t prox_fibers_seq(const T* A, const T* B, const T* C, InOp op, T* X, int out_op, FiberGeom g, T lam, const T* lamv,
+                            const int* list, long long nlist, cudaStream_t st) {
     long long cnt = list ? nlist : g.nf;
     if (cnt <= 0 || g.len <= 0) return cudaSuccess;
     unsigned blocks = (unsigned)((cnt + 31) / 32);
-    if (lamv) k_prox_seq<T, true><<<blocks, 32, 0, st>>>(A, B, (int)op, X, out_op, g, lam, lamv, list, nlist);
-    else      k_prox_seq<T, false><<<blocks, 32, 0, st>>>(A, B, (int)op, X, out_op, g, lam, lamv, list, nlist);
+    if (lamv) k_prox_seq<T, true><<<blocks, 32, 0, st>>>(A, B, C, (int)op, X, out_op, g, lam, lamv, list, nlist);
+    else      k_prox_seq<T, false><<<blocks, 32, 0, st>>>(A, B, C, (int)op, X, out_op, g, lam, lamv, list, nlist);
     return cudaGetLastError();
 }
 
-template cudaError_t prox_fibers_seq<double>(const double*, const double*, InOp, double*, int, FiberGeom, double, const double*,
+template cudaError_t prox_fibers_seq<double>(const double*, const double*, const double*, InOp, double*, int, FiberGeom, double, const double*,
                                              const int*, long long, cudaStream_t);
-template cudaError_t prox_fibers_seq<float>(const float*, const float*, InOp, float*, int, FiberGeom, float, const float*,
+template cudaError_t prox_fibers_seq<float>(const float*, const float*, const float*, InOp, float*, int, FiberGeom, float, const float*,
                                             const int*, long long, cudaStream_t);
 
 }  // namespace ptv

@@ -27,6 +27,10 @@ KernelSpan::KernelSpan(int cls_, int nkernels, cudaStream_t st_) : cls(cls_), st
         cudaEventRecord(a, st);
     }
 }
+void KernelSpan::cancel() {
+    g_launches[cls].fetch_sub(1, std::memory_order_relaxed);
+    if (a) { std::lock_guard<std::mutex> lk(g_pm); g_pool.push_back(a); a = nullptr; }
+}
 KernelSpan::~KernelSpan() {
     if (a) {
         std::lock_guard<std::mutex> lk(g_pm);

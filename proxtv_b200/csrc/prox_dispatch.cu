@@ -1,49 +1,84 @@
 // prox_dispatch.cu -- chooses the kernel family for one batched 1D prox over the fibers of an array.
 //
-//   contiguous fibers (inc == 1), len >= 64, fits shared memory -> chunked speculative kernel (kernels_chunked.cu)
-//   strided fibers with scratch space                          -> gather (fused input op) + chunked kernel + scatter
-//   everything else (tiny fibers, weighted strided, no scratch, ENGINE_SEQ) -> sequential lane-per-fiber kernel
+//   contiguous fibers (inc == 1), len >= 64, fits shared memory  -> chunked speculative kernel, TMA staged
+//   strided fibers, inc divisible by a sector's worth of fibers   -> chunked kernel staging FPB adjacent fibers directly
+//   other strided shapes, with scratch                            -> gather (fused input op) + chunked kernel + scatter
+//   everything else (tiny fibers, weighted strided, ENGINE_SEQ)   -> sequential lane-per-fiber kernel
 #include "ptv_internal.h"
+#include "chunk_core.cuh"
 
 namespace ptv {
 
 template <typename T>
-cudaError_t prox_fibers_seq(const T* A, const T* B, InOp op, T* X, int out_op, FiberGeom g, T lam, const T* lamv, const int* list,
-                            long long nlist, cudaStream_t st);
+cudaError_t prox_fibers_seq(const T* A, const T* B, const T* C, InOp op, T* X, int out_op, FiberGeom g, T lam, const T* lamv,
+                            const int* list, long long nlist, cudaStream_t st);
 template <typename T>
-cudaError_t prox_fibers_chunked_contig(const T* A, const T* B, InOp op, T* X, int out_op, FiberGeom g, T lam, const T* lamv,
-                                       cudaStream_t st);
+cudaError_t prox_fibers_chunked_contig(const T* A, const T* B, const T* C, InOp op, T* X, int out_op, FiberGeom g, T lam,
+                                       const T* lamv, cudaStream_t st);
+template <typename T>
+cudaError_t prox_fibers_chunked_strided(const T* A, const T* B, const T* C, InOp op, T* X, int out_op, FiberGeom g, T lam, T* V,
+                                        cudaStream_t st);
 template <typename T> cudaError_t gather_fibers(const T* A, const T* B, InOp op, T* out, FiberGeom g, cudaStream_t st);
 template <typename T> cudaError_t scatter_fibers(const T* in, T* X, FiberGeom g, cudaStream_t st);
+template <typename T>
+cudaError_t scatter_fibers_ex(const T* in, const T* A, const T* B, const T* C, InOp op, int out_op, T* X, FiberGeom g, cudaStream_t st);
 
 template <typename T>
-cudaError_t prox_fibers(const T* A, const T* B, InOp op, T* X, int out_op, FiberGeom g, T lam, const T* lamv, Engine eng,
-                        T* scratch, cudaStream_t st) {
+cudaError_t prox_fibers_ex(const T* A, const T* B, const T* C, InOp op, T* X, int out_op, FiberGeom g, T lam, const T* lamv,
+                           Engine eng, T* scratch, cudaStream_t st) {
     if (g.nf <= 0 || g.len <= 0) return cudaSuccess;
     if (eng != ENGINE_SEQ && g.len >= 2 * 32) {
         if (g.inc == 1) {
             KernelSpan span(KC_PROX_CONTIG, 1, st);
-            cudaError_t e = prox_fibers_chunked_contig<T>(A, B, op, X, out_op, g, lam, lamv, st);
+            cudaError_t e = prox_fibers_chunked_contig<T>(A, B, C, op, X, out_op, g, lam, lamv, st);
             if (e != cudaErrorInvalidConfiguration) return e;
             cudaGetLastError();
-        } else if (scratch && !lamv && g.nf % g.inc == 0) {
-            const long long n = g.nf * (long long)g.len;
-            T* t1 = scratch; T* t2 = scratch + n;
-            const FiberGeom gc{g.nf, g.len, 1};
-            cudaError_t e;
-            { KernelSpan span(KC_ELEMENTWISE, 1, st); e = gather_fibers<T>(A, B, op, t1, g, st); }
-            if (e != cudaSuccess) return e;
-            { KernelSpan span(KC_PROX_STRIDED, 1, st); e = prox_fibers_chunked_contig<T>(t1, nullptr, IN_A, t2, out_op, gc, lam, nullptr, st); }
-            if (e == cudaSuccess) { KernelSpan span(KC_ELEMENTWISE, 1, st); return scatter_fibers<T>(t2, X, g, st); }
-            if (e != cudaErrorInvalidConfiguration) return e;
-            cudaGetLastError();
+        } else if (!lamv) {
+            // Strided fibers.  Default: tiled gather (input op fused) -> contiguous chunked kernel -> tiled scatter (output form
+            // fused).  The scan is compute bound (IPC-limited, ~35 us of HBM time per 225 us pass), so the two extra streaming
+            // kernels cost less than staging strided fibers directly at one CTA per SM; ENGINE_CHUNKED_STRIDED selects the
+            // direct kernel (no transposed copy, FPB adjacent fibers per CTA) for comparison and for callers without scratch.
+            const bool direct = (eng == ENGINE_CHUNKED_STRIDED) || !scratch || g.nf % g.inc != 0;
+            if (direct) {
+                KernelSpan span(KC_PROX_STRIDED, 1, st);
+                cudaError_t e = prox_fibers_chunked_strided<T>(A, B, C, op, X, out_op, g, lam,
+                                                               (scratch && eng == ENGINE_CHUNKED_STRIDED) ? scratch : nullptr, st);
+                if (e != cudaErrorInvalidConfiguration) return e;
+                cudaGetLastError();
+                span.cancel();
+            }
+            if (scratch && g.nf % g.inc == 0) {
+                const long long n = g.nf * (long long)g.len;
+                T* t1 = scratch; T* t2 = scratch + n;
+                const FiberGeom gc{g.nf, g.len, 1};
+                cudaError_t e;
+                { KernelSpan span(KC_ELEMENTWISE, 1, st); e = gather_fibers<T>(A, B, op, t1, g, st); }
+                if (e != cudaSuccess) return e;
+                { KernelSpan span(KC_PROX_STRIDED, 1, st);
+                  e = prox_fibers_chunked_contig<T>(t1, nullptr, nullptr, IN_A, t2, OUT_X, gc, lam, nullptr, st); }
+                if (e == cudaSuccess) {
+                    KernelSpan span(KC_ELEMENTWISE, 1, st);
+                    return out_op == OUT_X ? scatter_fibers<T>(t2, X, g, st) : scatter_fibers_ex<T>(t2, A, B, C, op, out_op, X, g, st);
+                }
+                if (e != cudaErrorInvalidConfiguration) return e;
+                cudaGetLastError();
+            }
         }
     }
     KernelSpan span(g.inc == 1 ? KC_PROX_CONTIG : KC_PROX_STRIDED, 1, st);
-    return prox_fibers_seq<T>(A, B, op, X, out_op, g, lam, lamv, nullptr, 0, st);
+    return prox_fibers_seq<T>(A, B, C, op, X, out_op, g, lam, lamv, nullptr, 0, st);
 }
 
-template cudaError_t prox_fibers<double>(const double*, const double*, InOp, double*, int, FiberGeom, double, const double*, Engine, double*, cudaStream_t);
-template cudaError_t prox_fibers<float>(const float*, const float*, InOp, float*, int, FiberGeom, float, const float*, Engine, float*, cudaStream_t);
+template <typename T>
+cudaError_t prox_fibers(const T* A, const T* B, InOp op, T* X, int out_op, FiberGeom g, T lam, const T* lamv, Engine eng,
+                        T* scratch, cudaStream_t st) {
+    return prox_fibers_ex<T>(A, B, nullptr, op, X, out_op, g, lam, lamv, eng, scratch, st);
+}
+
+#define INST(T) \
+    template cudaError_t prox_fibers_ex<T>(const T*, const T*, const T*, InOp, T*, int, FiberGeom, T, const T*, Engine, T*, cudaStream_t); \
+    template cudaError_t prox_fibers<T>(const T*, const T*, InOp, T*, int, FiberGeom, T, const T*, Engine, T*, cudaStream_t);
+INST(double)
+INST(float)
 
 }  // namespace ptv

@@ -26,7 +26,7 @@ struct FiberGeom {
 enum InOp { IN_A = 0, IN_A_MINUS_B = 1, IN_A_PLUS_B = 2 };
 
 // Which kernel family prox_fibers() may use.
-enum Engine { ENGINE_AUTO = 0, ENGINE_SEQ = 1, ENGINE_CHUNKED = 2 };
+enum Engine { ENGINE_AUTO = 0, ENGINE_SEQ = 1, ENGINE_CHUNKED = 2, ENGINE_CHUNKED_STRIDED = 3 };
 
 struct ProxStats {           // filled asynchronously on the device; optional
     unsigned long long fallback_fibers;
@@ -39,12 +39,18 @@ template <typename T>
 cudaError_t prox_fibers(const T* A, const T* B, InOp op, T* X, int out_op, FiberGeom g, T lam, const T* lamv, Engine eng,
                         T* scratch /* 2 * nf * len elements, or nullptr */, cudaStream_t st);
 
+// Same, with a third array C for the fused Douglas-Rachford row pass (out_op 3 / 4, see OutOp in chunk_core.cuh).
+template <typename T>
+cudaError_t prox_fibers_ex(const T* A, const T* B, const T* C, InOp op, T* X, int out_op, FiberGeom g, T lam, const T* lamv,
+                           Engine eng, T* scratch, cudaStream_t st);
+
 // ---- launch accounting / event timing (profile.cu) ----
 enum KernelClass { KC_PROX_CONTIG = 0, KC_PROX_STRIDED = 1, KC_ELEMENTWISE = 2, KC_COUNT = 3 };
 struct KernelSpan {          // RAII: counts `nkernels` launches of class cls; when profiling is on, brackets them with events
     int cls; cudaStream_t st; cudaEvent_t a;
     KernelSpan(int cls, int nkernels, cudaStream_t st);
     ~KernelSpan();
+    void cancel();      // the bracketed launch did not happen: undo the count, drop the timing
 };
 void profile_enable(int on);
 void profile_reset();

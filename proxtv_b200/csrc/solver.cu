@@ -50,12 +50,12 @@ int dr2_device(size_t M, size_t N, int batch, int row_major, const T* Y, T w1, T
             PTV_TRY(ew_dr_reflect_bcast<T>(t, x, s, n, (long long)M * N, gc.len, gc.inc, st));
         } else
         PTV_TRY(prox_fibers<T>(t, nullptr, IN_A, s, 1 /*reflect: s = 2(t - prox) - t*/, gc, w1, nullptr, eng, scr, st));
-        PTV_TRY(prox_fibers<T>(Y, s, IN_A_MINUS_B, x, 0, gr, w2, nullptr, eng, scr, st));
-        PTV_TRY(ew_dr_combine_rows<T>(Y, s, x, t, n, st));
+        // second half fused into the row pass: in = Y - s ; tb = Y - (in - prox) ; tb = 2 tb - s ; t' = 0.5 (t + tb)
+        PTV_TRY(prox_fibers_ex<T>(Y, s, t, IN_A_MINUS_B, x, 3 /*OUT_DR_ROWS*/, gr, w2, nullptr, eng, scr, st));
+        { T* tmp = t; t = x; x = tmp; }                                       // t' was written to x: ping-pong
     }
     PTV_TRY(prox_fibers<T>(t, nullptr, IN_A, s, 2 /*s = t - prox*/, gc, w1, nullptr, eng, scr, st));   // :427-430
-    PTV_TRY(prox_fibers<T>(Y, s, IN_A_MINUS_B, x, 0, gr, w2, nullptr, eng, scr, st));
-    PTV_TRY(ew_dr_final_rows<T>(Y, s, x, out, n, st));
+    PTV_TRY(prox_fibers_ex<T>(Y, s, nullptr, IN_A_MINUS_B, out, 4 /*OUT_DR_ROWS_FINAL*/, gr, w2, nullptr, eng, scr, st));
     if (info) { info[INFO_ITERS] = maxit; info[INFO_RC] = RC_OK; }            // :433-436 (INFO_GAP is left untouched)
     return 0;                                                                 // :440 (the reference returns 0 on success)
 }

@@ -7,6 +7,7 @@
 // This is the simple route for the strided direction while the scan itself is compute-bound; the tile kernel that stages
 // strided fibers directly (DESIGN.md "next") removes these two extra sweeps.
 #include "ptv_internal.h"
+#include "chunk_core.cuh"
 
 namespace ptv {
 
@@ -52,6 +53,47 @@ __global__ void k_scatter(const T* __restrict__ in, T* __restrict__ X, int len, 
         if (k < len && r < inc) X[o * slab + (long long)k * inc + r] = tile[tx][dy];
     }
 }
+
+// scatter with a fused output form: X[g] = apply_out_ex(out_op, in(g), x(g)) where in(g) = A[g] (op) B[g] is recomputed exactly as
+// the gather computed it, and x is the prox value coming back from the transposed layout.
+template <typename T>
+__global__ void k_scatter_ex(const T* __restrict__ in, const T* __restrict__ A, const T* __restrict__ B, const T* __restrict__ C, int op,
+                             int out_op, T* __restrict__ X, int len, long long inc) {
+    __shared__ T tile[32][33];
+    const long long o = blockIdx.z;
+    const long long slab = (long long)len * inc;
+    const long long r0 = (long long)blockIdx.x * 32;
+    const int k0 = blockIdx.y * 32;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    for (int dy = ty; dy < 32; dy += 8) {
+        const long long r = r0 + dy; const int k = k0 + tx;
+        if (k < len && r < inc) tile[dy][tx] = in[o * slab + r * len + k];
+    }
+    __syncthreads();
+    for (int dy = ty; dy < 32; dy += 8) {
+        const int k = k0 + dy; const long long r = r0 + tx;
+        if (k < len && r < inc) {
+            const long long g = o * slab + (long long)k * inc + r;
+            T yin = A[g];
+            if (op == IN_A_MINUS_B) yin = yin - B[g]; else if (op == IN_A_PLUS_B) yin = yin + B[g];
+            X[g] = apply_out_ex<T>(out_op, yin, tile[tx][dy], A, B, C, g);
+        }
+    }
+}
+template <typename T>
+cudaError_t scatter_fibers_ex(const T* in, const T* A, const T* B, const T* C, InOp op, int out_op, T* X, FiberGeom g, cudaStream_t st) {
+    if (g.nf <= 0 || g.len <= 0) return cudaSuccess;
+    const long long outer = g.nf / g.inc;
+    dim3 grid((unsigned)((g.inc + 31) / 32), (unsigned)((g.len + 31) / 32), 1), block(32, 8);
+    for (long long o0 = 0; o0 < outer; o0 += 65535) {
+        grid.z = (unsigned)((outer - o0) < 65535 ? (outer - o0) : 65535);
+        const long long off = o0 * (long long)g.len * g.inc;
+        k_scatter_ex<T><<<grid, block, 0, st>>>(in + off, A + off, B ? B + off : nullptr, C ? C + off : nullptr, (int)op, out_op, X + off, g.len, g.inc);
+    }
+    return cudaGetLastError();
+}
+template cudaError_t scatter_fibers_ex<double>(const double*, const double*, const double*, const double*, InOp, int, double*, FiberGeom, cudaStream_t);
+template cudaError_t scatter_fibers_ex<float>(const float*, const float*, const float*, const float*, InOp, int, float*, FiberGeom, cudaStream_t);
 
 template <typename T>
 cudaError_t gather_fibers(const T* A, const T* B, InOp op, T* out, FiberGeom g, cudaStream_t st) {

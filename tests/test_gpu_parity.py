@@ -17,7 +17,7 @@ from conftest import jumps, relerr
 from oracle import oracle as O
 
 pytestmark = pytest.mark.gpu
-ENGINES = ["seq", "auto"]
+ENGINES = ["seq", "auto", "chunked-strided"]
 
 
 @pytest.fixture(params=ENGINES)
