@@ -60,7 +60,25 @@ __global__ void k_prox_const_fiber(const T* __restrict__ c, long long c_stride, 
     s.begin(0, y, lamf);
     int f, l; T v;
     while (s.i < n) {
-        int k = s.step(n, y, lamf, f, l, v);
+        const int i = s.i, d = i - s.last;
+        if (i < n - 1 && d < 65536) {
+            // regular step with the division a/d done as a*r + Markstein correction (== IEEE a/d, see chunk_core.cuh); the
+            // reciprocal r = 1/d only depends on the loop counters, so its (IEEE) division is off the dependent chain --
+            // a constant fiber never breaks, d runs up to n, and two chained IEEE divisions per step were the whole cost.
+            const T dd = T(d), r = T(1) / dd;
+            const T hlo = s.hlo + (s.lo - cv), hhi = s.hhi + (s.hi - cv);
+            if (!(lam < hlo) && !(-lam > hhi)) {
+                const T nh = lam - hhi, nl = -lam - hlo;
+                const T qh0 = nh * r, ql0 = nl * r;
+                const T qh = fma(fma(-qh0, dd, nh), r, qh0), ql = fma(fma(-ql0, dd, nl), r, ql0);
+                const bool thi = hhi >= lam, tlo = hlo <= -lam;
+                s.hi = thi ? s.hi + qh : s.hi;  s.hhi = thi ? lam : hhi;   s.bhi = thi ? i : s.bhi;
+                s.lo = tlo ? s.lo + ql : s.lo;  s.hlo = tlo ? -lam : hlo;  s.blo = tlo ? i : s.blo;
+                s.i = i + 1;
+                continue;
+            }
+        }
+        int k = s.step(n, y, lamf, f, l, v);          // breaks (none expected on a constant fiber) and the closing sample
         if (k != K_NONE) for (int q = f; q <= l; q++) out[q] = v;
     }
     for (int q = s.last + 1; q < n; q++) out[q] = s.lo;
