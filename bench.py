@@ -34,6 +34,19 @@ B_PER_PIXEL_SOLVE = lambda b, maxit=35: b * (1 + 6 * maxit + 5)      # noqa: E73
 LAM = 0.2
 
 
+def ncu_traffic():
+    """dram__bytes_read + dram__bytes_write per launch of the dominant kernel, from the committed ncu --set full capture."""
+    try:
+        r = w = None
+        for line in open(os.path.join(ROOT, "profiles", "r1_contig_kernel_ncu_full.csv")):
+            p = line.strip().split(",")
+            if p[0] == "dram__bytes_read.sum": r = float(p[2]) * (1e6 if p[1] == "Mbyte" else 1e9 if p[1] == "Gbyte" else 1.0)
+            if p[0] == "dram__bytes_write.sum": w = float(p[2]) * (1e6 if p[1] == "Mbyte" else 1e9 if p[1] == "Gbyte" else 1.0)
+        return r + w if r is not None and w is not None else None
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -52,7 +65,7 @@ class ClockSampler:
     def start(self):
         try:
             self.f = open(self.path, "w")
-            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.index)], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:  # noqa: BLE001
             self.proc = None
@@ -172,7 +185,8 @@ def main():
         solve()
     barrier()
     assert info[2] == 0, "DR2_TV reported an error: " + ptv._lib.last_error()
-    lib.proxtv_profile_reset(); lib.proxtv_profile_enable(1)
+    # ---- timed region: exactly K steps, device-resident, CUDA events on the launching stream (launch counters only) ----
+    lib.proxtv_profile_reset()
     clocks = ClockSampler(local); clocks.start()
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     e0.record(st)
@@ -181,10 +195,19 @@ def main():
     e1.record(st)
     barrier()
     ms = e0.elapsed_time(e1)
-    clk = clocks.stop()
-    lib.proxtv_profile_enable(0)
     kms = (C.c_double * 3)(); kl = (C.c_longlong * 3)(); ks = (C.c_longlong * 3)()
     lib.proxtv_profile_read(kms, kl, ks)
+    launches_timed_region = int(sum(kl[i] for i in range(3)))
+    # ---- per-kernel timing for the roofline: K more steps with CUDA events around EVERY launch, on the serial schedule
+    #      (engine 'chunked': same kernels, no stream overlap) so that a launch's duration is the kernel's own ----
+    ptv.set_engine("chunked" if args.engine == "auto" else args.engine)
+    lib.proxtv_profile_reset(); lib.proxtv_profile_enable(1)
+    for _ in range(args.steps):
+        solve()
+    barrier()
+    lib.proxtv_profile_enable(0)
+    lib.proxtv_profile_read(kms, kl, ks)
+    ptv.set_engine(args.engine)
     tmax = torch.tensor([ms], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -210,6 +233,7 @@ def main():
     if world > 1:
         dist.all_reduce(et, op=dist.ReduceOp.MAX)
     e2e_value = world * M * M / (float(et.item()) / args.steps * 1e-3) / 1e6
+    clk = clocks.stop()
     res = np.ctypeslib.as_array(C.cast(hout, C.POINTER(C.c_double)), shape=(M * M,))
     same = bool(np.array_equal(res, out.cpu().numpy().ravel()))
     lib.proxtv_host_free(hin); lib.proxtv_host_free(hout)
@@ -218,9 +242,9 @@ def main():
         peak, peak_src = peaks()
         names = ["prox_contiguous_fibers", "prox_strided_fibers", "elementwise"]
         # algorithmic bytes per launch of each kernel class for this workload (DESIGN.md "Kernels"): f64 sweeps of the image
-        # v0 (unfused) : contiguous prox 1R+1W ; strided prox 2R+1W ; elementwise helpers 2R+1W .. 4R+1W (avg listed)
-        fused = bool(int(kl[2]) < 10 * args.steps)
-        sweeps = {0: 2.0, 1: 4.0 if fused else 3.0, 2: 3.5}
+        # both prox classes are the chunked scan kernel over one image-sized array (the strided pass scans the gathered
+        # copy): 1R + 1W = 2 sweeps per launch; the tiled gather (2R+1W) and scatter+combine (4R+1W) average 4 sweeps
+        sweeps = {0: 2.0, 1: 2.0, 2: 4.0}
         dom = int(np.argmax([kms[i] for i in range(3)]))
         avg_ms = kms[dom] / max(ks[dom], 1)
         ach = sweeps[dom] * M * M * 8 / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
@@ -233,14 +257,17 @@ def main():
                                    % (M, M, LAM), "engine": args.engine,
                        "l2": "working set 4 x %d MiB > 126 MB L2 (inputs larger than L2, no flush)" % (nbytes >> 20)},
             "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": ach, "peak": peak, "unit": "GB/s",
-                         "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": ach / peak, "traffic": ncu_traffic() if (dom == 0 and M == 4096) else None,
+                         "traffic_source": "profiles/r1_contig_kernel_ncu_full.csv (ncu --set full, same kernel and shape)",
+                         "algorithmic_bytes_per_launch": sweeps[dom] * M * M * 8, "peak_source": peak_src,
                          "avg_launch_ms": avg_ms, "launches_timed": int(ks[dom]),
+                         "timing_region": "%d additional steps right after the timed region, serial schedule, CUDA events around every launch" % args.steps,
                          "class_ms_per_step": {names[i]: kms[i] / args.steps for i in range(3)}},
             "roofline_solve": {"algorithmic_bytes": solve_bytes, "achieved": solve_bytes / (ms_step * 1e-3) / 1e9,
                                "peak": peak, "unit": "GB/s", "frac": solve_bytes / (ms_step * 1e-3) / 1e9 / peak},
             "e2e": {"value": e2e_value, "unit": "Mpixels/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
                     "api": "DR2_TV() C ABI, pinned host buffers", "matches_device_path": same},
-            "gpu_launches": int(sum(kl[i] for i in range(3))),
+            "gpu_launches": launches_timed_region,
             "clocks": clk,
         }
         if world == 1 and not args.no_cpu_baseline:

@@ -147,7 +147,13 @@ PTV_HD bool walk_chunk(int q, int round, int nchunks, int n, LdY y, StV stv, Lam
                 s.hhi = lq; s.hlo = -lq;
             }
             s.last = a - 1; s.blo = s.bhi = a; s.i = a + 1;
-            k = cbk ? K_CEIL : K_FLOOR;
+            // the finished segment [f, a-1] has value v; a new one starts at a, kind CEIL (cbk) or FLOOR (kind bit 0 set)
+            stv(f, v);
+            if (a >= ce) { st.pend_a = a; st.pend_k = cbk ? K_CEIL : K_FLOOR; break; }
+            const uint32_t mb = 1u << (a - cb);
+            if (!ROUND0 && (oP & mb) && !(oK1 & mb) && (((oK0 & mb) != 0u) == fbk)) { merged = true; mbit = a - cb; break; }
+            P |= mb; K0 |= fbk ? mb : 0u;
+            continue;
         } else if (i < n) {                        // closing sample, or a segment longer than the table: rare, generic code
             int l;
             k = s.step(n, y, lam, f, l, v);

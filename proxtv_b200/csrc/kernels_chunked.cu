@@ -55,13 +55,19 @@ template <> __device__ __forceinline__ float SmemLd32<float>::operator()(int j) 
     float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(base + (uint32_t)((j + ((j >> 5) << 2)) << 2)) : "memory"); return v;
 }
 
+// make a kernel parameter an opaque register value: stops the compiler from re-loading it from the constant bank inside the
+// scan loop (each reload costs an LDC plus its latency on the dependent compare)
+__device__ __forceinline__ double in_register(double v) { asm volatile("" : "+d"(v)); return v; }
+__device__ __forceinline__ float in_register(float v) { asm volatile("" : "+f"(v)); return v; }
+__device__ __forceinline__ int in_register(int v) { asm volatile("" : "+r"(v)); return v; }
+
 template <typename T> struct GlobSt {            // sparse value store = the fiber's own output row (see chunk_core.cuh)
     T* p;
     __device__ __forceinline__ void operator()(int j, T v) const { p[j] = v; }
 };
 
-template <typename T, bool WEIGHTED>
-__global__ void k_prox_chunked_contig(const T* __restrict__ A, const T* __restrict__ B, const T* __restrict__ C, int in_op,
+template <typename T, bool WEIGHTED, int MAXT>
+__global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 2 : 1) k_prox_chunked_contig(const T* __restrict__ A, const T* __restrict__ B, const T* __restrict__ C, int in_op,
                                       T* __restrict__ X, int out_op,
                                       long long nf, int n, T lam, const T* __restrict__ lamv, int lpf, int fpb, int npad, int use_tma) {
     __shared__ uint64_t mbar;
@@ -121,13 +127,14 @@ __global__ void k_prox_chunked_contig(const T* __restrict__ A, const T* __restri
     LaneState<T> st;
     st.active = false; st.finished = false; st.pend_a = -1; st.pend_k = K_NONE;
 
+    const int nreg = in_register(n);
     auto phases = [&](auto lamf) {
-        bool act = lane_ok ? walk_chunk<T, true>(q, 0, nchunks, n, y, stv, lamf, div, st, m) : false;
+        bool act = lane_ok ? walk_chunk<T, true>(q, 0, nchunks, nreg, y, stv, lamf, div, st, m) : false;
         for (int r = 1; __syncthreads_or(act ? 1 : 0); r++)
-            act = lane_ok ? walk_chunk<T, false>(q, r, nchunks, n, y, stv, lamf, div, st, m) : false;
+            act = lane_ok ? walk_chunk<T, false>(q, r, nchunks, nreg, y, stv, lamf, div, st, m) : false;
     };
     if (WEIGHTED) phases(ArrayLam<T, SmemLd32<T>>{SmemLd32<T>{smem_u32(wsm + (size_t)fbc * npad)}});
-    else phases(UniformLam<T>{lam});
+    else phases(UniformLam<T>{in_register(lam)});
 
     // ---- value of the segment entering each chunk (gathered before any output is written: the store is the output) ----
     if (lane_ok) cval[(size_t)fbc * lpf + q] = __ldcg(xrow + carry_of(q, m));
@@ -183,7 +190,9 @@ cudaError_t prox_fibers_chunked_contig(const T* A, const T* B, const T* C, InOp 
     int threads = ((fpb * lpf + 31) / 32) * 32;
     if (threads < RCP_N) threads = RCP_N;
     unsigned blocks = (unsigned)((g.nf + fpb - 1) / fpb);
-    auto kern = lamv ? k_prox_chunked_contig<T, true> : k_prox_chunked_contig<T, false>;
+    // small CTAs (<= 256 threads) get a register budget of up to 128/thread so loop constants stay in registers
+    auto kern = threads <= 256 ? (lamv ? k_prox_chunked_contig<T, true, 256> : k_prox_chunked_contig<T, false, 256>)
+                               : (lamv ? k_prox_chunked_contig<T, true, 1024> : k_prox_chunked_contig<T, false, 1024>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -267,11 +276,12 @@ __global__ void __launch_bounds__(1024) k_prox_chunked_strided(const T* __restri
     RcpDiv<T> div{rcp};
     LaneState<T> st;
     st.active = false; st.finished = false; st.pend_a = -1; st.pend_k = K_NONE;
-    UniformLam<T> lamf{lam};
+    UniformLam<T> lamf{in_register(lam)};
+    const int nreg = in_register(n);
     {
-        bool act = lane_ok ? walk_chunk<T, true>(q, 0, nchunks, n, y, stv, lamf, div, st, m) : false;
+        bool act = lane_ok ? walk_chunk<T, true>(q, 0, nchunks, nreg, y, stv, lamf, div, st, m) : false;
         for (int r = 1; __syncthreads_or(act ? 1 : 0); r++)
-            act = lane_ok ? walk_chunk<T, false>(q, r, nchunks, n, y, stv, lamf, div, st, m) : false;
+            act = lane_ok ? walk_chunk<T, false>(q, r, nchunks, nreg, y, stv, lamf, div, st, m) : false;
     }
     if (lane_ok) cval[(size_t)fbc * lpf + q] = __ldcg(xfib + (long long)carry_of(q, m) * vinc);
     __syncthreads();

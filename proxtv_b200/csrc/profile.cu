@@ -59,3 +59,10 @@ void profile_read(double* ms, long long* launches, long long* spans) {
 }
 
 }  // namespace ptv
+
+namespace ptv {
+// helpers for CUDA-graph replays (solver.cu): a replay launches the captured kernels without passing through KernelSpan
+bool profile_is_enabled() { return g_prof_on.load() != 0; }
+void profile_counters(long long* out) { for (int i = 0; i < KC_COUNT; i++) out[i] = g_launches[i].load(); }
+void profile_add(const long long* delta) { for (int i = 0; i < KC_COUNT; i++) g_launches[i].fetch_add(delta[i]); }
+}  // namespace ptv

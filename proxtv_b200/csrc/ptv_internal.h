@@ -55,6 +55,9 @@ struct KernelSpan {          // RAII: counts `nkernels` launches of class cls; w
 void profile_enable(int on);
 void profile_reset();
 void profile_read(double* ms, long long* launches, long long* spans);   // arrays of KC_COUNT
+bool profile_is_enabled();
+void profile_counters(long long* out);          // current launch counters (KC_COUNT)
+void profile_add(const long long* delta);       // account for a CUDA-graph replay
 
 // ---- elementwise helpers (elementwise.cu) ----
 template <typename T> cudaError_t ew_image_means_x2(const T* Y, long long per_image, int batch, T* t, double* scratch,

@@ -12,13 +12,16 @@
 namespace ptv {
 
 template <typename T>
-__global__ void k_gather(const T* __restrict__ A, const T* __restrict__ B, int op, T* __restrict__ out, int len, long long inc) {
+__global__ void k_gather(const T* __restrict__ A, const T* __restrict__ B, int op, T* __restrict__ out, int len, long long inc,
+                         int k_begin, int k_end) {
     __shared__ T tile[32][33];
     const long long o = blockIdx.z;
     const long long slab = (long long)len * inc;
     const long long r0 = (long long)blockIdx.x * 32;     // along inc (fiber index inside the slab)
-    const int k0 = blockIdx.y * 32;                      // along the fiber
+    const int k0 = k_begin + blockIdx.y * 32;            // along the fiber (restricted to [k_begin, k_end))
     const int tx = threadIdx.x, ty = threadIdx.y;        // 32 x 8
+    len = len < k_end ? len : k_end;
+    const int flen = (int)(slab / inc);
     for (int dy = ty; dy < 32; dy += 8) {
         const int k = k0 + dy; const long long r = r0 + tx;
         if (k < len && r < inc) {
@@ -31,7 +34,7 @@ __global__ void k_gather(const T* __restrict__ A, const T* __restrict__ B, int o
     __syncthreads();
     for (int dy = ty; dy < 32; dy += 8) {
         const long long r = r0 + dy; const int k = k0 + tx;
-        if (k < len && r < inc) out[o * slab + r * len + k] = tile[tx][dy];
+        if (k < len && r < inc) out[o * slab + r * flen + k] = tile[tx][dy];
     }
 }
 
@@ -58,21 +61,22 @@ __global__ void k_scatter(const T* __restrict__ in, T* __restrict__ X, int len, 
 // the gather computed it, and x is the prox value coming back from the transposed layout.
 template <typename T>
 __global__ void k_scatter_ex(const T* __restrict__ in, const T* __restrict__ A, const T* __restrict__ B, const T* __restrict__ C, int op,
-                             int out_op, T* __restrict__ X, int len, long long inc) {
+                             int out_op, T* __restrict__ X, int len, long long inc, long long r_begin, long long r_end) {
     __shared__ T tile[32][33];
     const long long o = blockIdx.z;
     const long long slab = (long long)len * inc;
-    const long long r0 = (long long)blockIdx.x * 32;
+    const long long r0 = r_begin + (long long)blockIdx.x * 32;
     const int k0 = blockIdx.y * 32;
     const int tx = threadIdx.x, ty = threadIdx.y;
+    const long long rlim = inc < r_end ? inc : r_end;
     for (int dy = ty; dy < 32; dy += 8) {
         const long long r = r0 + dy; const int k = k0 + tx;
-        if (k < len && r < inc) tile[dy][tx] = in[o * slab + r * len + k];
+        if (k < len && r < rlim) tile[dy][tx] = in[o * slab + r * len + k];
     }
     __syncthreads();
     for (int dy = ty; dy < 32; dy += 8) {
         const int k = k0 + dy; const long long r = r0 + tx;
-        if (k < len && r < inc) {
+        if (k < len && r < rlim) {
             const long long g = o * slab + (long long)k * inc + r;
             T yin = A[g];
             if (op == IN_A_MINUS_B) yin = yin - B[g]; else if (op == IN_A_PLUS_B) yin = yin + B[g];
@@ -88,7 +92,7 @@ cudaError_t scatter_fibers_ex(const T* in, const T* A, const T* B, const T* C, I
     for (long long o0 = 0; o0 < outer; o0 += 65535) {
         grid.z = (unsigned)((outer - o0) < 65535 ? (outer - o0) : 65535);
         const long long off = o0 * (long long)g.len * g.inc;
-        k_scatter_ex<T><<<grid, block, 0, st>>>(in + off, A + off, B ? B + off : nullptr, C ? C + off : nullptr, (int)op, out_op, X + off, g.len, g.inc);
+        k_scatter_ex<T><<<grid, block, 0, st>>>(in + off, A + off, B ? B + off : nullptr, C ? C + off : nullptr, (int)op, out_op, X + off, g.len, g.inc, 0, g.inc);
     }
     return cudaGetLastError();
 }
@@ -103,7 +107,7 @@ cudaError_t gather_fibers(const T* A, const T* B, InOp op, T* out, FiberGeom g, 
     for (long long o0 = 0; o0 < outer; o0 += 65535) {                // gridDim.z limit
         grid.z = (unsigned)((outer - o0) < 65535 ? (outer - o0) : 65535);
         const long long off = o0 * (long long)g.len * g.inc;
-        k_gather<T><<<grid, block, 0, st>>>(A + off, B ? B + off : nullptr, (int)op, out + off, g.len, g.inc);
+        k_gather<T><<<grid, block, 0, st>>>(A + off, B ? B + off : nullptr, (int)op, out + off, g.len, g.inc, 0, g.len);
     }
     return cudaGetLastError();
 }
@@ -119,6 +123,28 @@ cudaError_t scatter_fibers(const T* in, T* X, FiberGeom g, cudaStream_t st) {
     }
     return cudaGetLastError();
 }
+
+// sub-range forms for the pipelined Douglas-Rachford driver (single slab: g.nf == g.inc)
+template <typename T>
+cudaError_t gather_fibers_range(const T* A, const T* B, InOp op, T* out, FiberGeom g, int k_begin, int k_end, cudaStream_t st) {
+    if (k_end <= k_begin) return cudaSuccess;
+    dim3 grid((unsigned)((g.inc + 31) / 32), (unsigned)((k_end - k_begin + 31) / 32), 1), block(32, 8);
+    k_gather<T><<<grid, block, 0, st>>>(A, B, (int)op, out, g.len, g.inc, k_begin, k_end);
+    return cudaGetLastError();
+}
+template <typename T>
+cudaError_t scatter_fibers_ex_range(const T* in, const T* A, const T* B, const T* C, InOp op, int out_op, T* X, FiberGeom g,
+                                    long long r_begin, long long r_end, cudaStream_t st) {
+    if (r_end <= r_begin) return cudaSuccess;
+    dim3 grid((unsigned)((r_end - r_begin + 31) / 32), (unsigned)((g.len + 31) / 32), 1), block(32, 8);
+    k_scatter_ex<T><<<grid, block, 0, st>>>(in, A, B, C, (int)op, out_op, X, g.len, g.inc, r_begin, r_end);
+    return cudaGetLastError();
+}
+#define INST_R(T) \
+    template cudaError_t gather_fibers_range<T>(const T*, const T*, InOp, T*, FiberGeom, int, int, cudaStream_t); \
+    template cudaError_t scatter_fibers_ex_range<T>(const T*, const T*, const T*, const T*, InOp, int, T*, FiberGeom, long long, long long, cudaStream_t);
+INST_R(double)
+INST_R(float)
 
 template cudaError_t gather_fibers<double>(const double*, const double*, InOp, double*, FiberGeom, cudaStream_t);
 template cudaError_t gather_fibers<float>(const float*, const float*, InOp, float*, FiberGeom, cudaStream_t);

@@ -235,6 +235,21 @@ def test_torch_device_path(ptv, port):
     assert np.array_equal(ow[7], port.tv1_weighted(X[7], W[7]))
 
 
+def test_pipelined_schedule_equals_serial_schedule(ptv, port):
+    """Large single images take the pipelined Douglas-Rachford schedule (half-kernels on two streams, transposes overlapped);
+    it must give bit-identical results to the serial schedule (engine 'chunked') and match the oracle."""
+    Y = O.gen_cfg2(1024, 1536, seed=5)
+    a = ptv.tv1_2d(Y, 0.2)
+    prev = ptv.set_engine("chunked")
+    try:
+        b = ptv.tv1_2d(Y, 0.2)
+    finally:
+        ptv.set_engine(prev)
+    assert np.array_equal(a, b)
+    S = np.asfortranarray(Y[:, :1024])
+    assert relerr(ptv.tv1_2d(S, 0.2, max_iters=3), port.dr2_tv(S, 0.2, maxit=3)[0]) <= 1e-9
+
+
 def test_full_size_properties_cfg2(ptv, port):
     """BASELINE config 2 (4096 x 4096 f64, lam = 0.2) is too big for the oracle to finish in seconds (10 s with 8 threads);
     check size-independent properties instead: a sub-band of rows/cols against the oracle is impossible (2D coupling), so
