@@ -6,6 +6,8 @@
 // stores.  HBM traffic per launch: every input array read once, the output written once.
 #include "ptv_internal.h"
 #include "chunk_core.cuh"
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
 
 namespace ptv {
 
@@ -66,10 +68,14 @@ template <typename T> struct GlobSt {            // sparse value store = the fib
     __device__ __forceinline__ void operator()(int j, T v) const { p[j] = v; }
 };
 
-template <typename T, bool WEIGHTED, int MAXT>
+// CL: how the optional transposed second output X2 is produced.  0: plain 8-byte scattered stores (slow: partial-sector writes make
+// L2 read-modify-write every sector); >= 1: the finished fiber rows of CL consecutive CTAs (a thread-block cluster when CL > 1)
+// are exchanged through (distributed) shared memory so that fpb*CL adjacent fibers are written together as full 32-byte sectors.
+template <typename T, bool WEIGHTED, int MAXT, int CL>
 __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 2 : 1) k_prox_chunked_contig(const T* __restrict__ A, const T* __restrict__ B, const T* __restrict__ C, int in_op,
                                       T* __restrict__ X, int out_op,
-                                      long long nf, int n, T lam, const T* __restrict__ lamv, int lpf, int fpb, int npad, int use_tma) {
+                                      long long nf, int n, T lam, const T* __restrict__ lamv, int lpf, int fpb, int npad, int use_tma,
+                                      T* __restrict__ X2, long long inc2) {
     __shared__ uint64_t mbar;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RcpPair<T>* rcp = reinterpret_cast<RcpPair<T>*>(smem_raw);    // reciprocal table        [RCP_N]   (16-byte aligned)
@@ -148,9 +154,10 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 2 : 1) k_prox_chunked_cont
     for (int fb2 = 0; fb2 < nfib; fb2++) {
         const long long gb = (f0 + fb2) * (long long)n;
         T* xr = X + gb;
+        const long long x2b = X2 ? ((f0 + fb2) / inc2) * inc2 * n + (f0 + fb2) % inc2 : 0;
         const uint32_t* Pm = mk + (size_t)fb2 * lpf;
         const T* cv = cval + (size_t)fb2 * lpf;
-        const T* yr = ys + (size_t)fb2 * npad;
+        T* yr = ys + (size_t)fb2 * npad;
         for (int c0 = warp * FW; c0 < nchunks; c0 += nwarps * FW) {
             T v[FW];
 #pragma unroll
@@ -166,16 +173,41 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 2 : 1) k_prox_chunked_cont
 #pragma unroll
             for (int u = 0; u < FW; u++) {
                 const int c = c0 + u, j = (c << 5) + lane;
-                if (c < nchunks && j < n) xr[j] = apply_out_ex<T>(out_op, yr[j + c * PADE], v[u], A, B, C, gb + j);
+                if (c < nchunks && j < n) {
+                    const T o = apply_out_ex<T>(out_op, yr[j + c * PADE], v[u], A, B, C, gb + j);
+                    xr[j] = o;
+                    if (CL == 0) { if (X2) X2[x2b + (long long)j * inc2] = o; }      // scattered 8-byte stores
+                    else yr[j + c * PADE] = o;                                       // keep the finished row for the exchange
+                }
             }
         }
+    }
+    if (CL >= 1) {
+        // ---- transposed second output, assembled from the G = fpb*CL adjacent fibers of this CTA / cluster: each group of G
+        //      consecutive lanes writes G*sizeof(T) contiguous bytes (>= one full sector), positions split between the CTAs ----
+        cg::cluster_group cluster = cg::this_cluster();
+        __syncthreads();
+        if (CL > 1) cluster.sync();
+        const int rank = (CL > 1) ? (int)cluster.block_rank() : 0;
+        const int G = fpb * CL;
+        const long long fg0 = f0 - (long long)rank * fpb;                 // first fiber of the group
+        const long long x2g = (fg0 / inc2) * inc2 * n + fg0 % inc2;
+        const int jper = (n + CL - 1) / CL, jb = rank * jper, je = (jb + jper < n) ? jb + jper : n;
+        for (int e = tid; e < (je - jb) * G; e += blockDim.x) {
+            const int g2 = e % G, j = jb + e / G;
+            const int owner = g2 / fpb, fbl = g2 - owner * fpb;
+            const T* row = ys + (size_t)fbl * npad;
+            if (CL > 1 && owner != rank) row = cluster.map_shared_rank(row, owner);
+            X2[x2g + (long long)j * inc2 + g2] = row[j + (j >> 5) * PADE];
+        }
+        if (CL > 1) cluster.sync();                                       // nobody leaves while its rows may still be read
     }
 }
 
 // Returns cudaErrorInvalidConfiguration if the fibers do not fit in shared memory (caller falls back to the sequential kernel).
 template <typename T>
 cudaError_t prox_fibers_chunked_contig(const T* A, const T* B, const T* C, InOp op, T* X, int out_op, FiberGeom g, T lam,
-                                       const T* lamv, cudaStream_t st) {
+                                       const T* lamv, cudaStream_t st, T* X2, long long inc2) {
     if (g.inc != 1) return cudaErrorInvalidConfiguration;
     if (g.nf <= 0 || g.len <= 0) return cudaSuccess;
     const int n = g.len;
@@ -190,22 +222,42 @@ cudaError_t prox_fibers_chunked_contig(const T* A, const T* B, const T* C, InOp 
     int threads = ((fpb * lpf + 31) / 32) * 32;
     if (threads < RCP_N) threads = RCP_N;
     unsigned blocks = (unsigned)((g.nf + fpb - 1) / fpb);
-    // small CTAs (<= 256 threads) get a register budget of up to 128/thread so loop constants stay in registers
-    auto kern = threads <= 256 ? (lamv ? k_prox_chunked_contig<T, true, 256> : k_prox_chunked_contig<T, false, 256>)
-                               : (lamv ? k_prox_chunked_contig<T, true, 1024> : k_prox_chunked_contig<T, false, 1024>);
+    // TMA staging needs 16-byte aligned rows: aligned base, row pitch a multiple of 16 bytes, single input array
+    const int use_tma = (op == IN_A) && (((uintptr_t)A & 15) == 0) && (((size_t)n * sizeof(T)) % 16 == 0);
+    constexpr int SECT = 32 / (int)sizeof(T);                 // fibers per 32-byte sector
+    using KernT = void (*)(const T*, const T*, const T*, int, T*, int, long long, int, T, const T*, int, int, int, int, T*, long long);
+    KernT kern; int cl = 0;
+    if (X2 && !lamv && threads <= 256 && inc2 > 0) {
+        // sector-assembled transposed output: the CTA's own fibers suffice, or a cluster of SECT single-fiber CTAs
+        if (fpb % SECT == 0 && g.nf % fpb == 0 && inc2 % fpb == 0) { kern = k_prox_chunked_contig<T, false, 256, 1>; cl = 1; }
+        else if (fpb == 1 && g.nf % SECT == 0 && inc2 % SECT == 0) { kern = k_prox_chunked_contig<T, false, 256, SECT>; cl = SECT; }
+        else kern = k_prox_chunked_contig<T, false, 256, 0>;
+    } else {
+        // small CTAs (<= 256 threads) get a register budget of up to 128/thread so loop constants stay in registers
+        kern = threads <= 256 ? (lamv ? k_prox_chunked_contig<T, true, 256, 0> : k_prox_chunked_contig<T, false, 256, 0>)
+                              : (lamv ? k_prox_chunked_contig<T, true, 1024, 0> : k_prox_chunked_contig<T, false, 1024, 0>);
+    }
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    // TMA staging needs 16-byte aligned rows: aligned base, row pitch a multiple of 16 bytes, single input array
-    const int use_tma = (op == IN_A) && (((uintptr_t)A & 15) == 0) && (((size_t)n * sizeof(T)) % 16 == 0);
-    kern<<<blocks, threads, smem, st>>>(A, B, C, (int)op, X, out_op, g.nf, n, lam, lamv, lpf, fpb, npad, use_tma);
+    const long long inc2a = inc2 > 0 ? inc2 : 1;
+    if (cl > 1) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(blocks); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        const int in_op_i = (int)op; const int use_tma_i = use_tma;
+        return cudaLaunchKernelEx(&cfg, kern, A, B, C, in_op_i, X, out_op, g.nf, n, lam, lamv, lpf, fpb, npad, use_tma_i, X2, inc2a);
+    }
+    kern<<<blocks, threads, smem, st>>>(A, B, C, (int)op, X, out_op, g.nf, n, lam, lamv, lpf, fpb, npad, use_tma, X2, inc2a);
     return cudaGetLastError();
 }
 
 template cudaError_t prox_fibers_chunked_contig<double>(const double*, const double*, const double*, InOp, double*, int, FiberGeom,
-                                                        double, const double*, cudaStream_t);
+                                                        double, const double*, cudaStream_t, double*, long long);
 template cudaError_t prox_fibers_chunked_contig<float>(const float*, const float*, const float*, InOp, float*, int, FiberGeom,
-                                                       float, const float*, cudaStream_t);
+                                                       float, const float*, cudaStream_t, float*, long long);
 
 // ------------------------------------------------------------------------------------------------------------------
 // k_prox_chunked_strided: fibers with element stride `inc` whose neighbours are adjacent in memory (every dimension but

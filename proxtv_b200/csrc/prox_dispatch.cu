@@ -14,7 +14,7 @@ cudaError_t prox_fibers_seq(const T* A, const T* B, const T* C, InOp op, T* X, i
                             const int* list, long long nlist, cudaStream_t st);
 template <typename T>
 cudaError_t prox_fibers_chunked_contig(const T* A, const T* B, const T* C, InOp op, T* X, int out_op, FiberGeom g, T lam,
-                                       const T* lamv, cudaStream_t st);
+                                       const T* lamv, cudaStream_t st, T* X2 = nullptr, long long inc2 = 0);
 template <typename T>
 cudaError_t prox_fibers_chunked_strided(const T* A, const T* B, const T* C, InOp op, T* X, int out_op, FiberGeom g, T lam, T* V,
                                         cudaStream_t st);

@@ -27,7 +27,7 @@ static constexpr size_t SCRATCH_BYTES = (REDUCE_BLOCKS + 8) * sizeof(double);
 // Same kernels, same arithmetic, same results as the serial schedule; only the order of independent work changes.
 template <typename T>
 cudaError_t prox_fibers_chunked_contig(const T* A, const T* B, const T* C, InOp op, T* X, int out_op, FiberGeom g, T lam,
-                                       const T* lamv, cudaStream_t st);
+                                       const T* lamv, cudaStream_t st, T* X2 = nullptr, long long inc2 = 0);
 template <typename T> cudaError_t gather_fibers_range(const T* A, const T* B, InOp op, T* out, FiberGeom g, int k_begin, int k_end, cudaStream_t st);
 template <typename T>
 cudaError_t scatter_fibers_ex_range(const T* in, const T* A, const T* B, const T* C, InOp op, int out_op, T* X, FiberGeom g,
@@ -118,6 +118,9 @@ static int dr2_piped_body(size_t M, size_t N, const T* Y, T w1, T w2, T* out, in
 #undef BTRY
 }
 
+template <typename T>
+int dr2_tspace_body(size_t M, size_t N, int batch, const T* Y, T w1, T w2, T* out, int maxit, void* ws, double* scratch, cudaStream_t st);
+
 struct DrGraphKey {
     size_t tsize, M, N; const void* Y; void* out; void* ws; double w1, w2; int maxit;
     bool operator==(const DrGraphKey& o) const {
@@ -131,7 +134,7 @@ static DrGraph g_dr_graph;
 // ------------------------------------------------------------------------------------------------------------------
 template <typename T> size_t ws_bytes_dr2(size_t M, size_t N, int batch) {
     size_t n = M * N * (size_t)batch;
-    return 5 * align256(n * sizeof(T)) + SCRATCH_BYTES;
+    return 7 * align256(n * sizeof(T)) + SCRATCH_BYTES;      // plain schedule: t, s, x, 2 staging; T-space schedule: 7 arrays
 }
 
 template <typename T>
@@ -143,23 +146,31 @@ int dr2_device(size_t M, size_t N, int batch, int row_major, const T* Y, T w1, T
     T* t = (T*)w; w += align256(n * sizeof(T));
     T* s = (T*)w; w += align256(n * sizeof(T));
     T* x = (T*)w; w += align256(n * sizeof(T));
-    T* scr = (T*)w; w += 2 * align256(n * sizeof(T));      // gather/scatter staging of the strided pass
+    T* scr = (T*)w; w += 4 * align256(n * sizeof(T));      // gather/scatter staging of the strided pass (+2 arrays of the T-space schedule)
     double* scratch = (double*)w;
     if (maxit <= 0) maxit = MAX_ITERS_DR;                                     // TV2Dopt.cpp:387
     // first pass: fibers along axis 0 (length M); second pass: along axis 1 (length N) -- the order is part of the contract.
     // column-major: axis-0 fibers are contiguous, axis-1 fibers have stride M; row-major storage swaps the two roles.
     const FiberGeom gc = row_major ? FiberGeom{(long long)N * batch, (int)M, (long long)N} : FiberGeom{(long long)N * batch, (int)M, 1};
     const FiberGeom gr = row_major ? FiberGeom{(long long)M * batch, (int)N, 1} : FiberGeom{(long long)M * batch, (int)N, (long long)M};
-    // large single column-major image, fibers of both directions long enough for the chunked kernel: pipelined schedule
-    const bool piped = eng == ENGINE_AUTO && !row_major && batch == 1 && M >= 1024 && N >= 1024 && M % 2 == 0 && N % 2 == 0 &&
+    // Schedule.  AUTO (and ENGINE_PIPELINED): for a large single column-major image the gather/scatter schedule with the
+    // transposes issued on a separate high-priority stream; ENGINE_TSPACE: the transposeless T-space schedule (dr_tspace.cu: two
+    // kernels per iteration, each writing its result in both layouts -- measured slower on B200, 27.7 ms vs 21.9 ms per
+    // 4096x4096 f64 solve, kept for comparison); everything else: the plain serial schedule below.
+    // The whole solve is captured once into a CUDA graph and replayed while the call's arguments stay the same (no host
+    // launch latency); event timing of single launches needs plain launches, so profiling bypasses the graph.
+    const bool tspace = eng == ENGINE_TSPACE && !row_major && M >= 64 && N >= 64 && g_pipe.init();
+    const bool piped = (eng == ENGINE_AUTO || eng == ENGINE_PIPELINED) && !row_major && batch == 1 && M >= 1024 && N >= 1024 && M % 2 == 0 && N % 2 == 0 &&
                        (size_t)((M > N ? M : N) * sizeof(T)) <= 96 * 1024 && g_pipe.init();
-    if (!piped) PTV_TRY(ew_image_means_x2<T>(Y, (long long)M * N, batch, t, scratch, st));        // :390-395
-    if (piped) {
-        // The whole solve (mean, 36 pipelined iterations, ~290 kernels on three streams) is captured once into a CUDA graph
-        // and replayed while the call's arguments stay the same: replays have no host launch latency and no host-side
-        // cross-stream bookkeeping.  Event timing of single launches needs the plain path, so profiling bypasses the graph.
-        DrGraphKey key{sizeof(T), M, N, (const void*)Y, (void*)out, ws, (double)w1, (double)w2, maxit};
-        if (!profile_is_enabled() && g_pipe.sg) {
+    if (tspace || piped) {
+        auto body = [&](cudaStream_t bs) -> int {
+            return tspace ? dr2_tspace_body<T>(M, N, batch, Y, w1, w2, out, maxit, ws, scratch, bs)
+                          : dr2_piped_body<T>(M, N, Y, w1, w2, out, maxit, t, s, x, scr, scratch, gc, n, bs);
+        };
+        DrGraphKey key{sizeof(T) + (tspace ? 100u : 0u) + 1000u * (size_t)batch, M, N, (const void*)Y, (void*)out, ws, (double)w1,
+                       (double)w2, maxit};
+        int rc = -1;
+        if (!profile_is_enabled()) {
             DrGraph& G = g_dr_graph;
             if (!(G.exec && G.key == key)) {
                 if (G.exec) { cudaGraphExecDestroy(G.exec); G.exec = nullptr; }
@@ -168,7 +179,7 @@ int dr2_device(size_t M, size_t N, int batch, int row_major, const T* Y, T w1, T
                 cudaGraph_t graph = nullptr;
                 bool okc = cudaStreamBeginCapture(g_pipe.sg, cudaStreamCaptureModeRelaxed) == cudaSuccess;
                 if (okc) {
-                    const int rc = dr2_piped_body<T>(M, N, Y, w1, w2, out, maxit, t, s, x, scr, scratch, gc, n, g_pipe.sg);
+                    rc = body(g_pipe.sg);
                     okc = (cudaStreamEndCapture(g_pipe.sg, &graph) == cudaSuccess) && rc == 0 && graph;
                 }
                 if (okc) okc = cudaGraphInstantiate(&G.exec, graph, 0) == cudaSuccess;
@@ -189,13 +200,12 @@ int dr2_device(size_t M, size_t N, int batch, int row_major, const T* Y, T w1, T
                 return 0;
             }
         }
-        if (dr2_piped_body<T>(M, N, Y, w1, w2, out, maxit, t, s, x, scr, scratch, gc, n, st) != 0) {
-            if (info) info[INFO_RC] = RC_ERROR;
-            return 0;
-        }
-        if (info) { info[INFO_ITERS] = maxit; info[INFO_RC] = RC_OK; }
-        return 0;
+        if (rc != 2) rc = body(st);              // 2: shape not supported by the chunked kernel (reported before anything ran)
+        if (rc == 0) { if (info) { info[INFO_ITERS] = maxit; info[INFO_RC] = RC_OK; } return 0; }
+        if (rc == 1) { if (info) info[INFO_RC] = RC_ERROR; return 0; }
+        // rc == 2: fall through to the plain schedule
     }
+    PTV_TRY(ew_image_means_x2<T>(Y, (long long)M * N, batch, t, scratch, st));        // :390-395
     for (int it = 0; it < maxit; it++) {                                      // :403-423
         if (it == 0 && eng != ENGINE_SEQ) {
             // the first input is the constant image 2*mean: every axis-0 fiber of an image is the same constant vector, so

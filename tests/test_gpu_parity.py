@@ -17,7 +17,7 @@ from conftest import jumps, relerr
 from oracle import oracle as O
 
 pytestmark = pytest.mark.gpu
-ENGINES = ["seq", "auto", "chunked-strided"]
+ENGINES = ["seq", "auto", "chunked", "chunked-strided"]
 
 
 @pytest.fixture(params=ENGINES)
@@ -236,16 +236,22 @@ def test_torch_device_path(ptv, port):
 
 
 def test_pipelined_schedule_equals_serial_schedule(ptv, port):
-    """Large single images take the pipelined Douglas-Rachford schedule (half-kernels on two streams, transposes overlapped);
-    it must give bit-identical results to the serial schedule (engine 'chunked') and match the oracle."""
+    """The default Douglas-Rachford schedule (dr_tspace.cu: no standalone transposes, every kernel writes both layouts, whole
+    solve replayed from a CUDA graph) and the 'pipelined' schedule (overlapped gather/scatter) must give bit-identical
+    results to the plain serial schedule (engine 'chunked'), call after call, and match the oracle."""
     Y = O.gen_cfg2(1024, 1536, seed=5)
     a = ptv.tv1_2d(Y, 0.2)
-    prev = ptv.set_engine("chunked")
-    try:
-        b = ptv.tv1_2d(Y, 0.2)
-    finally:
-        ptv.set_engine(prev)
-    assert np.array_equal(a, b)
+    a2 = ptv.tv1_2d(Y, 0.2)                       # second call: graph replay
+    res = {}
+    for e in ("chunked", "pipelined", "tspace"):
+        prev = ptv.set_engine(e)
+        try:
+            res[e] = ptv.tv1_2d(Y, 0.2)
+        finally:
+            ptv.set_engine(prev)
+    assert np.array_equal(a, a2) and np.array_equal(a, res["chunked"]) and np.array_equal(a, res["pipelined"]) and np.array_equal(a, res["tspace"])
+    Z = O.gen_cfg2(200, 136, seed=6, block=8)     # small, odd-ish shape through the same default schedule
+    assert relerr(ptv.tv1_2d(Z, 0.3), port.dr2_tv(Z, 0.3)[0]) <= 1e-9
     S = np.asfortranarray(Y[:, :1024])
     assert relerr(ptv.tv1_2d(S, 0.2, max_iters=3), port.dr2_tv(S, 0.2, maxit=3)[0]) <= 1e-9
 
