@@ -18,6 +18,10 @@ cudaError_t prox_fibers_chunked_contig(const T* A, const T* B, const T* C, InOp 
 template <typename T>
 cudaError_t prox_fibers_chunked_strided(const T* A, const T* B, const T* C, InOp op, T* X, int out_op, FiberGeom g, T lam, T* V,
                                         cudaStream_t st);
+template <typename T>
+cudaError_t prox_long_fibers(const T* A, const T* B, InOp op, T* X, int out_op, FiberGeom g, T lam, T* scratch, long long scratch_elems,
+                             cudaStream_t st);
+long long lf_scratch_elems(long long nf, long long len);
 template <typename T> cudaError_t gather_fibers(const T* A, const T* B, InOp op, T* out, FiberGeom g, cudaStream_t st);
 template <typename T> cudaError_t scatter_fibers(const T* in, T* X, FiberGeom g, cudaStream_t st);
 template <typename T>
@@ -25,7 +29,7 @@ cudaError_t scatter_fibers_ex(const T* in, const T* A, const T* B, const T* C, I
 
 template <typename T>
 cudaError_t prox_fibers_ex(const T* A, const T* B, const T* C, InOp op, T* X, int out_op, FiberGeom g, T lam, const T* lamv,
-                           Engine eng, T* scratch, cudaStream_t st) {
+                           Engine eng, T* scratch, cudaStream_t st, long long scratch_elems) {
     if (g.nf <= 0 || g.len <= 0) return cudaSuccess;
     if (eng != ENGINE_SEQ && g.len >= 2 * 32) {
         if (g.inc == 1) {
@@ -33,6 +37,14 @@ cudaError_t prox_fibers_ex(const T* A, const T* B, const T* C, InOp op, T* X, in
             cudaError_t e = prox_fibers_chunked_contig<T>(A, B, C, op, X, out_op, g, lam, lamv, st);
             if (e != cudaErrorInvalidConfiguration) return e;
             cudaGetLastError();
+            // too long for shared memory: overlapping tiles, verified stitching (long_fiber.cu); the scratch convention for
+            // this case is lf_scratch_elems() elements, which the 1D host entry points provide
+            if (!lamv && scratch && scratch_elems >= lf_scratch_elems(g.nf, g.len)) {
+                e = prox_long_fibers<T>(A, B, op, X, out_op, g, lam, scratch, lf_scratch_elems(g.nf, g.len), st);
+                if (e == cudaSuccess) return e;
+                if (e != cudaErrorInvalidConfiguration && e != cudaErrorNotReady) return e;
+                cudaGetLastError();
+            }
         } else if (!lamv) {
             // Strided fibers.  Default: tiled gather (input op fused) -> contiguous chunked kernel -> tiled scatter (output form
             // fused).  The scan is compute bound (IPC-limited, ~35 us of HBM time per 225 us pass), so the two extra streaming
@@ -71,13 +83,13 @@ cudaError_t prox_fibers_ex(const T* A, const T* B, const T* C, InOp op, T* X, in
 
 template <typename T>
 cudaError_t prox_fibers(const T* A, const T* B, InOp op, T* X, int out_op, FiberGeom g, T lam, const T* lamv, Engine eng,
-                        T* scratch, cudaStream_t st) {
-    return prox_fibers_ex<T>(A, B, nullptr, op, X, out_op, g, lam, lamv, eng, scratch, st);
+                        T* scratch, cudaStream_t st, long long scratch_elems) {
+    return prox_fibers_ex<T>(A, B, nullptr, op, X, out_op, g, lam, lamv, eng, scratch, st, scratch_elems);
 }
 
 #define INST(T) \
-    template cudaError_t prox_fibers_ex<T>(const T*, const T*, const T*, InOp, T*, int, FiberGeom, T, const T*, Engine, T*, cudaStream_t); \
-    template cudaError_t prox_fibers<T>(const T*, const T*, InOp, T*, int, FiberGeom, T, const T*, Engine, T*, cudaStream_t);
+    template cudaError_t prox_fibers_ex<T>(const T*, const T*, const T*, InOp, T*, int, FiberGeom, T, const T*, Engine, T*, cudaStream_t, long long); \
+    template cudaError_t prox_fibers<T>(const T*, const T*, InOp, T*, int, FiberGeom, T, const T*, Engine, T*, cudaStream_t, long long);
 INST(double)
 INST(float)
 

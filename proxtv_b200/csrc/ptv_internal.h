@@ -37,12 +37,15 @@ struct ProxStats {           // filled asynchronously on the device; optional
 // out_op (OutOp in chunk_core.cuh): 0 X = prox ; 1 X = 2*(in - prox) - in (DR reflection) ; 2 X = in - prox.
 template <typename T>
 cudaError_t prox_fibers(const T* A, const T* B, InOp op, T* X, int out_op, FiberGeom g, T lam, const T* lamv, Engine eng,
-                        T* scratch /* 2 * nf * len elements, or nullptr */, cudaStream_t st);
+                        T* scratch /* 2 * nf * len elements, or nullptr */, cudaStream_t st,
+                        long long scratch_elems = 0 /* actual size if larger than the 2n convention (long contiguous fibers) */);
 
 // Same, with a third array C for the fused Douglas-Rachford row pass (out_op 3 / 4, see OutOp in chunk_core.cuh).
 template <typename T>
 cudaError_t prox_fibers_ex(const T* A, const T* B, const T* C, InOp op, T* X, int out_op, FiberGeom g, T lam, const T* lamv,
-                           Engine eng, T* scratch, cudaStream_t st);
+                           Engine eng, T* scratch, cudaStream_t st, long long scratch_elems = 0);
+
+long long lf_scratch_elems(long long nf, long long len);     // scratch elements prox_fibers needs for contiguous fibers longer than shared memory
 
 // ---- launch accounting / event timing (profile.cu) ----
 enum KernelClass { KC_PROX_CONTIG = 0, KC_PROX_STRIDED = 1, KC_ELEMENTWISE = 2, KC_COUNT = 3 };

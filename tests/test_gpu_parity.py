@@ -235,6 +235,24 @@ def test_torch_device_path(ptv, port):
     assert np.array_equal(ow[7], port.tv1_weighted(X[7], W[7]))
 
 
+def test_long_fibers_config1(ptv, port):
+    """BASELINE config 1: tv1_1d on a 1e6-sample signal (longer than shared memory): overlapping tiles with verified
+    stitching (long_fiber.cu) must be bit-exact; a signal whose tiles cannot be verified (no jump in an overlap window)
+    must fall back to the sequential kernel and still be exact."""
+    y = O.gen_cfg1(1_000_000, seed=0)
+    got = ptv.tv1_1d(y, 0.5)
+    assert np.array_equal(got, port.tv1_linearized(y, 0.5))
+    assert np.abs(got - port.tv1_hybrid(y, 0.5)).max() <= 1e-9                  # the reference's default method
+    assert np.array_equal(jumps(got), jumps(port.tv1_hybrid(y, 0.5)))
+    z = np.concatenate([np.random.default_rng(3).normal(0, 1, 30000), np.full(40000, 0.25),
+                        np.random.default_rng(4).normal(0, 1, 30000)])       # 40000-sample plateau spans several overlaps
+    assert np.array_equal(ptv.tv1_1d(z, 0.3), port.tv1_linearized(z, 0.3))
+    Xb = np.stack([O.gen_cfg1(60000, seed=s) for s in range(3)])                # a small batch of long signals
+    Gb = ptv.tv1_1d_batched(Xb, 0.5)
+    for b in range(3):
+        assert np.array_equal(Gb[b], port.tv1_linearized(Xb[b], 0.5))
+
+
 def test_pipelined_schedule_equals_serial_schedule(ptv, port):
     """The default Douglas-Rachford schedule (dr_tspace.cu: no standalone transposes, every kernel writes both layouts, whole
     solve replayed from a CUDA graph) and the 'pipelined' schedule (overlapped gather/scatter) must give bit-identical
