@@ -81,8 +81,12 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 2 : 1) k_prox_chunked_cont
     RcpPair<T>* rcp = reinterpret_cast<RcpPair<T>*>(smem_raw);    // reciprocal table        [RCP_N]   (16-byte aligned)
     T* ys = reinterpret_cast<T*>(rcp + RCP_N);                    // staged input            [fpb][npad] (npad*sizeof(T) % 16 == 0)
     T* wsm = ys + (size_t)fpb * npad;                             // per-edge weights        [fpb][npad] (weighted only)
-    T* cval = wsm + (WEIGHTED ? (size_t)fpb * npad : 0);          // value entering each chunk [fpb][lpf]
-    uint32_t* mk = reinterpret_cast<uint32_t*>(cval + (size_t)fpb * lpf);      // masks P, K0, K1 [3][fpb][lpf]
+    // value entering each chunk [fpb][lpf]: only needed after the scan, so for small CTAs it re-uses the reciprocal table's
+    // bytes (the table is dead once the last round's barrier has passed) -- the 1 KB saved buys a sixth resident CTA per SM
+    const bool cval_aliased = (size_t)fpb * lpf <= 2 * RCP_N;
+    T* cval_own = wsm + (WEIGHTED ? (size_t)fpb * npad : 0);
+    T* cval = cval_aliased ? reinterpret_cast<T*>(rcp) : cval_own;
+    uint32_t* mk = reinterpret_cast<uint32_t*>(cval_own + (cval_aliased ? 0 : (size_t)fpb * lpf));      // masks P, K0, K1 [3][fpb][lpf]
     constexpr int PADE = PadCfg<T>::PADE;
     const int tid = threadIdx.x;
     const long long f0 = (long long)blockIdx.x * fpb;
@@ -214,9 +218,10 @@ cudaError_t prox_fibers_chunked_contig(const T* A, const T* B, const T* C, InOp 
     const int lpf = (n + CH - 1) / CH;
     if (lpf > 1024) return cudaErrorInvalidConfiguration;
     const int npad = (n + (lpf + 1) * PadCfg<T>::PADE + PadCfg<T>::PADE - 1) / PadCfg<T>::PADE * PadCfg<T>::PADE;
-    const size_t per_fiber = (size_t)npad * sizeof(T) * (lamv ? 2 : 1) + (size_t)lpf * (12 + sizeof(T));
     int fpb = 128 / lpf; if (fpb < 1) fpb = 1;
     if ((long long)fpb > g.nf) fpb = (int)g.nf;
+    const bool cval_aliased = (size_t)fpb * lpf <= 2 * RCP_N;          // see the kernel
+    const size_t per_fiber = (size_t)npad * sizeof(T) * (lamv ? 2 : 1) + (size_t)lpf * (12 + (cval_aliased ? 0 : sizeof(T)));
     const size_t smem = per_fiber * fpb + RCP_N * 2 * sizeof(T) + 16;
     if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;
     int threads = ((fpb * lpf + 31) / 32) * 32;
