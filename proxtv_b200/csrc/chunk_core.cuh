@@ -105,12 +105,14 @@ PTV_HD bool walk_chunk(int q, int round, int nchunks, int n, LdY y, StV stv, Lam
         P = 1u << bit; K0 = (uint32_t)(kk & 1) << bit; K1 = (uint32_t)(kk >> 1) << bit;
     }
     bool merged = false; int mbit = 0;
+    // hot-path guard folded into one compare: i < stop, stop = min(n - 1, last + RCP_N), refreshed whenever `last` moves
+    int stop = (st.s.last + RCP_N < n - 1) ? st.s.last + RCP_N : n - 1;
     for (;;) {
         int k, f, a; T v;
         Scan<T>& s = st.s;
         const int i = s.i;
-        const int d = i - s.last;
-        if (i < n - 1 && d < RCP_N) {
+        if (i < stop) {
+            const int d = i - s.last;
             // ---- hot path: regular step (taut_scan.cuh Scan::step, i < n-1 branch), straight-line, break handled in place.
             //      Both touch updates are computed unconditionally with the exact table division and selected. ----
             const T yi = y(i);
@@ -147,6 +149,7 @@ PTV_HD bool walk_chunk(int q, int round, int nchunks, int n, LdY y, StV stv, Lam
                 s.hhi = lq; s.hlo = -lq;
             }
             s.last = a - 1; s.blo = s.bhi = a; s.i = a + 1;
+            stop = (a - 1 + RCP_N < n - 1) ? a - 1 + RCP_N : n - 1;
             // the finished segment [f, a-1] has value v; a new one starts at a, kind CEIL (cbk) or FLOOR (kind bit 0 set)
             stv(f, v);
             if (a >= ce) { st.pend_a = a; st.pend_k = cbk ? K_CEIL : K_FLOOR; break; }
@@ -157,6 +160,7 @@ PTV_HD bool walk_chunk(int q, int round, int nchunks, int n, LdY y, StV stv, Lam
         } else if (i < n) {                        // closing sample, or a segment longer than the table: rare, generic code
             int l;
             k = s.step(n, y, lam, f, l, v);
+            stop = (s.last + RCP_N < n - 1) ? s.last + RCP_N : n - 1;
             if (k == K_NONE) continue;
             a = l + 1;
         } else {                                   // the fiber ended: value of the last open segment

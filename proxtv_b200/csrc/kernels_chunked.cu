@@ -51,10 +51,10 @@ template <typename T> struct SmemLd32 {
     __device__ __forceinline__ T operator()(int j) const;
 };
 template <> __device__ __forceinline__ double SmemLd32<double>::operator()(int j) const {
-    double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(base + (uint32_t)((j + ((j >> 5) << 1)) << 3)) : "memory"); return v;
+    double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(base + (((uint32_t)j + 2u * ((uint32_t)j >> 5)) << 3)) : "memory"); return v;
 }
 template <> __device__ __forceinline__ float SmemLd32<float>::operator()(int j) const {
-    float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(base + (uint32_t)((j + ((j >> 5) << 2)) << 2)) : "memory"); return v;
+    float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(base + (((uint32_t)j + 4u * ((uint32_t)j >> 5)) << 2)) : "memory"); return v;
 }
 
 // make a kernel parameter an opaque register value: stops the compiler from re-loading it from the constant bank inside the
@@ -64,9 +64,11 @@ __device__ __forceinline__ float in_register(float v) { asm volatile("" : "+f"(v
 __device__ __forceinline__ int in_register(int v) { asm volatile("" : "+r"(v)); return v; }
 
 template <typename T> struct GlobSt {            // sparse value store = the fiber's own output row (see chunk_core.cuh)
-    T* p;
-    __device__ __forceinline__ void operator()(int j, T v) const { p[j] = v; }
+    T* p;                                        // per-lane register copy of the row pointer: one IMAD.WIDE per store
+    __device__ __forceinline__ void operator()(int j, T v) const { p[(unsigned)j] = v; }
 };
+__device__ __forceinline__ double* in_register(double* v) { asm volatile("" : "+l"(v)); return v; }
+__device__ __forceinline__ float* in_register(float* v) { asm volatile("" : "+l"(v)); return v; }
 
 // CL: how the optional transposed second output X2 is produced.  0: plain 8-byte scattered stores (slow: partial-sector writes make
 // L2 read-modify-write every sector); >= 1: the finished fiber rows of CL consecutive CTAs (a thread-block cluster when CL > 1)
@@ -132,7 +134,7 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 2 : 1) k_prox_chunked_cont
     ChunkMasks m{mk + (size_t)fbc * lpf, mk + (size_t)(fpb + fbc) * lpf, mk + (size_t)(2 * fpb + fbc) * lpf};
     SmemLd32<T> y{smem_u32(ys + (size_t)fbc * npad)};
     T* xrow = X + (f0 + fbc) * (long long)n;
-    GlobSt<T> stv{xrow};
+    GlobSt<T> stv{in_register(xrow)};
     RcpDiv<T> div{rcp};
     LaneState<T> st;
     st.active = false; st.finished = false; st.pend_a = -1; st.pend_k = K_NONE;
