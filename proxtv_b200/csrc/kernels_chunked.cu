@@ -70,6 +70,15 @@ template <typename T> struct GlobSt {            // sparse value store = the fib
 __device__ __forceinline__ double* in_register(double* v) { asm volatile("" : "+l"(v)); return v; }
 __device__ __forceinline__ float* in_register(float* v) { asm volatile("" : "+l"(v)); return v; }
 
+#ifdef PTV_PHASE_TIMING
+// debug build only (make EXTRA=-DPTV_PHASE_TIMING): per-phase CTA time of the contiguous kernel, summed over CTAs
+__device__ unsigned long long g_phase_ns[8];
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define PHASE_MARK(k) do { if (threadIdx.x == 0) { const unsigned long long t_ = gtime(); atomicAdd(&g_phase_ns[k], t_ - t_prev); t_prev = t_; } } while (0)
+#else
+#define PHASE_MARK(k) do { } while (0)
+#endif
+
 // CL: how the optional transposed second output X2 is produced.  0: plain 8-byte scattered stores (slow: partial-sector writes make
 // L2 read-modify-write every sector); >= 1: the finished fiber rows of CL consecutive CTAs (a thread-block cluster when CL > 1)
 // are exchanged through (distributed) shared memory so that fpb*CL adjacent fibers are written together as full 32-byte sectors.
@@ -95,6 +104,9 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 2 : 1) k_prox_chunked_cont
     const int nfib = (int)((nf - f0) < fpb ? (nf - f0) : fpb);
     const int nchunks = (n + CH - 1) / CH;
 
+#ifdef PTV_PHASE_TIMING
+    unsigned long long t_prev = gtime();
+#endif
     // ---- stage the fibers ----
     if (tid < RCP_N) { rcp[tid].r = tid ? T(1) / T(tid) : T(0); rcp[tid].d = T(tid); }
     if (use_tma) {
@@ -126,6 +138,7 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 2 : 1) k_prox_chunked_cont
     }
     if (use_tma) mbar_wait(&mbar, 0);
     __syncthreads();
+    PHASE_MARK(0);
 
     // ---- scan: own chunk, then rounds until every lane has merged ----
     const int fb = tid / lpf, q = tid - fb * lpf;
@@ -142,8 +155,15 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 2 : 1) k_prox_chunked_cont
     const int nreg = in_register(n);
     auto phases = [&](auto lamf) {
         bool act = lane_ok ? walk_chunk<T, true>(q, 0, nchunks, nreg, y, stv, lamf, div, st, m) : false;
-        for (int r = 1; __syncthreads_or(act ? 1 : 0); r++)
+        int r = 1;
+        for (; __syncthreads_or(act ? 1 : 0); r++) {
+            if (r == 1) PHASE_MARK(1);
             act = lane_ok ? walk_chunk<T, false>(q, r, nchunks, nreg, y, stv, lamf, div, st, m) : false;
+        }
+        PHASE_MARK(2);
+#ifdef PTV_PHASE_TIMING
+        if (threadIdx.x == 0) { atomicAdd(&g_phase_ns[6], (unsigned long long)r); atomicAdd(&g_phase_ns[7], 1ull); }
+#endif
     };
     if (WEIGHTED) phases(ArrayLam<T, SmemLd32<T>>{SmemLd32<T>{smem_u32(wsm + (size_t)fbc * npad)}});
     else phases(UniformLam<T>{in_register(lam)});
@@ -151,11 +171,15 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 2 : 1) k_prox_chunked_cont
     // ---- value of the segment entering each chunk (gathered before any output is written: the store is the output) ----
     if (lane_ok) cval[(size_t)fbc * lpf + q] = __ldcg(xrow + carry_of(q, m));
     __syncthreads();
+    PHASE_MARK(3);
 
-    // ---- fill: 32-sample windows, FW per warp at a time: all sparse reads of the batch (L2 round trips overlap), then its
-    //      coalesced writes.  Reads of a window only touch that window, so batching windows is hazard free. ----
-    constexpr int FW = 4;
-    const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+    // ---- fill: 32-sample windows, FW per warp and batch: all sparse reads of the batch (segment values parked in the output
+    //      row: L2 round trips that overlap), then its coalesced writes.  Reads of a window only touch that window, so batching
+    //      windows is hazard free; the __syncwarp orders a window's reads before its own writes.  Measured on B200 (n = 4096
+    //      f64): FW 2/4/8 -> 206/195/189 us; FW >= 16 costs registers (a CTA less per SM); software-pipelining the batches or
+    //      hoisting the Douglas-Rachford operand loads ahead of the stores was slower (200-208 us). ----
+    constexpr int FW = 8;
+    const int warp = tid >> 5, lane = tid & 31, wstep = (blockDim.x >> 5) * FW;
     const uint32_t below = 0xffffffffu >> (31 - lane);
     for (int fb2 = 0; fb2 < nfib; fb2++) {
         const long long gb = (f0 + fb2) * (long long)n;
@@ -164,13 +188,13 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 2 : 1) k_prox_chunked_cont
         const uint32_t* Pm = mk + (size_t)fb2 * lpf;
         const T* cv = cval + (size_t)fb2 * lpf;
         T* yr = ys + (size_t)fb2 * npad;
-        for (int c0 = warp * FW; c0 < nchunks; c0 += nwarps * FW) {
+        for (int c0 = warp * FW; c0 < nchunks; c0 += wstep) {
             T v[FW];
 #pragma unroll
             for (int u = 0; u < FW; u++) {
-                const int c = c0 + u, j = (c << 5) + lane;
+                const int c = c0 + u;
                 v[u] = T(0);
-                if (c < nchunks && j < n) {
+                if (c < nchunks && (c << 5) + lane < n) {
                     const uint32_t w = Pm[c] & below;
                     v[u] = w ? __ldcg(xr + (c << 5) + high_bit(w)) : cv[c];
                 }
@@ -188,6 +212,8 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 2 : 1) k_prox_chunked_cont
             }
         }
     }
+    __syncthreads();
+    PHASE_MARK(4);
     if (CL >= 1) {
         // ---- transposed second output, assembled from the G = fpb*CL adjacent fibers of this CTA / cluster: each group of G
         //      consecutive lanes writes G*sizeof(T) contiguous bytes (>= one full sector), positions split between the CTAs ----
@@ -418,3 +444,11 @@ template cudaError_t prox_fibers_chunked_strided<double>(const double*, const do
 template cudaError_t prox_fibers_chunked_strided<float>(const float*, const float*, const float*, InOp, float*, int, FiberGeom, float, float*, cudaStream_t);
 
 }  // namespace ptv
+
+#ifdef PTV_PHASE_TIMING
+extern "C" void proxtv_debug_phase_read(unsigned long long* out, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, ptv::g_phase_ns, sizeof(unsigned long long) * 8);
+    if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(ptv::g_phase_ns, z, sizeof(z)); }
+}
+#endif

@@ -42,6 +42,12 @@ def main():
                     ot = torch.empty_like(xt)
                     f = lambda: fn_c(C.c_void_p(xt.data_ptr()), C.c_void_p(ot.data_ptr()), nf, n, nf, lam, None, st)
                 ms = timeit(f, reps=5 if eng == "seq" else 20)
+                if hasattr(lib, "proxtv_debug_phase_read"):       # debug build: make EXTRA=-DPTV_PHASE_TIMING
+                    ph = (C.c_ulonglong * 8)(); lib.proxtv_debug_phase_read(ph, 1)
+                    if ph[7]:
+                        tot = sum(ph[k] for k in range(5))
+                        print("    phases (CTA-time share) stage/round0/rounds/cval/fill: " + " ".join(f"{100*ph[k]/tot:.1f}%" for k in range(5))
+                              + f"  mean CTA life {tot/ph[7]/1e3:.1f} us, rounds {ph[6]/ph[7]:.2f}")
                 gbs = 2 * nf * n * x.element_size() / ms / 1e6
                 print(f"{eng:8s} {name:18s} {label:10s} n={n} nf={nf} {dt}: {ms*1e3:9.1f} us  {gbs:8.1f} GB/s (1R+1W)", flush=True)
 
