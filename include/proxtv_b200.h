@@ -58,6 +58,11 @@ int TV(double *y, double lambda, double *x, double *info, int n, double p, void 
  * norm1, norm2 must be 1; nThreads is ignored. */
 int DR2_TV(size_t M, size_t N, double *unary, double W1, double W2, double norm1, double norm2, double *s, int nThreads,
            int maxit, double *info);
+/* replaces src/TV2DWopt.cpp:46 (src/TVopt.h:116): DR2_TV's iteration with per-edge weights.  unary, s: M x N column-major;
+ * W1: (M-1) x N column-major (weights of the edges along columns), W2: M x (N-1) column-major (edges along rows).
+ * info = {maxit, untouched, RC_OK}; returns 0 on success AND on error, like the reference (:135, :64-68).  nThreads is
+ * ignored.  Fibers of length 1 (M == 1 or N == 1) are left unchanged (the reference reads past an empty weight line). */
+int DR2L1W_TV(size_t M, size_t N, double *unary, double *W1, double *W2, double *s, int nThreads, int maxit, double *info);
 /* replaces src/TV2Dopt.cpp:59 (src/TVopt.h:126).  npen <= 2, norms must be 1, dims are 1-based; info = {iters, stop, RC};
  * RC_ITERS is set when iters >= 35 regardless of maxIters (:289); returns 1 ok / 0 error. */
 int PD2_TV(double *y, double *lambdas, double *norms, double *dims, double *x, double *info, int *ns, int nds, int npen,
@@ -105,6 +110,12 @@ int proxtv_DR2_TV_batched_f64(size_t M, size_t N, int batch, const double *Y, do
                               double *info);
 int proxtv_DR2_TV_batched_f32(size_t M, size_t N, int batch, const float *Y, float W1, float W2, float *out, int maxit,
                               double *info);
+
+/* DR2L1W_TV with device arrays (layouts as above; f32 is an extension the reference lacks). */
+int proxtv_DR2L1W_TV_dev_f64(size_t M, size_t N, const double *Y, const double *W1, const double *W2, double *out, int maxit,
+                             double *info, void *stream);
+int proxtv_DR2L1W_TV_dev_f32(size_t M, size_t N, const float *Y, const float *W1, const float *W2, float *out, int maxit,
+                             double *info, void *stream);
 
 /* PD2_TV / PD_TV with device arrays y, x (lambdas, dims, ns, info stay on the host).  Synchronous (the stop test needs
  * one 8-byte read-back per iteration).  proxtv_PD_TV_* scale lambdas in place like PD_TV. */

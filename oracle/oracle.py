@@ -49,6 +49,7 @@ class Port:
         L.orc_tv1_condat.argtypes = [_dp, _dp, C.c_int, C.c_double]
         L.orc_tv1_weighted.argtypes = [_dp, _dp, _dp, C.c_int]
         L.orc_dr2_tv.argtypes = [C.c_size_t, C.c_size_t, _dp, C.c_double, C.c_double, _dp, C.c_int, _dp]
+        L.orc_dr2l1w_tv.argtypes = [C.c_size_t, C.c_size_t, _dp, _dp, _dp, _dp, C.c_int, _dp]
         L.orc_pd2_tv.argtypes = [_dp, _dp, _dp, _dp, _dp, _ip, C.c_int, C.c_int, C.c_int]
         L.orc_pd_tv.argtypes = [_dp, _dp, _dp, _dp, _dp, _ip, C.c_int, C.c_int, C.c_int]
         L.orc_jump_set.argtypes = [_dp, C.c_long, C.c_long, _ip]
@@ -82,6 +83,14 @@ class Port:
         Y = _f64(Y, "F"); out = np.zeros(Y.shape, order="F"); info = np.zeros(3)
         self.lib.orc_dr2_tv(Y.shape[0], Y.shape[1], _p(Y), float(w1), float(w1 if w2 is None else w2), _p(out),
                             int(maxit), _p(info))
+        return out, info
+
+    def dr2l1w_tv(self, Y, W1, W2, maxit=0, n_threads=1):
+        """W1: (M-1, N) weights of the edges along columns, W2: (M, N-1) along rows (prox_tv.tv1w_2d's w_col, w_row)."""
+        Y = _f64(Y, "F"); W1 = _f64(W1, "F"); W2 = _f64(W2, "F"); out = np.zeros(Y.shape, order="F"); info = np.zeros(3)
+        assert W1.shape == (Y.shape[0] - 1, Y.shape[1]) and W2.shape == (Y.shape[0], Y.shape[1] - 1)
+        self.lib.orc_dr2l1w_tv(Y.shape[0], Y.shape[1], _p(Y), _p(np.append(W1.ravel("F"), 0.0)), _p(np.append(W2.ravel("F"), 0.0)),
+                               _p(out), int(maxit), _p(info))
         return out, info
 
     def _pd(self, fn, Y, ws, ds, maxit):
@@ -123,6 +132,7 @@ class Ref:
         L.tautString_TV1_Weighted.argtypes = [_dp, _dp, _dp, C.c_int]
         L.DR2_TV.argtypes = [C.c_size_t, C.c_size_t, _dp, C.c_double, C.c_double, C.c_double, C.c_double, _dp,
                              C.c_int, C.c_int, _dp]
+        L.DR2L1W_TV.argtypes = [C.c_size_t, C.c_size_t, _dp, _dp, _dp, _dp, C.c_int, C.c_int, _dp]
         for f in (L.PD2_TV, L.PD_TV):
             f.argtypes = [_dp, _dp, _dp, _dp, _dp, _dp, _ip, C.c_int, C.c_int, C.c_int, C.c_int]
 
@@ -155,6 +165,13 @@ class Ref:
         Y = _f64(Y, "F"); out = np.zeros(Y.shape, order="F"); info = np.zeros(3)
         self.lib.DR2_TV(Y.shape[0], Y.shape[1], _p(Y), float(w1), float(w1 if w2 is None else w2), 1.0, 1.0, _p(out),
                         int(n_threads), int(maxit), _p(info))
+        return out, info
+
+    def dr2l1w_tv(self, Y, W1, W2, maxit=0, n_threads=1):
+        Y = _f64(Y, "F"); W1 = _f64(W1, "F"); W2 = _f64(W2, "F"); out = np.zeros(Y.shape, order="F"); info = np.zeros(3)
+        assert W1.shape == (Y.shape[0] - 1, Y.shape[1]) and W2.shape == (Y.shape[0], Y.shape[1] - 1)
+        self.lib.DR2L1W_TV(Y.shape[0], Y.shape[1], _p(Y), _p(np.append(W1.ravel("F"), 0.0)), _p(np.append(W2.ravel("F"), 0.0)),
+                           _p(out), int(n_threads), int(maxit), _p(info))
         return out, info
 
     def _pd(self, fn, Y, ws, ds, maxit, n_threads):

@@ -17,7 +17,7 @@ import numpy as np
 from . import _lib
 from ._lib import ProxTVError, load, require_device  # noqa: F401
 
-__all__ = ["tv1_1d", "tv1w_1d", "tv1_2d", "tvgen", "tv1_1d_batched", "tv1w_1d_batched", "tv1_2d_batched",
+__all__ = ["tv1_1d", "tv1w_1d", "tv1_2d", "tv1w_2d", "tvgen", "tv1_1d_batched", "tv1w_1d_batched", "tv1_2d_batched",
            "set_engine", "ProxTVError"]
 
 _N_INFO = 3                      # prox_tv/__init__.py:67
@@ -196,6 +196,53 @@ def tv1_2d(x, w, n_threads=1, max_iters=0, method="dr"):
                         int(n_threads), int(max_iters))
         _check(ok and info[2] != 3, "PD2_TV")
     return y
+
+
+def tv1w_2d(x, w_col, w_row, max_iters=0, n_threads=1):
+    r"""2D weighted anisotropic TV-L1 prox by Douglas-Rachford splitting (prox_tv/__init__.py:445-481 -> DR2L1W_TV).
+
+    ``w_col``: (M-1, N) weights of the differences along columns, ``w_row``: (M, N-1) along rows.  Same fixed-iteration
+    scheme as ``tv1_2d(method='dr')`` (35 iterations unless ``max_iters`` > 0).  ``n_threads`` is ignored.
+    numpy input: Fortran-ordered float64 result like the reference.  torch CUDA tensors (float64 / float32, all three on
+    the same device): computed on the device, returns a tensor shaped and typed like ``x``.
+    """
+    if _is_torch(x):
+        return _drw_torch(x, w_col, w_row, max_iters)
+    assert np.all(np.asarray(w_col) >= 0)
+    assert np.all(np.asarray(w_row) >= 0)
+    M, N = np.shape(x)
+    assert np.shape(w_col) == (M - 1, N)
+    assert np.shape(w_row) == (M, N - 1)
+    x = np.asfortranarray(x, dtype="float64")
+    y = np.zeros(x.shape, order="F")
+    w_col = np.asfortranarray(w_col, dtype="float64")
+    w_row = np.asfortranarray(w_row, dtype="float64")
+    info = np.zeros(_N_INFO)
+    lib = require_device()
+    lib.DR2L1W_TV(M, N, _ptr(x), _ptr(w_col), _ptr(w_row), _ptr(y), int(n_threads), int(max_iters), _ptr(info))
+    _check(info[2] != 3, "DR2L1W_TV")
+    return y
+
+
+def _drw_torch(x, w_col, w_row, max_iters):
+    import torch
+    assert x.is_cuda and x.dtype in (torch.float64, torch.float32) and x.dim() == 2
+    M, N = int(x.shape[0]), int(x.shape[1])
+    assert tuple(w_col.shape) == (M - 1, N) and tuple(w_row.shape) == (M, N - 1)
+    # the solver works on column-major arrays == the row-major storage of the transposes
+    xt = x.t().contiguous()
+    w1 = w_col.to(device=x.device, dtype=x.dtype).t().contiguous()
+    w2 = w_row.to(device=x.device, dtype=x.dtype).t().contiguous()
+    out = torch.empty_like(xt)
+    info = np.zeros(_N_INFO)
+    lib = require_device()
+    st = C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+    fn = lib.proxtv_DR2L1W_TV_dev_f32 if x.dtype == torch.float32 else lib.proxtv_DR2L1W_TV_dev_f64
+    with torch.cuda.device(x.device):
+        fn(M, N, C.c_void_p(xt.data_ptr()), C.c_void_p(w1.data_ptr()), C.c_void_p(w2.data_ptr()), C.c_void_p(out.data_ptr()),
+           int(max_iters), _ptr(info), st)
+    _check(info[2] != 3, "DR2L1W_TV (device)")
+    return out.t()
 
 
 def _dr2_torch(x, w, max_iters, batched):

@@ -98,6 +98,30 @@ int host_dr2(const char* fn, size_t M, size_t N, int batch, const T* Y, T W1, T 
     return 0;
 }
 
+// DR2L1W_TV with host (host_io) or device arrays.  W1: (M-1) x N, W2: M x (N-1), column-major like Y.
+template <typename T>
+int run_drw(const char* fn, bool host_io, size_t M, size_t N, const T* Y, const T* W1, const T* W2, T* out, int maxit, double* info,
+            cudaStream_t st) {
+    if (!have_device(fn, info)) return 0;
+    std::lock_guard<std::mutex> lk(g_mu);
+    const size_t n = M * N, n1 = M ? (M - 1) * N : 0, n2 = N ? M * (N - 1) : 0;
+    if (n == 0) { if (info) { info[INFO_ITERS] = maxit <= 0 ? MAX_ITERS_DR : maxit; info[INFO_RC] = RC_OK; } return 0; }
+    void* ws = g_ws.get(ws_bytes_dr2<T>(M, N, 1));
+    if (!ws) { fail(fn, "out of memory", info); return 0; }                             // TV2DWopt.cpp:78-79
+    if (!host_io) return drw_device<T>(M, N, Y, W1, W2, out, maxit, info, ws, (Engine)g_engine, st);
+    char* d = (char*)g_io.get(2 * al(n * sizeof(T)) + al(n1 * sizeof(T) + 8) + al(n2 * sizeof(T) + 8));
+    if (!d) { fail(fn, "out of memory", info); return 0; }
+    T* dY = (T*)d; T* dout = (T*)(d + al(n * sizeof(T))); T* d1 = (T*)(d + 2 * al(n * sizeof(T))); T* d2 = (T*)((char*)d1 + al(n1 * sizeof(T) + 8));
+    if (!cuda_ok(fn, cudaMemcpyAsync(dY, Y, n * sizeof(T), cudaMemcpyHostToDevice, st), info)) return 0;
+    if (n1 && !cuda_ok(fn, cudaMemcpyAsync(d1, W1, n1 * sizeof(T), cudaMemcpyHostToDevice, st), info)) return 0;
+    if (n2 && !cuda_ok(fn, cudaMemcpyAsync(d2, W2, n2 * sizeof(T), cudaMemcpyHostToDevice, st), info)) return 0;
+    drw_device<T>(M, N, dY, d1, d2, dout, maxit, info, ws, (Engine)g_engine, st);
+    if (info && info[INFO_RC] == RC_ERROR) { fail(fn, "device solver failed", info); return 0; }
+    if (!cuda_ok(fn, cudaMemcpyAsync(out, dout, n * sizeof(T), cudaMemcpyDeviceToHost, st), info)) return 0;
+    if (!cuda_ok(fn, cudaStreamSynchronize(st), info)) return 0;
+    return 0;
+}
+
 // mode 0: PD2_TV, 1: PD_TV.  y/x host (host_io) or device pointers.
 template <typename T>
 int run_pd(const char* fn, int mode, bool host_io, const T* y, double* lambdas, double* norms, double* dims, T* x, double* info,
@@ -196,6 +220,9 @@ int DR2_TV(size_t M, size_t N, double* unary, double W1, double W2, double norm1
     if (norm1 != 1.0 || norm2 != 1.0) { fail("DR2_TV", "only p = 1 (TV-L1) penalties are implemented on the GPU path", info); return 0; }
     return host_dr2<double>("DR2_TV", M, N, 1, unary, W1, W2, s, maxit, info);
 }
+int DR2L1W_TV(size_t M, size_t N, double* unary, double* W1, double* W2, double* s, int, int maxit, double* info) {
+    return run_drw<double>("DR2L1W_TV", true, M, N, unary, W1, W2, s, maxit, info, 0);
+}
 int PD2_TV(double* y, double* lambdas, double* norms, double* dims, double* x, double* info, int* ns, int nds, int npen, int,
            int maxIters) {
     return run_pd<double>("PD2_TV", 0, true, y, lambdas, norms, dims, x, info, ns, nds, npen, maxIters, 0);
@@ -231,6 +258,11 @@ int proxtv_DR2_TV_batched_f64(size_t M, size_t N, int batch, const double* Y, do
     return host_dr2<double>("proxtv_DR2_TV_batched_f64", M, N, batch, Y, W1, W2, out, maxit, info); }
 int proxtv_DR2_TV_batched_f32(size_t M, size_t N, int batch, const float* Y, float W1, float W2, float* out, int maxit, double* info) {
     return host_dr2<float>("proxtv_DR2_TV_batched_f32", M, N, batch, Y, W1, W2, out, maxit, info); }
+
+int proxtv_DR2L1W_TV_dev_f64(size_t M, size_t N, const double* Y, const double* W1, const double* W2, double* out, int maxit, double* info, void* stream) {
+    return run_drw<double>("proxtv_DR2L1W_TV_dev_f64", false, M, N, Y, W1, W2, out, maxit, info, (cudaStream_t)stream); }
+int proxtv_DR2L1W_TV_dev_f32(size_t M, size_t N, const float* Y, const float* W1, const float* W2, float* out, int maxit, double* info, void* stream) {
+    return run_drw<float>("proxtv_DR2L1W_TV_dev_f32", false, M, N, Y, W1, W2, out, maxit, info, (cudaStream_t)stream); }
 
 int proxtv_PD2_TV_dev_f64(const double* y, double* lambdas, double* dims, double* x, double* info, int* ns, int nds, int npen, int maxIters, void* stream) {
     return run_pd<double>("proxtv_PD2_TV_dev_f64", 0, false, y, lambdas, nullptr, dims, x, info, ns, nds, npen, maxIters, (cudaStream_t)stream); }

@@ -192,7 +192,8 @@ PTV_HD bool walk_chunk(int q, int round, int nchunks, int n, LdY y, StV stv, Lam
 // Output forms (what is written for input sample yin and prox value x).  The two DR_ROWS forms additionally read the
 // arrays the pass was staged from (A = Y, B = s, C = t) at the sample's own position and fuse the second half of a
 // Douglas-Rachford iteration into the pass (src/TV2Dopt.cpp:515-520, :419, :422 resp. :429-430), same operation order.
-enum OutOp { OUT_X = 0, OUT_REFLECT = 1, OUT_DIFF = 2, OUT_DR_ROWS = 3, OUT_DR_ROWS_FINAL = 4 };
+enum OutOp { OUT_X = 0, OUT_REFLECT = 1, OUT_DIFF = 2, OUT_DR_ROWS = 3, OUT_DR_ROWS_FINAL = 4,
+             OUT_DRW_ROWS = 5, OUT_DRW_ROWS_FINAL = 6 };     // weighted Douglas-Rachford (src/TV2DWopt.cpp): opposite signs
 template <typename T> PTV_HD T apply_out(int op, T yin, T x) {
     if (op == OUT_X) return x;
     T d = yin - x;                                            // DR_proxDiff           (src/TV2Dopt.cpp:545-546)
@@ -203,6 +204,12 @@ template <typename T> PTV_HD T apply_out(int op, T yin, T x) {
 template <typename T> PTV_HD T apply_out_ex(int op, T yin, T x, const T* A, const T* B, const T* C, long long g) {
     if (op < OUT_DR_ROWS) return apply_out<T>(op, yin, x);
     const T Yv = A[g], sv = B[g];
+    if (op >= OUT_DRW_ROWS) {
+        T tw = (yin - x) - Yv;                                // output[idx] = out - ref             (src/TV2DWopt.cpp:218)
+        if (op == OUT_DRW_ROWS_FINAL) return -sv - tw;        // s = -s - tb                          (:125)
+        tw = T(-2) * tw - sv;                                 // tb = -2 tb - s                       (:115)
+        return T(0.5) * (C[g] + tw);                          // t = 0.5 (t + tb)                     (:118)
+    }
     T tb = Yv - (yin - x);                                    // output[idx] = ref[idx] - (in - prox)      (:520, :546)
     if (op == OUT_DR_ROWS_FINAL) return tb - sv;              // s = tb - s                                (:430)
     tb = T(2) * tb - sv;                                      // tb = 2 tb - s                             (:419)

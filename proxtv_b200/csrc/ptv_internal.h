@@ -83,6 +83,9 @@ constexpr int REDUCE_BLOCKS = 1184;    // 148 SMs x 8; partial sums are combined
 template <typename T> size_t ws_bytes_dr2(size_t M, size_t N, int batch);
 template <typename T> int dr2_device(size_t M, size_t N, int batch, int row_major, const T* Y, T w1, T w2, T* out, int maxit, double* info,
                                      void* ws, Engine eng, cudaStream_t st);
+// DR2L1W_TV on one M x N column-major image; W1: (M-1) x N, W2: M x (N-1) column-major; workspace of ws_bytes_dr2(M, N, 1) bytes
+template <typename T> int drw_device(size_t M, size_t N, const T* Y, const T* W1, const T* W2, T* out, int maxit, double* info, void* ws,
+                                     Engine eng, cudaStream_t st);
 template <typename T> size_t ws_bytes_pd(long long n, int npen);
 template <typename T> int pd2_device(const T* y, const double* lambdas, const double* dims, T* x, double* info, const int* ns,
                                      int nds, int npen, int maxIters, void* ws, Engine eng, cudaStream_t st);

@@ -226,6 +226,63 @@ int dr2_device(size_t M, size_t N, int batch, int row_major, const T* Y, T w1, T
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// DR2L1W_TV (src/TV2DWopt.cpp:46-140): the Douglas-Rachford skeleton of DR2_TV with per-edge weights -- W1: (M-1) x N
+// (column fibers, contiguous, exactly the [fiber][len-1] layout of the weighted chunked kernel), W2: M x (N-1) (row
+// fibers, stride M) -- and the opposite reflection signs (:115, :125).  Rows go through the same gather -> contiguous
+// chunked kernel -> fused scatter route as DR2_TV; their weights are constant over the solve and are gathered once.
+template <typename T> cudaError_t gather_fibers(const T* A, const T* B, InOp op, T* out, FiberGeom g, cudaStream_t st);
+template <typename T>
+cudaError_t scatter_fibers_ex(const T* in, const T* A, const T* B, const T* C, InOp op, int out_op, T* X, FiberGeom g, cudaStream_t st);
+
+template <typename T>
+int drw_device(size_t M, size_t N, const T* Y, const T* W1, const T* W2, T* out, int maxit, double* info, void* ws, Engine eng,
+               cudaStream_t st) {
+    const long long n = (long long)M * (long long)N;
+    if (maxit <= 0) maxit = MAX_ITERS_DR;                                     // TV2DWopt.cpp:82
+    if (n == 0) { if (info) { info[INFO_ITERS] = maxit; info[INFO_RC] = RC_OK; } return 0; }
+    char* w = (char*)ws;
+    T* t = (T*)w; w += align256(n * sizeof(T));
+    T* s = (T*)w; w += align256(n * sizeof(T));
+    T* x = (T*)w; w += align256(n * sizeof(T));
+    T* t1 = (T*)w; w += align256(n * sizeof(T));
+    T* t2 = (T*)w; w += align256(n * sizeof(T));
+    T* w2t = (T*)w; w += 2 * align256(n * sizeof(T));
+    double* scratch = (double*)w;
+    const FiberGeom gc{(long long)N, (int)M, 1}, gr{(long long)M, (int)N, (long long)M}, grc{(long long)M, (int)N, 1};
+    bool fast_rows = eng != ENGINE_SEQ && N >= 64 && M >= 1;
+    if (fast_rows) { KernelSpan sp(KC_ELEMENTWISE, 1, st);
+                     PTV_TRY(gather_fibers<T>(W2, nullptr, IN_A, w2t, FiberGeom{(long long)M, (int)N - 1, (long long)M}, st)); }
+    PTV_TRY(ew_image_means_x2<T>(Y, n, 1, t, scratch, st));                   // :85-89
+    for (int it = 0; it <= maxit; it++) {                                     // :94-119, then the final pair :122-125
+        const bool final = it == maxit;
+        // columns: s = 2 (t - prox_W1(t)) - t   (final: s = t - prox_W1(t))
+        PTV_TRY(prox_fibers_ex<T>(t, nullptr, nullptr, IN_A, s, final ? 2 : 1, gc, T(0), M > 1 ? W1 : nullptr, eng, nullptr, st, 0));
+        // rows: in = Y - s ; tb = (in - prox_W2(in)) - Y ; tb = -2 tb - s ; t' = 0.5 (t + tb)   (final: out = -s - tb)
+        T* dst = final ? out : x;
+        const int oop = final ? 6 : 5;
+        bool done = false;
+        if (fast_rows) {
+            { KernelSpan sp(KC_ELEMENTWISE, 1, st); PTV_TRY(gather_fibers<T>(Y, s, IN_A_MINUS_B, t1, gr, st)); }
+            cudaError_t e;
+            { KernelSpan sp(KC_PROX_STRIDED, 1, st);
+              e = prox_fibers_chunked_contig<T>(t1, nullptr, nullptr, IN_A, t2, 0, grc, T(0), w2t, st);
+              if (e == cudaErrorInvalidConfiguration) sp.cancel(); }
+            if (e == cudaErrorInvalidConfiguration) { cudaGetLastError(); fast_rows = false; }
+            else {
+                PTV_TRY(e);
+                KernelSpan sp(KC_ELEMENTWISE, 1, st);
+                PTV_TRY(scatter_fibers_ex<T>(t2, Y, s, t, IN_A_MINUS_B, oop, dst, gr, st));
+                done = true;
+            }
+        }
+        if (!done) PTV_TRY(prox_fibers_ex<T>(Y, s, t, IN_A_MINUS_B, dst, oop, gr, T(0), N > 1 ? W2 : nullptr, ENGINE_SEQ, nullptr, st, 0));
+        if (!final) { T* tmp = t; t = x; x = tmp; }
+    }
+    if (info) { info[INFO_ITERS] = maxit; info[INFO_RC] = RC_OK; }            // :128-131
+    return 0;                                                                 // :135 (returns 0 on success, like DR2_TV)
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 template <typename T> size_t ws_bytes_pd(long long n, int npen) {
     int arrays = 2 * npen + 4;   // PD_TV: p_i, z_i ; PD2_TV (npen <= 2): p, q, z, xl  -> 4 <= 2*2+2
     if (arrays < 6) arrays = 6;
@@ -327,6 +384,7 @@ int pd_device(const T* y, const double* lam, const double* dims, T* x, double* i
 #define INST(T) \
     template size_t ws_bytes_dr2<T>(size_t, size_t, int); \
     template int dr2_device<T>(size_t, size_t, int, int, const T*, T, T, T*, int, double*, void*, Engine, cudaStream_t); \
+    template int drw_device<T>(size_t, size_t, const T*, const T*, const T*, T*, int, double*, void*, Engine, cudaStream_t); \
     template size_t ws_bytes_pd<T>(long long, int); \
     template int pd2_device<T>(const T*, const double*, const double*, T*, double*, const int*, int, int, int, void*, Engine, cudaStream_t); \
     template int pd_device<T>(const T*, const double*, const double*, T*, double*, const int*, int, int, int, void*, Engine, cudaStream_t);

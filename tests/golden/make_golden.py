@@ -63,6 +63,17 @@ def main():
     out["pd4_V"] = V4; out["pd4_out"] = o; out["pd4_info"] = info
     o, info = R.pd_tv(cases[5][0], [0.7], [1])                     # 1 term on a 1D signal (tvgen_1d)
     out["pd1_out"] = o; out["pd1_info"] = info
+    # ---- weighted 2D DR (DR2L1W_TV); its own generator so that everything above keeps its draws ----
+    rw = np.random.default_rng(20260925)
+    shapes = [(2, 2, 0), (3, 4, 0), (5, 2, 4), (37, 53, 0), (64, 48, 7), (96, 128, 0), (130, 100, 0)]
+    for k, (M, N, it) in enumerate(shapes):
+        Y = O.gen_cfg2(M, N, seed=300 + k, block=8) if min(M, N) >= 8 else np.asfortranarray(rw.normal(0, 1, (M, N)))
+        W1 = np.asfortranarray(rw.uniform(0.02, 0.6, (M - 1, N))); W2 = np.asfortranarray(rw.uniform(0.02, 0.6, (M, N - 1)))
+        if k == 4: W1[::3] = 0.0                                   # some zero weights (no coupling across those edges)
+        o, info = R.dr2l1w_tv(Y, W1, W2, maxit=it)
+        out["drw_%d_Y" % k] = Y; out["drw_%d_W1" % k] = W1; out["drw_%d_W2" % k] = W2; out["drw_%d_it" % k] = np.int64(it)
+        out["drw_%d_out" % k] = o; out["drw_%d_info" % k] = info
+    out["drw_count"] = np.int64(len(shapes))
     path = os.path.join(ROOT, "tests", "golden", "golden_v1.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes,", len(out), "arrays")

@@ -31,7 +31,7 @@ def test_reference_hot_path_symbols_present():
     """The subset of the reference's cffi cdef (prox_tv/prox_tv_build.py:8-77) that is the hot path."""
     lib = proxtv_b200.load()
     for n in ["hybridTautString_TV1", "hybridTautString_TV1_custom", "classicTautString_TV1", "linearizedTautString_TV1",
-              "TV1D_denoise", "tautString_TV1_Weighted", "TV", "DR2_TV", "PD2_TV", "PD_TV"]:
+              "TV1D_denoise", "tautString_TV1_Weighted", "TV", "DR2_TV", "DR2L1W_TV", "PD2_TV", "PD_TV"]:
         assert hasattr(lib, n)
 
 

@@ -151,6 +151,60 @@ def test_dr2_edge_shapes(ptv, port, eng):
     assert relerr(ptv.tv1_2d(Yc, 0.0), Yc) <= 1e-12                 # w = 0: identity
 
 
+def test_weighted_dr_golden(golden, ptv, eng):
+    """tv1w_2d -> DR2L1W_TV (src/TV2DWopt.cpp:46) against the reference's outputs."""
+    for k in range(int(golden["drw_count"])):
+        Y = golden["drw_%d_Y" % k]; W1 = golden["drw_%d_W1" % k]; W2 = golden["drw_%d_W2" % k]; it = int(golden["drw_%d_it" % k])
+        got = ptv.tv1w_2d(Y, W1, W2, max_iters=it)
+        assert got.flags.f_contiguous and got.dtype == np.float64 and got.shape == Y.shape
+        assert relerr(got, golden["drw_%d_out" % k]) <= 1e-6, k
+
+
+def test_weighted_dr_tight_parity_abi_and_shapes(ptv, port, eng):
+    lib = ptv.load()
+    rng = np.random.default_rng(31)
+    Y = O.gen_cfg2(300, 211, seed=22, block=16)
+    W1 = np.asfortranarray(rng.uniform(0.0, 0.5, (299, 211))); W2 = np.asfortranarray(rng.uniform(0.0, 0.5, (300, 210)))
+    out = np.zeros(Y.shape, order="F"); info = np.array([-1.0, -5.0, -1.0])
+    rc = lib.DR2L1W_TV(300, 211, C.c_void_p(Y.ctypes.data), C.c_void_p(W1.ctypes.data), C.c_void_p(W2.ctypes.data),
+                       C.c_void_p(out.ctypes.data), 4, 0, C.c_void_p(info.ctypes.data))
+    want, winfo = port.dr2l1w_tv(Y, W1, W2)
+    assert rc == 0 and info[0] == 35 and info[1] == -5.0 and info[2] == 0
+    assert relerr(out, want) <= 1e-9            # only the 2*mean reduction order differs from the reference
+    rc = lib.DR2L1W_TV(300, 211, C.c_void_p(Y.ctypes.data), C.c_void_p(W1.ctypes.data), C.c_void_p(W2.ctypes.data),
+                       C.c_void_p(out.ctypes.data), 1, 3, C.c_void_p(info.ctypes.data))
+    assert info[0] == 3 and relerr(out, port.dr2l1w_tv(Y, W1, W2, maxit=3)[0]) <= 1e-9
+    # shapes around the kernel-family switches (short / long fibers, odd sizes); fibers of length 1 stay unchanged
+    for shape in [(2, 2), (3, 2), (2, 3), (63, 65), (65, 63), (17, 1024), (1024, 17), (129, 257)]:
+        M, N = shape
+        Yq = np.asfortranarray(rng.normal(size=shape)); A = rng.uniform(0, 0.7, (M - 1, N)); B = rng.uniform(0, 0.7, (M, N - 1))
+        assert relerr(ptv.tv1w_2d(Yq, A, B), port.dr2l1w_tv(Yq, A, B)[0]) <= 1e-9, shape
+    Yq = np.asfortranarray(rng.normal(size=(1, 40))); B = rng.uniform(0, 0.7, (1, 39))
+    assert relerr(ptv.tv1w_2d(Yq, np.zeros((0, 40)), B), port.dr2l1w_tv(Yq, np.zeros((0, 40)), B)[0]) <= 1e-9
+    # reference-style checks (prox_tv_test.py:129-178): uniform weights == tv1_2d, integer inputs are coerced
+    Yq = O.gen_cfg2(80, 72, seed=5, block=8)
+    assert relerr(ptv.tv1w_2d(Yq, np.full((79, 72), 0.3), np.full((80, 71), 0.3)), ptv.tv1_2d(Yq, 0.3)) <= 1e-9
+    a = -np.array([[1, 2, 3], [4, 5, 6], [7, 8, 9]]) / 10.
+    s1 = ptv.tv1w_2d(a, np.array([[1, 1, 1], [1, 1, 1]]), np.array([[1, 1], [1, 1], [1, 1]]), max_iters=100)
+    assert np.allclose(s1, ptv.tv1_2d(a, 1, max_iters=100), atol=1e-3)
+    with pytest.raises(AssertionError):
+        ptv.tv1w_2d(Yq, np.full((79, 72), -0.3), np.full((80, 71), 0.3))
+
+
+def test_weighted_dr_torch_and_f32(ptv, port):
+    import torch
+    rng = np.random.default_rng(32)
+    Y = O.gen_cfg2(160, 136, seed=6, block=16)
+    W1 = rng.uniform(0.05, 0.5, (159, 136)); W2 = rng.uniform(0.05, 0.5, (160, 135))
+    want = port.dr2l1w_tv(Y, W1, W2)[0]
+    dev = torch.device("cuda:0")
+    g = ptv.tv1w_2d(torch.tensor(np.ascontiguousarray(Y), device=dev), torch.tensor(W1, device=dev), torch.tensor(W2, device=dev))
+    assert g.is_cuda and g.dtype == torch.float64 and relerr(g.cpu().numpy(), want) <= 1e-9
+    g32 = ptv.tv1w_2d(torch.tensor(np.ascontiguousarray(Y), device=dev, dtype=torch.float32), torch.tensor(W1, device=dev),
+                      torch.tensor(W2, device=dev))
+    assert g32.dtype == torch.float32 and relerr(g32.cpu().numpy(), want) <= 5e-5
+
+
 def test_dr2_order_dependence_is_reproduced(ptv, port):
     """DR2_TV is unconverged by design: transposing the image changes the result by ~1e-3; we must match the reference's
     pass order, not a converged answer."""

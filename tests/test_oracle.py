@@ -35,6 +35,12 @@ def test_port_matches_golden_2d(golden, port):
         assert np.array_equal(o, golden["pd2_%d_out" % k]) and np.array_equal(info, golden["pd2_%d_info" % k])
 
 
+def test_port_matches_golden_weighted_2d(golden, port):
+    for k in range(int(golden["drw_count"])):
+        o, info = port.dr2l1w_tv(golden["drw_%d_Y" % k], golden["drw_%d_W1" % k], golden["drw_%d_W2" % k], maxit=int(golden["drw_%d_it" % k]))
+        assert np.array_equal(o, golden["drw_%d_out" % k]) and np.array_equal(info, golden["drw_%d_info" % k]), k
+
+
 def test_port_matches_golden_nd(golden, port):
     o, info = port.pd_tv(golden["pd3_V"], [0.2, 0.2, 0.2], [1, 2, 3])
     assert np.array_equal(o, golden["pd3_out"]) and np.array_equal(info, golden["pd3_info"])
@@ -67,6 +73,19 @@ def test_port_matches_compiled_reference_2d(port, ref):
     assert np.array_equal(a, b) and np.array_equal(ia, ib)
     a, ia = port.pd2_tv(Y, [0.2, 0.3], [2, 1]); b, ib = ref.pd2_tv(Y, [0.2, 0.3], [2, 1])
     assert np.array_equal(a, b) and ia[0] == ib[0]
+
+
+def test_port_matches_compiled_reference_weighted_2d(port, ref):
+    rng = np.random.default_rng(12)
+    for (M, N, it) in [(2, 2, 0), (4, 2, 5), (33, 47, 0), (70, 45, 0), (64, 64, 3)]:
+        Y = np.asfortranarray(rng.normal(0, 1, (M, N)))
+        W1 = rng.uniform(0, 0.6, (M - 1, N)); W2 = rng.uniform(0, 0.6, (M, N - 1))
+        a, ia = port.dr2l1w_tv(Y, W1, W2, maxit=it); b, ib = ref.dr2l1w_tv(Y, W1, W2, maxit=it, n_threads=3)
+        assert np.array_equal(a, b) and np.array_equal(ia, ib), (M, N)
+    # uniform weights: the weighted iteration is the unweighted one up to rounding (prox_tv_test.py:129-153 allows 1e-3)
+    Y = O.gen_cfg2(64, 48, seed=3, block=8)
+    a, _ = port.dr2l1w_tv(Y, np.full((63, 48), 0.2), np.full((64, 47), 0.2)); b, _ = port.dr2_tv(Y, 0.2)
+    assert np.abs(a - b).max() <= 1e-12
 
 
 # ---- known-answer properties (hold for the exact minimiser, any implementation) ----
