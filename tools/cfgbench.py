@@ -54,6 +54,23 @@ if "cfg4" in which:
     if small:
         want, winfo = P.pd_tv(Vf.astype(np.float64), [0.2, 0.2, 0.2], [1, 2, 3])
         print("   vs f64 oracle on f32-rounded input: rel err %.2e  iters oracle %d" % (np.abs(g - want).max() / np.abs(want).max(), winfo[0]))
+if "w2d" in which:
+    M = 1024 if small else 4096
+    rng = np.random.default_rng(0)
+    Y = O.gen_cfg2(M, M, seed=0)
+    Yd = torch.from_numpy(np.ascontiguousarray(Y.T)).cuda()                     # column-major image
+    W1 = torch.from_numpy(rng.uniform(0.1, 0.3, (M, M - 1))).cuda()              # (M-1) x N column-major == (N, M-1) row-major
+    W2 = torch.from_numpy(rng.uniform(0.1, 0.3, (M - 1, M))).cuda()              # M x (N-1) column-major == (N-1, M) row-major
+    outd = torch.empty_like(Yd); inf = np.zeros(3)
+    def runw():
+        lib.proxtv_DR2L1W_TV_dev_f64(M, M, C.c_void_p(Yd.data_ptr()), C.c_void_p(W1.data_ptr()), C.c_void_p(W2.data_ptr()),
+                                     C.c_void_p(outd.data_ptr()), 0, C.c_void_p(inf.ctypes.data), None)
+    ms = ev_time(runw, reps=3)
+    line = f"tv1w_2d DR2L1W_TV {M}x{M} f64 device-resident: {ms:.2f} ms  {M*M/ms/1e3:.1f} Mpix/s"
+    if small:
+        want, _ = P.dr2l1w_tv(Y, W1.cpu().numpy().T, W2.cpu().numpy().T)
+        line += "  rel err vs oracle %.2e" % (np.abs(outd.cpu().numpy().T - want).max() / np.abs(want).max())
+    print(line, flush=True)
 if "cfg5" in which:
     Bn, H = (16, 2048) if not small else (8, 512)
     imgs = torch.stack([torch.from_numpy(np.ascontiguousarray(O.gen_cfg2(H, H, seed=s).astype(np.float32))) for s in range(Bn)]).cuda()
