@@ -175,7 +175,7 @@ extern "C" {
 int proxtv_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; } return n; }
 const char* proxtv_last_error(void) { return g_err.c_str(); }
 const char* proxtv_version(void) { return "proxtv_b200 0.1 (sm_100a)"; }
-int proxtv_set_engine(int e) { int o = g_engine; if (e >= 0 && e <= 5) g_engine = e; return o; }
+int proxtv_set_engine(int e) { int o = g_engine; if (e >= 0 && e <= 6) g_engine = e; return o; }
 void* proxtv_host_alloc(size_t bytes) { void* p = nullptr; if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; } return p; }
 void proxtv_host_free(void* p) { if (p) cudaFreeHost(p); }
 void proxtv_profile_enable(int on) { profile_enable(on); }

@@ -22,6 +22,7 @@ template <typename T>
 cudaError_t prox_fibers_chunked_contig(const T* A, const T* B, const T* C, InOp op, T* X, int out_op, FiberGeom g, T lam,
                                        const T* lamv, cudaStream_t st, T* X2 = nullptr, long long inc2 = 0);
 template <typename T> cudaError_t gather_fibers(const T* A, const T* B, InOp op, T* out, FiberGeom g, cudaStream_t st);
+template <typename T> cudaError_t scatter_fibers(const T* in, T* X, FiberGeom g, cudaStream_t st);
 
 static inline size_t al256(size_t b) { return (b + 255) & ~(size_t)255; }
 
@@ -30,7 +31,7 @@ template <typename T> size_t ws_arrays_dr2_tspace() { return 7; }
 // returns 0 ok, 1 CUDA error, 2 shape not supported by the chunked kernel (nothing enqueued that matters: caller falls back)
 template <typename T>
 int dr2_tspace_body(size_t M, size_t N, int batch, const T* Y, T w1, T w2, T* out, int maxit, void* ws, double* scratch,
-                    cudaStream_t st) {
+                    cudaStream_t st, bool plain_transposes) {
     const long long per = (long long)M * N, n = per * batch;
     char* w = (char*)ws; const size_t ab = al256((size_t)n * sizeof(T));
     T* t = (T*)w; w += ab; T* t2 = (T*)w; w += ab; T* tT = (T*)w; w += ab; T* tT2 = (T*)w; w += ab;
@@ -50,9 +51,20 @@ int dr2_tspace_body(size_t M, size_t N, int batch, const T* Y, T w1, T w2, T* ou
             TTRY(prox_const_fibers<T>(t, per, batch, (int)M, w1, s, st));
             TTRY(ew_dr_reflect_bcast<T>(tT, s, sT, n, per, (int)M, (long long)N, st));
         } else {
-            KernelSpan sp(KC_PROX_CONTIG, 1, st);
-            TTRY(prox_fibers_chunked_contig<T>(t, nullptr, nullptr, IN_A, s, final ? OUT_DIFF : OUT_REFLECT, gcols, w1, nullptr, st,
-                                               sT, (long long)N));
+            { KernelSpan sp(KC_PROX_CONTIG, 1, st);
+              TTRY(prox_fibers_chunked_contig<T>(t, nullptr, nullptr, IN_A, s, final ? OUT_DIFF : OUT_REFLECT, gcols, w1, nullptr, st,
+                                                 plain_transposes ? nullptr : sT, (long long)N)); }
+            if (plain_transposes) { KernelSpan sp(KC_ELEMENTWISE, 1, st); TTRY(gather_fibers<T>(s, nullptr, IN_A, sT, gstr, st)); }
+        }
+        if (plain_transposes) {
+            // the fused row kernel stays in T-space (reads YT, sT, tT; writes tT'); one plain transpose brings t' back
+            T* dstT = tT2;
+            { KernelSpan sp(KC_PROX_STRIDED, 1, st);
+              TTRY(prox_fibers_chunked_contig<T>(YT, sT, final ? nullptr : tT, IN_A_MINUS_B, dstT, final ? OUT_DR_ROWS_FINAL : OUT_DR_ROWS,
+                                                 grows, w2, nullptr, st)); }
+            { KernelSpan sp(KC_ELEMENTWISE, 1, st); TTRY(scatter_fibers<T>(dstT, final ? out : t2, gstr, st)); }
+            if (!final) { T* tmp = t; t = t2; t2 = tmp; tmp = tT; tT = tT2; tT2 = tmp; }
+            continue;
         }
         KernelSpan sp(KC_PROX_STRIDED, 1, st);
         if (!final) {
@@ -68,7 +80,7 @@ int dr2_tspace_body(size_t M, size_t N, int batch, const T* Y, T w1, T w2, T* ou
 
 template size_t ws_arrays_dr2_tspace<double>();
 template size_t ws_arrays_dr2_tspace<float>();
-template int dr2_tspace_body<double>(size_t, size_t, int, const double*, double, double, double*, int, void*, double*, cudaStream_t);
-template int dr2_tspace_body<float>(size_t, size_t, int, const float*, float, float, float*, int, void*, double*, cudaStream_t);
+template int dr2_tspace_body<double>(size_t, size_t, int, const double*, double, double, double*, int, void*, double*, cudaStream_t, bool);
+template int dr2_tspace_body<float>(size_t, size_t, int, const float*, float, float, float*, int, void*, double*, cudaStream_t, bool);
 
 }  // namespace ptv

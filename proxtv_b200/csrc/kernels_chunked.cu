@@ -79,6 +79,36 @@ __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; as
 #define PHASE_MARK(k) do { } while (0)
 #endif
 
+// One batch of the fill phase: FW consecutive 32-sample windows of one fiber, handled by one warp (see the kernel).
+template <typename T, int FW, int CL>
+__device__ __forceinline__ void fill_batch(int c0, int nchunks, int n, int lane, uint32_t below, T* __restrict__ xr, long long gb, long long x2b,
+                                           const uint32_t* __restrict__ Pm, const T* __restrict__ cv, T* __restrict__ yr, int out_op,
+                                           const T* __restrict__ A, const T* __restrict__ B, const T* __restrict__ C, T* __restrict__ X2,
+                                           long long inc2) {
+    constexpr int PADE = PadCfg<T>::PADE;
+    T v[FW];
+#pragma unroll
+    for (int u = 0; u < FW; u++) {
+        const int c = c0 + u;
+        v[u] = T(0);
+        if (c < nchunks && (c << 5) + lane < n) {
+            const uint32_t w = Pm[c] & below;
+            v[u] = w ? __ldcg(xr + (c << 5) + high_bit(w)) : cv[c];
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int u = 0; u < FW; u++) {
+        const int c = c0 + u, j = (c << 5) + lane;
+        if (c < nchunks && j < n) {
+            const T o = apply_out_ex<T>(out_op, yr[j + c * PADE], v[u], A, B, C, gb + j);
+            xr[j] = o;
+            if (CL == 0) { if (X2) X2[x2b + (long long)j * inc2] = o; }      // scattered 8-byte stores
+            else yr[j + c * PADE] = o;                                       // keep the finished row for the exchange
+        }
+    }
+}
+
 // CL: how the optional transposed second output X2 is produced.  0: plain 8-byte scattered stores (slow: partial-sector writes make
 // L2 read-modify-write every sector); >= 1: the finished fiber rows of CL consecutive CTAs (a thread-block cluster when CL > 1)
 // are exchanged through (distributed) shared memory so that fpb*CL adjacent fibers are written together as full 32-byte sectors.
@@ -179,37 +209,24 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 2 : 1) k_prox_chunked_cont
     //      f64): FW 2/4/8 -> 206/195/189 us; FW >= 16 costs registers (a CTA less per SM); software-pipelining the batches or
     //      hoisting the Douglas-Rachford operand loads ahead of the stores was slower (200-208 us). ----
     constexpr int FW = 8;
-    const int warp = tid >> 5, lane = tid & 31, wstep = (blockDim.x >> 5) * FW;
+    const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
     const uint32_t below = 0xffffffffu >> (31 - lane);
-    for (int fb2 = 0; fb2 < nfib; fb2++) {
-        const long long gb = (f0 + fb2) * (long long)n;
-        T* xr = X + gb;
-        const long long x2b = X2 ? ((f0 + fb2) / inc2) * inc2 * n + (f0 + fb2) % inc2 : 0;
-        const uint32_t* Pm = mk + (size_t)fb2 * lpf;
-        const T* cv = cval + (size_t)fb2 * lpf;
-        T* yr = ys + (size_t)fb2 * npad;
-        for (int c0 = warp * FW; c0 < nchunks; c0 += wstep) {
-            T v[FW];
-#pragma unroll
-            for (int u = 0; u < FW; u++) {
-                const int c = c0 + u;
-                v[u] = T(0);
-                if (c < nchunks && (c << 5) + lane < n) {
-                    const uint32_t w = Pm[c] & below;
-                    v[u] = w ? __ldcg(xr + (c << 5) + high_bit(w)) : cv[c];
-                }
-            }
-            __syncwarp();
-#pragma unroll
-            for (int u = 0; u < FW; u++) {
-                const int c = c0 + u, j = (c << 5) + lane;
-                if (c < nchunks && j < n) {
-                    const T o = apply_out_ex<T>(out_op, yr[j + c * PADE], v[u], A, B, C, gb + j);
-                    xr[j] = o;
-                    if (CL == 0) { if (X2) X2[x2b + (long long)j * inc2] = o; }      // scattered 8-byte stores
-                    else yr[j + c * PADE] = o;                                       // keep the finished row for the exchange
-                }
-            }
+    const int bpf = (nchunks + FW - 1) / FW;                      // batches per fiber
+    if (bpf >= nwarps) {                                          // long fibers: every warp has work inside each fiber
+        for (int fb2 = 0; fb2 < nfib; fb2++) {
+            const long long gb = (f0 + fb2) * (long long)n;
+            const long long x2b = X2 ? ((f0 + fb2) / inc2) * inc2 * n + (f0 + fb2) % inc2 : 0;
+            for (int c0 = warp * FW; c0 < nchunks; c0 += nwarps * FW)
+                fill_batch<T, FW, CL>(c0, nchunks, n, lane, below, X + gb, gb, x2b, mk + (size_t)fb2 * lpf, cval + (size_t)fb2 * lpf,
+                                      ys + (size_t)fb2 * npad, out_op, A, B, C, X2, inc2);
+        }
+    } else {                                                      // short fibers: deal all (fiber, batch) pairs to the warps
+        for (int bi = warp; bi < nfib * bpf; bi += nwarps) {
+            const int fb2 = bi / bpf, c0 = (bi - fb2 * bpf) * FW;
+            const long long gb = (f0 + fb2) * (long long)n;
+            const long long x2b = X2 ? ((f0 + fb2) / inc2) * inc2 * n + (f0 + fb2) % inc2 : 0;
+            fill_batch<T, FW, CL>(c0, nchunks, n, lane, below, X + gb, gb, x2b, mk + (size_t)fb2 * lpf, cval + (size_t)fb2 * lpf,
+                                  ys + (size_t)fb2 * npad, out_op, A, B, C, X2, inc2);
         }
     }
     __syncthreads();

@@ -32,13 +32,13 @@ __global__ void __launch_bounds__(32) k_prox_seq(const T* __restrict__ A, const 
         while (s.i < n) {
             int k = s.step(n, y, lamf, f, l, v);
             if (k != K_NONE)
-                for (int q = f; q <= l; q++) { const long long g2 = base + (long long)q * inc; X[g2] = out_op ? apply_out_ex<T>(out_op, y(q), v, A, B, C, g2) : v; }
+                for (int q = f; q <= l; q++) { const long long g2 = base + (long long)q * inc; X[g2] = out_op ? apply_out_any<T>(out_op, y(q), v, A, B, C, g2) : v; }
         }
-        for (int q = s.last + 1; q < n; q++) { const long long g2 = base + (long long)q * inc; X[g2] = out_op ? apply_out_ex<T>(out_op, y(q), s.lo, A, B, C, g2) : s.lo; }
+        for (int q = s.last + 1; q < n; q++) { const long long g2 = base + (long long)q * inc; X[g2] = out_op ? apply_out_any<T>(out_op, y(q), s.lo, A, B, C, g2) : s.lo; }
     };
     if (n <= 0) return;
     if (WEIGHTED) {
-        if (n == 1) { X[base] = apply_out_ex<T>(out_op, y(0), y(0), A, B, C, base); return; }     // the reference reads lambda[0] out of bounds here; identity is the limit
+        if (n == 1) { X[base] = apply_out_any<T>(out_op, y(0), y(0), A, B, C, base); return; }     // the reference reads lambda[0] out of bounds here; identity is the limit
         auto ld = [&](int i) -> T { return lamv[wbase + (long long)i * inc]; };
         run(ArrayLam<T, decltype(ld)>{ld});
     } else {

@@ -119,7 +119,8 @@ static int dr2_piped_body(size_t M, size_t N, const T* Y, T w1, T w2, T* out, in
 }
 
 template <typename T>
-int dr2_tspace_body(size_t M, size_t N, int batch, const T* Y, T w1, T w2, T* out, int maxit, void* ws, double* scratch, cudaStream_t st);
+int dr2_tspace_body(size_t M, size_t N, int batch, const T* Y, T w1, T w2, T* out, int maxit, void* ws, double* scratch, cudaStream_t st,
+                    bool plain_transposes);
 
 struct DrGraphKey {
     size_t tsize, M, N; const void* Y; void* out; void* ws; double w1, w2; int maxit;
@@ -159,15 +160,16 @@ int dr2_device(size_t M, size_t N, int batch, int row_major, const T* Y, T w1, T
     // 4096x4096 f64 solve, kept for comparison); everything else: the plain serial schedule below.
     // The whole solve is captured once into a CUDA graph and replayed while the call's arguments stay the same (no host
     // launch latency); event timing of single launches needs plain launches, so profiling bypasses the graph.
-    const bool tspace = eng == ENGINE_TSPACE && !row_major && M >= 64 && N >= 64 && g_pipe.init();
+    const bool tpose = eng == ENGINE_TPOSE;
+    const bool tspace = (eng == ENGINE_TSPACE || tpose) && !row_major && M >= 64 && N >= 64 && g_pipe.init();
     const bool piped = (eng == ENGINE_AUTO || eng == ENGINE_PIPELINED) && !row_major && batch == 1 && M >= 1024 && N >= 1024 && M % 2 == 0 && N % 2 == 0 &&
                        (size_t)((M > N ? M : N) * sizeof(T)) <= 96 * 1024 && g_pipe.init();
     if (tspace || piped) {
         auto body = [&](cudaStream_t bs) -> int {
-            return tspace ? dr2_tspace_body<T>(M, N, batch, Y, w1, w2, out, maxit, ws, scratch, bs)
+            return tspace ? dr2_tspace_body<T>(M, N, batch, Y, w1, w2, out, maxit, ws, scratch, bs, tpose)
                           : dr2_piped_body<T>(M, N, Y, w1, w2, out, maxit, t, s, x, scr, scratch, gc, n, bs);
         };
-        DrGraphKey key{sizeof(T) + (tspace ? 100u : 0u) + 1000u * (size_t)batch, M, N, (const void*)Y, (void*)out, ws, (double)w1,
+        DrGraphKey key{sizeof(T) + (tspace ? 100u : 0u) + (tpose ? 200u : 0u) + 1000u * (size_t)batch, M, N, (const void*)Y, (void*)out, ws, (double)w1,
                        (double)w2, maxit};
         int rc = -1;
         if (!profile_is_enabled()) {

@@ -59,7 +59,8 @@ __global__ void k_scatter(const T* __restrict__ in, T* __restrict__ X, int len, 
 
 // scatter with a fused output form: X[g] = apply_out_ex(out_op, in(g), x(g)) where in(g) = A[g] (op) B[g] is recomputed exactly as
 // the gather computed it, and x is the prox value coming back from the transposed layout.
-template <typename T>
+// WOPS: also knows the weighted Douglas-Rachford forms (kept out of the default instance: the wider switch slows it measurably)
+template <typename T, bool WOPS>
 __global__ void k_scatter_ex(const T* __restrict__ in, const T* __restrict__ A, const T* __restrict__ B, const T* __restrict__ C, int op,
                              int out_op, T* __restrict__ X, int len, long long inc, long long r_begin, long long r_end) {
     __shared__ T tile[32][33];
@@ -80,7 +81,7 @@ __global__ void k_scatter_ex(const T* __restrict__ in, const T* __restrict__ A, 
             const long long g = o * slab + (long long)k * inc + r;
             T yin = A[g];
             if (op == IN_A_MINUS_B) yin = yin - B[g]; else if (op == IN_A_PLUS_B) yin = yin + B[g];
-            X[g] = apply_out_ex<T>(out_op, yin, tile[tx][dy], A, B, C, g);
+            X[g] = WOPS ? apply_out_any<T>(out_op, yin, tile[tx][dy], A, B, C, g) : apply_out_ex<T>(out_op, yin, tile[tx][dy], A, B, C, g);
         }
     }
 }
@@ -92,7 +93,10 @@ cudaError_t scatter_fibers_ex(const T* in, const T* A, const T* B, const T* C, I
     for (long long o0 = 0; o0 < outer; o0 += 65535) {
         grid.z = (unsigned)((outer - o0) < 65535 ? (outer - o0) : 65535);
         const long long off = o0 * (long long)g.len * g.inc;
-        k_scatter_ex<T><<<grid, block, 0, st>>>(in + off, A + off, B ? B + off : nullptr, C ? C + off : nullptr, (int)op, out_op, X + off, g.len, g.inc, 0, g.inc);
+        if (out_op >= OUT_DRW_ROWS)
+            k_scatter_ex<T, true><<<grid, block, 0, st>>>(in + off, A + off, B ? B + off : nullptr, C ? C + off : nullptr, (int)op, out_op, X + off, g.len, g.inc, 0, g.inc);
+        else
+            k_scatter_ex<T, false><<<grid, block, 0, st>>>(in + off, A + off, B ? B + off : nullptr, C ? C + off : nullptr, (int)op, out_op, X + off, g.len, g.inc, 0, g.inc);
     }
     return cudaGetLastError();
 }
@@ -137,7 +141,8 @@ cudaError_t scatter_fibers_ex_range(const T* in, const T* A, const T* B, const T
                                     long long r_begin, long long r_end, cudaStream_t st) {
     if (r_end <= r_begin) return cudaSuccess;
     dim3 grid((unsigned)((r_end - r_begin + 31) / 32), (unsigned)((g.len + 31) / 32), 1), block(32, 8);
-    k_scatter_ex<T><<<grid, block, 0, st>>>(in, A, B, C, (int)op, out_op, X, g.len, g.inc, r_begin, r_end);
+    if (out_op >= OUT_DRW_ROWS) k_scatter_ex<T, true><<<grid, block, 0, st>>>(in, A, B, C, (int)op, out_op, X, g.len, g.inc, r_begin, r_end);
+    else k_scatter_ex<T, false><<<grid, block, 0, st>>>(in, A, B, C, (int)op, out_op, X, g.len, g.inc, r_begin, r_end);
     return cudaGetLastError();
 }
 #define INST_R(T) \

@@ -315,13 +315,13 @@ def test_pipelined_schedule_equals_serial_schedule(ptv, port):
     a = ptv.tv1_2d(Y, 0.2)
     a2 = ptv.tv1_2d(Y, 0.2)                       # second call: graph replay
     res = {}
-    for e in ("chunked", "pipelined", "tspace"):
+    for e in ("chunked", "pipelined", "tspace", "tpose"):
         prev = ptv.set_engine(e)
         try:
             res[e] = ptv.tv1_2d(Y, 0.2)
         finally:
             ptv.set_engine(prev)
-    assert np.array_equal(a, a2) and np.array_equal(a, res["chunked"]) and np.array_equal(a, res["pipelined"]) and np.array_equal(a, res["tspace"])
+    assert np.array_equal(a, a2) and np.array_equal(a, res["chunked"]) and np.array_equal(a, res["pipelined"]) and np.array_equal(a, res["tspace"]) and np.array_equal(a, res["tpose"])
     Z = O.gen_cfg2(200, 136, seed=6, block=8)     # small, odd-ish shape through the same default schedule
     assert relerr(ptv.tv1_2d(Z, 0.3), port.dr2_tv(Z, 0.3)[0]) <= 1e-9
     S = np.asfortranarray(Y[:, :1024])
