@@ -5,6 +5,7 @@
 // the two sums (image mean, stop criterion), which are tree reductions with a fixed, deterministic order instead of the
 // reference's serial / OpenMP-reduction order.
 #include "ptv_internal.h"
+#include <stdint.h>
 
 namespace ptv {
 
@@ -170,11 +171,70 @@ template <typename T> __global__ void k_pd_combine(T* const* __restrict__ p, T* 
     acc = block_sum(acc);
     if (threadIdx.x == 0) partial[blockIdx.x] = acc;
 }
-template <typename T> cudaError_t ew_pd_combine(T* const* p, T* const* z, int k, T* x, long long n, double* scratch, double* result,
-                                                cudaStream_t st) {
+// Same arithmetic, K known at compile time, the 2K array pointers passed by value and 16-byte vector accesses: the generic kernel
+// above chases 2K pointers through memory and moves 4-8 bytes per access (measured 1474 us for 3 x 67M f32, 3.2x the HBM time).
+template <typename T, int K> struct PdPtrs { T* p[K]; T* z[K]; };
+template <typename T, int K>
+__global__ void __launch_bounds__(256) k_pd_combine_vec(PdPtrs<T, K> a, T* __restrict__ x, long long n, double* __restrict__ partial) {
+    constexpr int V = 16 / (int)sizeof(T);
+    struct alignas(16) Vec { T v[V]; };
+    double acc = 0;
+    const T kk = (T)K;
+    const long long nv = n / V;
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < nv; q += (long long)gridDim.x * blockDim.x) {
+        Vec xo = reinterpret_cast<const Vec*>(x)[q], pv[K], zv[K], xn;
+#pragma unroll
+        for (int i = 0; i < K; i++) { pv[i] = reinterpret_cast<const Vec*>(a.p[i])[q]; zv[i] = reinterpret_cast<const Vec*>(a.z[i])[q]; }
+#pragma unroll
+        for (int e = 0; e < V; e++) {
+            T s = T(0);
+#pragma unroll
+            for (int i = 0; i < K; i++) s += pv[i].v[e] / kk;
+#pragma unroll
+            for (int i = 0; i < K; i++) zv[i].v[e] += s - pv[i].v[e];
+            xn.v[e] = s;
+            acc += fabs((double)s - (double)xo.v[e]);
+        }
+#pragma unroll
+        for (int i = 0; i < K; i++) reinterpret_cast<Vec*>(a.z[i])[q] = zv[i];
+        reinterpret_cast<Vec*>(x)[q] = xn;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)                       // the < V trailing elements
+        for (long long q = nv * V; q < n; q++) {
+            T xo = x[q], s = T(0);
+            for (int i = 0; i < K; i++) s += a.p[i][q] / kk;
+            for (int i = 0; i < K; i++) a.z[i][q] += s - a.p[i][q];
+            x[q] = s; acc += fabs((double)s - (double)xo);
+        }
+    acc = block_sum(acc);
+    if (threadIdx.x == 0) partial[blockIdx.x] = acc;
+}
+template <typename T, int K>
+static void launch_pd_vec(T* const* hp, T* const* hz, T* x, long long n, double* scratch, int nblk, cudaStream_t st) {
+    PdPtrs<T, K> a;
+    for (int i = 0; i < K; i++) { a.p[i] = hp[i]; a.z[i] = hz[i]; }
+    k_pd_combine_vec<T, K><<<nblk, 256, 0, st>>>(a, x, n, scratch);
+}
+
+// dp, dz: device copies of the pointer arrays (generic kernel); hp, hz: the same pointers on the host (vector kernel, K <= 4)
+template <typename T> cudaError_t ew_pd_combine(T* const* dp, T* const* dz, T* const* hp, T* const* hz, int k, T* x, long long n,
+                                                double* scratch, double* result, cudaStream_t st) {
     KernelSpan span(KC_ELEMENTWISE, 2, st);
-    int nblk = (int)grid_for(n, 256, 4); if (nblk > REDUCE_BLOCKS) nblk = REDUCE_BLOCKS;
-    k_pd_combine<T><<<nblk, 256, 0, st>>>(p, z, k, x, n, scratch);
+    bool aligned = (((uintptr_t)x) & 15) == 0;
+    for (int i = 0; i < k && aligned; i++) aligned = ((((uintptr_t)hp[i]) | ((uintptr_t)hz[i])) & 15) == 0;
+    int nblk;
+    if (aligned && k >= 1 && k <= 4) {
+        nblk = (int)grid_for(n, 256, 16 / (int)sizeof(T) * 2); if (nblk > REDUCE_BLOCKS) nblk = REDUCE_BLOCKS;
+        switch (k) {
+            case 1: launch_pd_vec<T, 1>(hp, hz, x, n, scratch, nblk, st); break;
+            case 2: launch_pd_vec<T, 2>(hp, hz, x, n, scratch, nblk, st); break;
+            case 3: launch_pd_vec<T, 3>(hp, hz, x, n, scratch, nblk, st); break;
+            default: launch_pd_vec<T, 4>(hp, hz, x, n, scratch, nblk, st); break;
+        }
+    } else {
+        nblk = (int)grid_for(n, 256, 4); if (nblk > REDUCE_BLOCKS) nblk = REDUCE_BLOCKS;
+        k_pd_combine<T><<<nblk, 256, 0, st>>>(dp, dz, k, x, n, scratch);
+    }
     k_final_mean<<<1, 256, 0, st>>>(scratch, nblk, n, result);
     return cudaGetLastError();
 }
@@ -188,7 +248,7 @@ template <typename T> cudaError_t ew_pd_combine(T* const* p, T* const* z, int k,
     template cudaError_t ew_dual_update<T>(T*, const T*, const T*, long long, cudaStream_t); \
     template cudaError_t ew_dr_reflect_bcast<T>(const T*, const T*, T*, long long, long long, int, long long, cudaStream_t); \
     template cudaError_t ew_mean_abs_diff<T>(const T*, const T*, long long, double*, double*, cudaStream_t); \
-    template cudaError_t ew_pd_combine<T>(T* const*, T* const*, int, T*, long long, double*, double*, cudaStream_t);
+    template cudaError_t ew_pd_combine<T>(T* const*, T* const*, T* const*, T* const*, int, T*, long long, double*, double*, cudaStream_t);
 INST(double)
 INST(float)
 

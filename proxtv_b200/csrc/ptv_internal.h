@@ -75,8 +75,8 @@ template <typename T> cudaError_t prox_const_fibers(const T* c, long long c_stri
 template <typename T> cudaError_t ew_dual_update(T* p, const T* a, const T* b, long long n, cudaStream_t st);  // p += a - b
 template <typename T> cudaError_t ew_mean_abs_diff(const T* a, const T* b, long long n, double* scratch, double* result,
                                                    cudaStream_t st);                  // *result = mean|a-b| (device)
-template <typename T> cudaError_t ew_pd_combine(T* const* p, T* const* z, int k, T* x, long long n, double* scratch,
-                                                double* result, cudaStream_t st);
+template <typename T> cudaError_t ew_pd_combine(T* const* dp, T* const* dz, T* const* hp, T* const* hz, int k, T* x, long long n,
+                                                double* scratch, double* result, cudaStream_t st);
 constexpr int REDUCE_BLOCKS = 1184;    // 148 SMs x 8; partial sums are combined in a fixed order (deterministic)
 
 // ---- device-resident solvers (solver.cu).  All arrays are device pointers; `ws` must hold ws_bytes_*() bytes. ----

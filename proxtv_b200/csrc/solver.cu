@@ -371,7 +371,7 @@ int pd_device(const T* y, const double* lam, const double* dims, T* x, double* i
         while (stop > STOP_PD && iters < maxIters) {                                                  // :151
             for (int i = 0; i < npen; i++)
                 PTV_TRY(prox_fibers<T>(hz[i], nullptr, IN_A, hp[i], 0, g[i], (T)lam[i], nullptr, eng, scr, st));  // :171-208
-            PTV_TRY(ew_pd_combine<T>(dp, dz, npen, x, n, scratch, dres, st));                         // :212-227
+            PTV_TRY(ew_pd_combine<T>(dp, dz, hp, hz, npen, x, n, scratch, dres, st));                         // :212-227
             if (!read_stop(dres, &stop, st)) { PTV_TRY(cudaGetLastError()); PTV_TRY(cudaErrorUnknown); }
             iters++;
         }

@@ -8,6 +8,7 @@
 // strided fibers directly (DESIGN.md "next") removes these two extra sweeps.
 #include "ptv_internal.h"
 #include "chunk_core.cuh"
+#include <stdint.h>
 
 namespace ptv {
 
@@ -85,6 +86,95 @@ __global__ void k_scatter_ex(const T* __restrict__ in, const T* __restrict__ A, 
         }
     }
 }
+// ---- 64 x 64 tiles with 8-byte accesses for 4-byte element types: a 32 x 32 tile of floats moves only 128-byte rows and
+//      leaves half of the memory pipeline idle (measured 197 / 178 us per 268 MB f32 gather / scatter vs ~95 us of HBM time).
+//      Requirements (checked by the launchers): len, inc, k_begin/k_end, r_begin/r_end even and all bases 8-byte aligned. ----
+struct alignas(8) F2 { float a, b; };
+__device__ __forceinline__ float in_apply(int op, float a, float b) { return op == IN_A_MINUS_B ? a - b : (op == IN_A_PLUS_B ? a + b : a); }
+
+__global__ void __launch_bounds__(256) k_gather_w(const float* __restrict__ A, const float* __restrict__ B, int op, float* __restrict__ out, int len,
+                                                 long long inc, int k_begin, int k_end) {
+    __shared__ float tile[64][65];
+    const long long o = blockIdx.z, slab = (long long)len * inc;
+    const long long r0 = (long long)blockIdx.x * 64;
+    const int k0 = k_begin + blockIdx.y * 64;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int flen = len;
+    len = len < k_end ? len : k_end;
+    for (int dy = ty; dy < 64; dy += 8) {
+        const int k = k0 + dy; const long long r = r0 + 2 * tx;
+        if (k < len && r < inc) {
+            const long long idx = o * slab + (long long)k * inc + r;
+            F2 a = *reinterpret_cast<const F2*>(A + idx), b{0.f, 0.f};
+            if (op != IN_A) b = *reinterpret_cast<const F2*>(B + idx);
+            tile[dy][2 * tx] = in_apply(op, a.a, b.a); tile[dy][2 * tx + 1] = in_apply(op, a.b, b.b);
+        }
+    }
+    __syncthreads();
+    for (int dy = ty; dy < 64; dy += 8) {
+        const long long r = r0 + dy; const int k = k0 + 2 * tx;
+        if (k < len && r < inc) *reinterpret_cast<F2*>(out + o * slab + r * flen + k) = F2{tile[2 * tx][dy], tile[2 * tx + 1][dy]};
+    }
+}
+
+template <bool WOPS, bool EX>
+__global__ void __launch_bounds__(256) k_scatter_w(const float* __restrict__ in, const float* __restrict__ A, const float* __restrict__ B,
+                                                  const float* __restrict__ C, int op, int out_op, float* __restrict__ X, int len, long long inc,
+                                                  long long r_begin, long long r_end) {
+    __shared__ float tile[64][65];
+    const long long o = blockIdx.z, slab = (long long)len * inc;
+    const long long r0 = r_begin + (long long)blockIdx.x * 64;
+    const int k0 = blockIdx.y * 64;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const long long rlim = inc < r_end ? inc : r_end;
+    for (int dy = ty; dy < 64; dy += 8) {
+        const long long r = r0 + dy; const int k = k0 + 2 * tx;
+        if (k < len && r < rlim) { const F2 v = *reinterpret_cast<const F2*>(in + o * slab + r * len + k); tile[dy][2 * tx] = v.a; tile[dy][2 * tx + 1] = v.b; }
+    }
+    __syncthreads();
+    for (int dy = ty; dy < 64; dy += 8) {
+        const int k = k0 + dy; const long long r = r0 + 2 * tx;
+        if (k < len && r < rlim) {
+            const long long g = o * slab + (long long)k * inc + r;
+            F2 res{tile[2 * tx][dy], tile[2 * tx + 1][dy]};
+            if (EX) {
+                const F2 a = *reinterpret_cast<const F2*>(A + g);
+                F2 b{0.f, 0.f};
+                if (op != IN_A) b = *reinterpret_cast<const F2*>(B + g);
+                const float y0 = in_apply(op, a.a, b.a), y1 = in_apply(op, a.b, b.b);
+                res.a = WOPS ? apply_out_any<float>(out_op, y0, res.a, A, B, C, g) : apply_out_ex<float>(out_op, y0, res.a, A, B, C, g);
+                res.b = WOPS ? apply_out_any<float>(out_op, y1, res.b, A, B, C, g + 1) : apply_out_ex<float>(out_op, y1, res.b, A, B, C, g + 1);
+            }
+            *reinterpret_cast<F2*>(X + g) = res;
+        }
+    }
+}
+static inline bool wide_ok(const void* a, const void* b, const void* c, const void* d, const void* e, long long len, long long inc,
+                           long long lo, long long hi) {
+    const uintptr_t m = (uintptr_t)a | (uintptr_t)b | (uintptr_t)c | (uintptr_t)d | (uintptr_t)e;
+    return (m & 7) == 0 && len % 2 == 0 && inc % 2 == 0 && lo % 2 == 0 && hi % 2 == 0;
+}
+// float front ends: the wide kernels when the shape allows, else fall through (return false) to the generic 32 x 32 tiles
+static bool gather_wide(const float* A, const float* B, int op, float* out, int len, long long inc, int k_begin, int k_end, unsigned gz,
+                        cudaStream_t st) {
+    if (!wide_ok(A, B, out, nullptr, nullptr, len, inc, k_begin, k_end)) return false;
+    dim3 grid((unsigned)((inc + 63) / 64), (unsigned)((k_end - k_begin + 63) / 64), gz), block(32, 8);
+    k_gather_w<<<grid, block, 0, st>>>(A, B, op, out, len, inc, k_begin, k_end);
+    return true;
+}
+static bool gather_wide(const double*, const double*, int, double*, int, long long, int, int, unsigned, cudaStream_t) { return false; }
+static bool scatter_wide(const float* in, const float* A, const float* B, const float* C, int op, int out_op, bool ex, float* X, int len,
+                         long long inc, long long r_begin, long long r_end, unsigned gz, cudaStream_t st) {
+    if (!wide_ok(in, A, B, C, X, len, inc, r_begin, r_end)) return false;
+    dim3 grid((unsigned)((r_end - r_begin + 63) / 64), (unsigned)((len + 63) / 64), gz), block(32, 8);
+    if (!ex) k_scatter_w<false, false><<<grid, block, 0, st>>>(in, A, B, C, op, out_op, X, len, inc, r_begin, r_end);
+    else if (out_op >= OUT_DRW_ROWS) k_scatter_w<true, true><<<grid, block, 0, st>>>(in, A, B, C, op, out_op, X, len, inc, r_begin, r_end);
+    else k_scatter_w<false, true><<<grid, block, 0, st>>>(in, A, B, C, op, out_op, X, len, inc, r_begin, r_end);
+    return true;
+}
+static bool scatter_wide(const double*, const double*, const double*, const double*, int, int, bool, double*, int, long long, long long,
+                         long long, unsigned, cudaStream_t) { return false; }
+
 template <typename T>
 cudaError_t scatter_fibers_ex(const T* in, const T* A, const T* B, const T* C, InOp op, int out_op, T* X, FiberGeom g, cudaStream_t st) {
     if (g.nf <= 0 || g.len <= 0) return cudaSuccess;
@@ -93,6 +183,7 @@ cudaError_t scatter_fibers_ex(const T* in, const T* A, const T* B, const T* C, I
     for (long long o0 = 0; o0 < outer; o0 += 65535) {
         grid.z = (unsigned)((outer - o0) < 65535 ? (outer - o0) : 65535);
         const long long off = o0 * (long long)g.len * g.inc;
+        if (scatter_wide(in + off, A + off, B ? B + off : nullptr, C ? C + off : nullptr, (int)op, out_op, true, X + off, g.len, g.inc, 0, g.inc, grid.z, st)) continue;
         if (out_op >= OUT_DRW_ROWS)
             k_scatter_ex<T, true><<<grid, block, 0, st>>>(in + off, A + off, B ? B + off : nullptr, C ? C + off : nullptr, (int)op, out_op, X + off, g.len, g.inc, 0, g.inc);
         else
@@ -111,6 +202,7 @@ cudaError_t gather_fibers(const T* A, const T* B, InOp op, T* out, FiberGeom g, 
     for (long long o0 = 0; o0 < outer; o0 += 65535) {                // gridDim.z limit
         grid.z = (unsigned)((outer - o0) < 65535 ? (outer - o0) : 65535);
         const long long off = o0 * (long long)g.len * g.inc;
+        if (gather_wide(A + off, B ? B + off : nullptr, (int)op, out + off, g.len, g.inc, 0, g.len, grid.z, st)) continue;
         k_gather<T><<<grid, block, 0, st>>>(A + off, B ? B + off : nullptr, (int)op, out + off, g.len, g.inc, 0, g.len);
     }
     return cudaGetLastError();
@@ -123,6 +215,7 @@ cudaError_t scatter_fibers(const T* in, T* X, FiberGeom g, cudaStream_t st) {
     for (long long o0 = 0; o0 < outer; o0 += 65535) {
         grid.z = (unsigned)((outer - o0) < 65535 ? (outer - o0) : 65535);
         const long long off = o0 * (long long)g.len * g.inc;
+        if (scatter_wide(in + off, nullptr, nullptr, nullptr, 0, 0, false, X + off, g.len, g.inc, 0, g.inc, grid.z, st)) continue;
         k_scatter<T><<<grid, block, 0, st>>>(in + off, X + off, g.len, g.inc);
     }
     return cudaGetLastError();
@@ -132,6 +225,7 @@ cudaError_t scatter_fibers(const T* in, T* X, FiberGeom g, cudaStream_t st) {
 template <typename T>
 cudaError_t gather_fibers_range(const T* A, const T* B, InOp op, T* out, FiberGeom g, int k_begin, int k_end, cudaStream_t st) {
     if (k_end <= k_begin) return cudaSuccess;
+    if (gather_wide(A, B, (int)op, out, g.len, g.inc, k_begin, k_end, 1, st)) return cudaGetLastError();
     dim3 grid((unsigned)((g.inc + 31) / 32), (unsigned)((k_end - k_begin + 31) / 32), 1), block(32, 8);
     k_gather<T><<<grid, block, 0, st>>>(A, B, (int)op, out, g.len, g.inc, k_begin, k_end);
     return cudaGetLastError();
@@ -140,6 +234,7 @@ template <typename T>
 cudaError_t scatter_fibers_ex_range(const T* in, const T* A, const T* B, const T* C, InOp op, int out_op, T* X, FiberGeom g,
                                     long long r_begin, long long r_end, cudaStream_t st) {
     if (r_end <= r_begin) return cudaSuccess;
+    if (scatter_wide(in, A, B, C, (int)op, out_op, true, X, g.len, g.inc, r_begin, r_end, 1, st)) return cudaGetLastError();
     dim3 grid((unsigned)((r_end - r_begin + 31) / 32), (unsigned)((g.len + 31) / 32), 1), block(32, 8);
     if (out_op >= OUT_DRW_ROWS) k_scatter_ex<T, true><<<grid, block, 0, st>>>(in, A, B, C, (int)op, out_op, X, g.len, g.inc, r_begin, r_end);
     else k_scatter_ex<T, false><<<grid, block, 0, st>>>(in, A, B, C, (int)op, out_op, X, g.len, g.inc, r_begin, r_end);
