@@ -21,3 +21,8 @@ kms = (C.c_double * 3)(); kl = (C.c_longlong * 3)(); ks = (C.c_longlong * 3)()
 lib.proxtv_profile_read(kms, kl, ks)
 print("PD_TV", shp, "f32 total %.1f ms iters %d" % (e0.elapsed_time(e1), inf[0]), "class ms:", [round(kms[i], 1) for i in range(3)], "spans:", [ks[i] for i in range(3)],
       "avg us:", [round(1e3 * kms[i] / max(ks[i], 1), 1) for i in range(3)])
+if hasattr(lib, "proxtv_debug_phase_read"):               # debug build: make EXTRA=-DPTV_PHASE_TIMING
+    ph = (C.c_ulonglong * 8)(); lib.proxtv_debug_phase_read(ph, 1)
+    tot = sum(ph[k] for k in range(5))
+    print("    contig-kernel phases (CTA-time share) stage/round0/rounds/cval/fill: " + " ".join(f"{100*ph[k]/tot:.1f}%" for k in range(5))
+          + f"  mean CTA life {tot/ph[7]/1e3:.1f} us, rounds {ph[6]/ph[7]:.2f}")
