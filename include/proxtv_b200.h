@@ -81,8 +81,10 @@ int proxtv_device_count(void);                 /* usable CUDA devices (0 => ever
 const char *proxtv_last_error(void);           /* last error text of the calling thread ("" if none) */
 const char *proxtv_version(void);
 
-/* kernel family: 0 auto, 1 sequential lane-per-fiber, 2 chunked speculative, 3 chunked with direct strided staging.
- * Returns the previous value. */
+/* kernel family / Douglas-Rachford schedule (results are bit-identical across 0, 2, 4, 5, 6; for measurements and tests):
+ * 0 auto, 1 sequential lane-per-fiber, 2 chunked speculative with the plain serial schedule, 3 chunked with direct strided
+ * staging, 4 pipelined gather/scatter schedule (what auto picks for one large image), 5 transposeless schedule (scan kernels
+ * write both layouts), 6 plain transposes around a fused row kernel.  Returns the previous value. */
 int proxtv_set_engine(int engine);
 
 /* Batched 1D prox over the fibers of a column-major array: nf fibers of len samples, fiber j starting at

@@ -25,7 +25,8 @@ ENGINES = {"auto": 0, "seq": 1, "chunked": 2, "chunked-strided": 3, "pipelined":
 
 
 def set_engine(name):
-    """Select the kernel family ('auto' | 'seq' | 'chunked' | 'chunked-strided'); returns the previous one."""
+    """Select the kernel family / DR schedule ('auto' | 'seq' | 'chunked' | 'chunked-strided' | 'pipelined' | 'tspace' |
+    'tpose', see include/proxtv_b200.h); returns the previous one.  Only measurements and tests need this."""
     prev = load().proxtv_set_engine(ENGINES[name])
     return [k for k, v in ENGINES.items() if v == prev][0]
 

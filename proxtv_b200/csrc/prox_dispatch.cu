@@ -1,8 +1,8 @@
 // prox_dispatch.cu -- chooses the kernel family for one batched 1D prox over the fibers of an array.
 //
 //   contiguous fibers (inc == 1), len >= 64, fits shared memory  -> chunked speculative kernel, TMA staged
-//   strided fibers, inc divisible by a sector's worth of fibers   -> chunked kernel staging FPB adjacent fibers directly
-//   other strided shapes, with scratch                            -> gather (fused input op) + chunked kernel + scatter
+//   strided fibers, with scratch (default)                        -> tiled gather (fused input op) + chunked kernel + tiled scatter (fused output form)
+//   strided fibers, ENGINE_CHUNKED_STRIDED or no scratch          -> chunked kernel staging FPB adjacent fibers directly
 //   everything else (tiny fibers, weighted strided, ENGINE_SEQ)   -> sequential lane-per-fiber kernel
 #include "ptv_internal.h"
 #include "chunk_core.cuh"
