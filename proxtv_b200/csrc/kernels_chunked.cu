@@ -116,7 +116,7 @@ template <typename T, bool WEIGHTED, int MAXT, int CL>
 __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 2 : 1) k_prox_chunked_contig(const T* __restrict__ A, const T* __restrict__ B, const T* __restrict__ C, int in_op,
                                       T* __restrict__ X, int out_op,
                                       long long nf, int n, T lam, const T* __restrict__ lamv, int lpf, int fpb, int npad, int use_tma,
-                                      T* __restrict__ X2, long long inc2) {
+                                      T* __restrict__ X2, long long inc2, uint32_t* __restrict__ Mk, T* __restrict__ Cv) {
     __shared__ uint64_t mbar;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RcpPair<T>* rcp = reinterpret_cast<RcpPair<T>*>(smem_raw);    // reciprocal table        [RCP_N]   (16-byte aligned)
@@ -199,7 +199,15 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 2 : 1) k_prox_chunked_cont
     else phases(UniformLam<T>{in_register(lam)});
 
     // ---- value of the segment entering each chunk (gathered before any output is written: the store is the output) ----
-    if (lane_ok) cval[(size_t)fbc * lpf + q] = __ldcg(xrow + carry_of(q, m));
+    const T cvq = lane_ok ? __ldcg(xrow + carry_of(q, m)) : T(0);
+    if (Mk) {
+        // sparse result: the output row keeps only the segment values at their start positions; the chunk's start mask and the value
+        // entering it go to Mk / Cv and the consumer (the fused tiled scatter, transpose.cu) expands the segments while it
+        // transposes -- the fill phase (a fifth of this CTA's life) is not run at all
+        if (lane_ok) { const long long e = (f0 + fbc) * (long long)lpf + q; Mk[e] = m.P[q]; Cv[e] = cvq; }
+        return;
+    }
+    if (lane_ok) cval[(size_t)fbc * lpf + q] = cvq;
     __syncthreads();
     PHASE_MARK(3);
 
@@ -255,8 +263,8 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 2 : 1) k_prox_chunked_cont
 
 // Returns cudaErrorInvalidConfiguration if the fibers do not fit in shared memory (caller falls back to the sequential kernel).
 template <typename T>
-cudaError_t prox_fibers_chunked_contig(const T* A, const T* B, const T* C, InOp op, T* X, int out_op, FiberGeom g, T lam,
-                                       const T* lamv, cudaStream_t st, T* X2, long long inc2) {
+static cudaError_t launch_chunked_contig(const T* A, const T* B, const T* C, InOp op, T* X, int out_op, FiberGeom g, T lam,
+                                         const T* lamv, cudaStream_t st, T* X2, long long inc2, uint32_t* Mk, T* Cv) {
     if (g.inc != 1) return cudaErrorInvalidConfiguration;
     if (g.nf <= 0 || g.len <= 0) return cudaSuccess;
     const int n = g.len;
@@ -275,7 +283,7 @@ cudaError_t prox_fibers_chunked_contig(const T* A, const T* B, const T* C, InOp 
     // TMA staging needs 16-byte aligned rows: aligned base, row pitch a multiple of 16 bytes, single input array
     const int use_tma = (op == IN_A) && (((uintptr_t)A & 15) == 0) && (((size_t)n * sizeof(T)) % 16 == 0);
     constexpr int SECT = 32 / (int)sizeof(T);                 // fibers per 32-byte sector
-    using KernT = void (*)(const T*, const T*, const T*, int, T*, int, long long, int, T, const T*, int, int, int, int, T*, long long);
+    using KernT = void (*)(const T*, const T*, const T*, int, T*, int, long long, int, T, const T*, int, int, int, int, T*, long long, uint32_t*, T*);
     KernT kern; int cl = 0;
     if (X2 && !lamv && threads <= 256 && inc2 > 0) {
         // sector-assembled transposed output: the CTA's own fibers suffice, or a cluster of SECT single-fiber CTAs
@@ -298,11 +306,26 @@ cudaError_t prox_fibers_chunked_contig(const T* A, const T* B, const T* C, InOp 
         at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
         const int in_op_i = (int)op; const int use_tma_i = use_tma;
-        return cudaLaunchKernelEx(&cfg, kern, A, B, C, in_op_i, X, out_op, g.nf, n, lam, lamv, lpf, fpb, npad, use_tma_i, X2, inc2a);
+        uint32_t* mk0 = nullptr; T* cv0 = nullptr;
+        return cudaLaunchKernelEx(&cfg, kern, A, B, C, in_op_i, X, out_op, g.nf, n, lam, lamv, lpf, fpb, npad, use_tma_i, X2, inc2a, mk0, cv0);
     }
-    kern<<<blocks, threads, smem, st>>>(A, B, C, (int)op, X, out_op, g.nf, n, lam, lamv, lpf, fpb, npad, use_tma, X2, inc2a);
+    kern<<<blocks, threads, smem, st>>>(A, B, C, (int)op, X, out_op, g.nf, n, lam, lamv, lpf, fpb, npad, use_tma, X2, inc2a, Mk, Cv);
     return cudaGetLastError();
 }
+
+template <typename T>
+cudaError_t prox_fibers_chunked_contig(const T* A, const T* B, const T* C, InOp op, T* X, int out_op, FiberGeom g, T lam,
+                                       const T* lamv, cudaStream_t st, T* X2, long long inc2) {
+    return launch_chunked_contig<T>(A, B, C, op, X, out_op, g, lam, lamv, st, X2, inc2, nullptr, nullptr);
+}
+// Plain prox (OUT_X) with a SPARSE result: X only holds each segment's value at its start; Mk[fiber][chunk] = start mask,
+// Cv[fiber][chunk] = value entering the chunk (chunks of 32 samples, (len + 31) / 32 per fiber).  See scatter_fibers_ex_sparse.
+template <typename T>
+cudaError_t prox_fibers_chunked_contig_sparse(const T* A, T* X, FiberGeom g, T lam, const T* lamv, uint32_t* Mk, T* Cv, cudaStream_t st) {
+    return launch_chunked_contig<T>(A, nullptr, nullptr, IN_A, X, OUT_X, g, lam, lamv, st, nullptr, 0, Mk, Cv);
+}
+template cudaError_t prox_fibers_chunked_contig_sparse<double>(const double*, double*, FiberGeom, double, const double*, uint32_t*, double*, cudaStream_t);
+template cudaError_t prox_fibers_chunked_contig_sparse<float>(const float*, float*, FiberGeom, float, const float*, uint32_t*, float*, cudaStream_t);
 
 template cudaError_t prox_fibers_chunked_contig<double>(const double*, const double*, const double*, InOp, double*, int, FiberGeom,
                                                         double, const double*, cudaStream_t, double*, long long);

@@ -32,6 +32,11 @@ template <typename T> cudaError_t gather_fibers_range(const T* A, const T* B, In
 template <typename T>
 cudaError_t scatter_fibers_ex_range(const T* in, const T* A, const T* B, const T* C, InOp op, int out_op, T* X, FiberGeom g,
                                     long long r_begin, long long r_end, cudaStream_t st);
+template <typename T>
+cudaError_t prox_fibers_chunked_contig_sparse(const T* A, T* X, FiberGeom g, T lam, const T* lamv, uint32_t* Mk, T* Cv, cudaStream_t st);
+template <typename T>
+cudaError_t scatter_fibers_ex_sparse_range(const T* in, const uint32_t* Mk, const T* Cv, const T* A, const T* B, const T* C, InOp op, int out_op,
+                                           T* X, FiberGeom g, long long r_begin, long long r_end, cudaStream_t st);
 
 struct DrPipe {
     static constexpr int MAXP = 8;
@@ -67,9 +72,13 @@ static DrPipe g_pipe;     // calls are serialised by the C-ABI mutex
 // the high-priority stream as soon as that piece is done, so it runs under the following pieces.
 template <typename T>
 static bool dr_iteration_pipelined(DrPipe& p, size_t M, size_t N, const T* Y, T* t, T* s, T* x, T* scr, T w1, T w2, bool skip_cols,
-                                   bool final, cudaStream_t st) {
+                                   bool final, bool sparse, cudaStream_t st) {
     const long long n = (long long)M * N;
     T* t1 = scr; T* t2 = scr + n;
+    // sparse row pass: the scan leaves segment values at their starts + per-chunk masks / entering values (third and fourth
+    // staging arrays), and the fused scatter expands them while it transposes -- the scan kernel's fill phase is skipped
+    const long long lpf = ((long long)N + 31) / 32;
+    T* Cv = scr + 2 * n; uint32_t* Mk = reinterpret_cast<uint32_t*>(scr + 3 * n);
     const FiberGeom gr{(long long)M, (int)N, (long long)M};
     const int outA = final ? 2 : 1, outB = final ? 4 : 3;
     const int P = p.parts;
@@ -96,12 +105,18 @@ static bool dr_iteration_pipelined(DrPipe& p, size_t M, size_t N, const T* Y, T*
         const long long r0 = cut(M, j, P), r1 = (j + 1 == P) ? (long long)M : cut(M, j + 1, P);
         if (r1 > r0) {
             KernelSpan sp(KC_PROX_STRIDED, 1, sc);
-            PCHK(prox_fibers_chunked_contig<T>(t1 + r0 * (long long)N, nullptr, nullptr, IN_A, t2 + r0 * (long long)N, 0,
-                                               FiberGeom{r1 - r0, (int)N, 1}, w2, nullptr, sc));
+            if (sparse) PCHK(prox_fibers_chunked_contig_sparse<T>(t1 + r0 * (long long)N, t2 + r0 * (long long)N, FiberGeom{r1 - r0, (int)N, 1}, w2,
+                                                                  nullptr, Mk + r0 * lpf, Cv + r0 * lpf, sc));
+            else PCHK(prox_fibers_chunked_contig<T>(t1 + r0 * (long long)N, nullptr, nullptr, IN_A, t2 + r0 * (long long)N, 0,
+                                                    FiberGeom{r1 - r0, (int)N, 1}, w2, nullptr, sc));
         }
         PCHK(cudaEventRecord(p.eP[j], sc));
         PCHK(cudaStreamWaitEvent(p.sx, p.eP[j], 0));
-        if (r1 > r0) { KernelSpan sp(KC_ELEMENTWISE, 1, p.sx); PCHK(scatter_fibers_ex_range<T>(t2, Y, s, t, IN_A_MINUS_B, outB, x, gr, r0, r1, p.sx)); }
+        if (r1 > r0) {
+            KernelSpan sp(KC_ELEMENTWISE, 1, p.sx);
+            if (sparse) PCHK(scatter_fibers_ex_sparse_range<T>(t2, Mk, Cv, Y, s, t, IN_A_MINUS_B, outB, x, gr, r0, r1, p.sx));
+            else PCHK(scatter_fibers_ex_range<T>(t2, Y, s, t, IN_A_MINUS_B, outB, x, gr, r0, r1, p.sx));
+        }
     }
     PCHK(cudaEventRecord(p.eS, p.sx));
     PCHK(cudaStreamWaitEvent(st, p.eS, 0));
@@ -112,7 +127,7 @@ static bool dr_iteration_pipelined(DrPipe& p, size_t M, size_t N, const T* Y, T*
 // the complete pipelined solve on origin stream st (plain launch order; also what gets captured into the CUDA graph)
 template <typename T>
 static int dr2_piped_body(size_t M, size_t N, const T* Y, T w1, T w2, T* out, int maxit, T* t, T* s, T* x, T* scr, double* scratch,
-                          FiberGeom gc, long long n, cudaStream_t st) {
+                          FiberGeom gc, long long n, bool sparse, cudaStream_t st) {
 #define BTRY(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { \
     fprintf(stderr, "proxtv_b200: CUDA error %s at %s:%d\n", cudaGetErrorString(e__), __FILE__, __LINE__); return 1; } } while (0)
     BTRY(ew_image_means_x2<T>(Y, (long long)M * N, 1, t, scratch, st));               // t = 2 mean      (:390-395)
@@ -122,7 +137,7 @@ static int dr2_piped_body(size_t M, size_t N, const T* Y, T w1, T w2, T* out, in
             BTRY(prox_const_fibers<T>(t, (long long)M * N, 1, (int)M, w1, x, st));
             BTRY(ew_dr_reflect_bcast<T>(t, x, s, n, (long long)M * N, gc.len, gc.inc, st));
         }
-        if (!dr_iteration_pipelined<T>(g_pipe, M, N, Y, t, s, final ? out : x, scr, w1, w2, first, final, st)) {
+        if (!dr_iteration_pipelined<T>(g_pipe, M, N, Y, t, s, final ? out : x, scr, w1, w2, first, final, sparse, st)) {
             BTRY(cudaGetLastError()); return 1; }
         if (!final) { T* tmp = t; t = x; x = tmp; }
     }
@@ -179,9 +194,9 @@ int dr2_device(size_t M, size_t N, int batch, int row_major, const T* Y, T w1, T
     if (tspace || piped) {
         auto body = [&](cudaStream_t bs) -> int {
             return tspace ? dr2_tspace_body<T>(M, N, batch, Y, w1, w2, out, maxit, ws, scratch, bs, tpose)
-                          : dr2_piped_body<T>(M, N, Y, w1, w2, out, maxit, t, s, x, scr, scratch, gc, n, bs);
+                          : dr2_piped_body<T>(M, N, Y, w1, w2, out, maxit, t, s, x, scr, scratch, gc, n, eng == ENGINE_AUTO && sizeof(T) == 8, bs);
         };
-        DrGraphKey key{sizeof(T) + (tspace ? 100u : 0u) + (tpose ? 200u : 0u) + 1000u * (size_t)batch, M, N, (const void*)Y, (void*)out, ws, (double)w1,
+        DrGraphKey key{sizeof(T) + (tspace ? 100u : 0u) + (tpose ? 200u : 0u) + (eng == ENGINE_AUTO ? 400u : 0u) + 1000u * (size_t)batch, M, N, (const void*)Y, (void*)out, ws, (double)w1,
                        (double)w2, maxit};
         int rc = -1;
         if (!profile_is_enabled()) {

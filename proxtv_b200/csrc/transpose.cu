@@ -61,10 +61,13 @@ __global__ void k_scatter(const T* __restrict__ in, T* __restrict__ X, int len, 
 // scatter with a fused output form: X[g] = apply_out_ex(out_op, in(g), x(g)) where in(g) = A[g] (op) B[g] is recomputed exactly as
 // the gather computed it, and x is the prox value coming back from the transposed layout.
 // WOPS: also knows the weighted Douglas-Rachford forms (kept out of the default instance: the wider switch slows it measurably)
-template <typename T, bool WOPS>
+template <typename T, bool WOPS, bool EXPAND>
 __global__ void k_scatter_ex(const T* __restrict__ in, const T* __restrict__ A, const T* __restrict__ B, const T* __restrict__ C, int op,
-                             int out_op, T* __restrict__ X, int len, long long inc, long long r_begin, long long r_end) {
+                             int out_op, T* __restrict__ X, int len, long long inc, long long r_begin, long long r_end,
+                             const uint32_t* __restrict__ Mk, const T* __restrict__ Cv) {
     __shared__ T tile[32][33];
+    __shared__ uint32_t pm[32];
+    __shared__ T cvs[32];
     const long long o = blockIdx.z;
     const long long slab = (long long)len * inc;
     const long long r0 = r_begin + (long long)blockIdx.x * 32;
@@ -75,6 +78,12 @@ __global__ void k_scatter_ex(const T* __restrict__ in, const T* __restrict__ A, 
         const long long r = r0 + dy; const int k = k0 + tx;
         if (k < len && r < rlim) tile[dy][tx] = in[o * slab + r * len + k];
     }
+    if (EXPAND && ty == 0) {
+        // sparse input (prox_fibers_chunked_contig_sparse): this tile is chunk k0/32 of 32 fibers; fetch their start masks and
+        // entering values, the segment values themselves sit in the tile at their start positions
+        const long long r = r0 + tx;
+        if (r < rlim) { const long long e = (o * inc + r) * (long long)((len + 31) >> 5) + (k0 >> 5); pm[tx] = Mk[e]; cvs[tx] = Cv[e]; }
+    }
     __syncthreads();
     for (int dy = ty; dy < 32; dy += 8) {
         const int k = k0 + dy; const long long r = r0 + tx;
@@ -82,10 +91,14 @@ __global__ void k_scatter_ex(const T* __restrict__ in, const T* __restrict__ A, 
             const long long g = o * slab + (long long)k * inc + r;
             T yin = A[g];
             if (op == IN_A_MINUS_B) yin = yin - B[g]; else if (op == IN_A_PLUS_B) yin = yin + B[g];
-            X[g] = WOPS ? apply_out_any<T>(out_op, yin, tile[tx][dy], A, B, C, g) : apply_out_ex<T>(out_op, yin, tile[tx][dy], A, B, C, g);
+            T xv;
+            if (EXPAND) { const uint32_t w = pm[tx] & (0xffffffffu >> (31 - dy)); xv = w ? tile[tx][high_bit(w)] : cvs[tx]; }
+            else xv = tile[tx][dy];
+            X[g] = WOPS ? apply_out_any<T>(out_op, yin, xv, A, B, C, g) : apply_out_ex<T>(out_op, yin, xv, A, B, C, g);
         }
     }
 }
+
 // ---- 64 x 64 tiles with 8-byte accesses for 4-byte element types: a 32 x 32 tile of floats moves only 128-byte rows and
 //      leaves half of the memory pipeline idle (measured 197 / 178 us per 268 MB f32 gather / scatter vs ~95 us of HBM time).
 //      Requirements (checked by the launchers): len, inc, k_begin/k_end, r_begin/r_end even and all bases 8-byte aligned. ----
@@ -185,9 +198,9 @@ cudaError_t scatter_fibers_ex(const T* in, const T* A, const T* B, const T* C, I
         const long long off = o0 * (long long)g.len * g.inc;
         if (scatter_wide(in + off, A + off, B ? B + off : nullptr, C ? C + off : nullptr, (int)op, out_op, true, X + off, g.len, g.inc, 0, g.inc, grid.z, st)) continue;
         if (out_op >= OUT_DRW_ROWS)
-            k_scatter_ex<T, true><<<grid, block, 0, st>>>(in + off, A + off, B ? B + off : nullptr, C ? C + off : nullptr, (int)op, out_op, X + off, g.len, g.inc, 0, g.inc);
+            k_scatter_ex<T, true, false><<<grid, block, 0, st>>>(in + off, A + off, B ? B + off : nullptr, C ? C + off : nullptr, (int)op, out_op, X + off, g.len, g.inc, 0, g.inc, nullptr, nullptr);
         else
-            k_scatter_ex<T, false><<<grid, block, 0, st>>>(in + off, A + off, B ? B + off : nullptr, C ? C + off : nullptr, (int)op, out_op, X + off, g.len, g.inc, 0, g.inc);
+            k_scatter_ex<T, false, false><<<grid, block, 0, st>>>(in + off, A + off, B ? B + off : nullptr, C ? C + off : nullptr, (int)op, out_op, X + off, g.len, g.inc, 0, g.inc, nullptr, nullptr);
     }
     return cudaGetLastError();
 }
@@ -236,11 +249,22 @@ cudaError_t scatter_fibers_ex_range(const T* in, const T* A, const T* B, const T
     if (r_end <= r_begin) return cudaSuccess;
     if (scatter_wide(in, A, B, C, (int)op, out_op, true, X, g.len, g.inc, r_begin, r_end, 1, st)) return cudaGetLastError();
     dim3 grid((unsigned)((r_end - r_begin + 31) / 32), (unsigned)((g.len + 31) / 32), 1), block(32, 8);
-    if (out_op >= OUT_DRW_ROWS) k_scatter_ex<T, true><<<grid, block, 0, st>>>(in, A, B, C, (int)op, out_op, X, g.len, g.inc, r_begin, r_end);
-    else k_scatter_ex<T, false><<<grid, block, 0, st>>>(in, A, B, C, (int)op, out_op, X, g.len, g.inc, r_begin, r_end);
+    if (out_op >= OUT_DRW_ROWS) k_scatter_ex<T, true, false><<<grid, block, 0, st>>>(in, A, B, C, (int)op, out_op, X, g.len, g.inc, r_begin, r_end, nullptr, nullptr);
+    else k_scatter_ex<T, false, false><<<grid, block, 0, st>>>(in, A, B, C, (int)op, out_op, X, g.len, g.inc, r_begin, r_end, nullptr, nullptr);
+    return cudaGetLastError();
+}
+// fused scatter of a SPARSE prox result (see prox_fibers_chunked_contig_sparse): expands the segments while it transposes
+template <typename T>
+cudaError_t scatter_fibers_ex_sparse_range(const T* in, const uint32_t* Mk, const T* Cv, const T* A, const T* B, const T* C, InOp op, int out_op,
+                                           T* X, FiberGeom g, long long r_begin, long long r_end, cudaStream_t st) {
+    if (r_end <= r_begin) return cudaSuccess;
+    dim3 grid((unsigned)((r_end - r_begin + 31) / 32), (unsigned)((g.len + 31) / 32), 1), block(32, 8);
+    if (out_op >= OUT_DRW_ROWS) k_scatter_ex<T, true, true><<<grid, block, 0, st>>>(in, A, B, C, (int)op, out_op, X, g.len, g.inc, r_begin, r_end, Mk, Cv);
+    else k_scatter_ex<T, false, true><<<grid, block, 0, st>>>(in, A, B, C, (int)op, out_op, X, g.len, g.inc, r_begin, r_end, Mk, Cv);
     return cudaGetLastError();
 }
 #define INST_R(T) \
+    template cudaError_t scatter_fibers_ex_sparse_range<T>(const T*, const uint32_t*, const T*, const T*, const T*, const T*, InOp, int, T*, FiberGeom, long long, long long, cudaStream_t); \
     template cudaError_t gather_fibers_range<T>(const T*, const T*, InOp, T*, FiberGeom, int, int, cudaStream_t); \
     template cudaError_t scatter_fibers_ex_range<T>(const T*, const T*, const T*, const T*, InOp, int, T*, FiberGeom, long long, long long, cudaStream_t);
 INST_R(double)
