@@ -64,7 +64,7 @@ int host_prox_fibers(const char* fn, const T* in, T* out, long long nf, int len,
     const size_t n = (size_t)nf * len, nw = lamv ? (size_t)nf * (len - 1) : 0;
     char* d = (char*)g_io.get(2 * al(n * sizeof(T)) + al(nw * sizeof(T) + 8));
     // scratch: staging of strided fibers (2n), or the overlapping tiles of contiguous fibers longer than shared memory
-    T* scr = (inc != 1) ? (T*)g_ws.get(2 * al(n * sizeof(T)))
+    T* scr = (inc != 1) ? (T*)g_ws.get(al((size_t)strided_scratch_elems(nf, len) * sizeof(T)))
                         : (len > 16384 && !lamv ? (T*)g_ws.get(al((size_t)lf_scratch_elems(nf, len) * sizeof(T)) + 256) : nullptr);
     if (!d) return fail(fn, "out of device memory", nullptr) ? 1 : 0;
     T* din = (T*)d; T* dout = (T*)(d + al(n * sizeof(T))); T* dw = (T*)(d + 2 * al(n * sizeof(T)));
@@ -73,7 +73,7 @@ int host_prox_fibers(const char* fn, const T* in, T* out, long long nf, int len,
     if (nw && !cuda_ok(fn, cudaMemcpyAsync(dw, lamv, nw * sizeof(T), cudaMemcpyHostToDevice, st), nullptr)) return 0;
     FiberGeom g{nf, len, inc};
     if (!cuda_ok(fn, prox_fibers<T>(din, nullptr, IN_A, dout, 0, g, lam, lamv ? dw : nullptr, (Engine)g_engine, scr, st,
-                                     (inc == 1 && scr) ? lf_scratch_elems(nf, len) : 0), nullptr)) return 0;
+                                     (inc == 1 && scr) ? lf_scratch_elems(nf, len) : (inc != 1 ? strided_scratch_elems(nf, len) : 0)), nullptr)) return 0;
     if (!cuda_ok(fn, cudaMemcpyAsync(out, dout, n * sizeof(T), cudaMemcpyDeviceToHost, st), nullptr)) return 0;
     if (!cuda_ok(fn, cudaStreamSynchronize(st), nullptr)) return 0;
     return 1;
@@ -156,7 +156,7 @@ template <typename T> static T* dev_scratch(long long nf, int len, long long inc
     if (nf <= 0 || len <= 0 || (inc == 1 && len <= 16384)) return nullptr;
     std::lock_guard<std::mutex> lk(g_mu);
     if (inc == 1) return (T*)g_ws.get(al((size_t)lf_scratch_elems(nf, len) * sizeof(T)) + 256);
-    return (T*)g_ws.get(2 * al((size_t)nf * len * sizeof(T)));
+    return (T*)g_ws.get(al((size_t)strided_scratch_elems(nf, len) * sizeof(T)));
 }
 
 template <typename T>
@@ -236,12 +236,12 @@ int PD_TV(double* y, double* lambdas, double* norms, double* dims, double* x, do
 int proxtv_prox_fibers_dev_f64(const double* in, double* out, long long nf, int len, long long inc, double lam, const double* lamv, void* stream) {
     if (!have_device("proxtv_prox_fibers_dev_f64", nullptr)) return 0;
     return cuda_ok("proxtv_prox_fibers_dev_f64", prox_fibers<double>(in, nullptr, IN_A, out, 0, FiberGeom{nf, len, inc}, lam, lamv, (Engine)g_engine, dev_scratch<double>(nf, len, inc), (cudaStream_t)stream,
-                                                                 (inc == 1 && len > 16384) ? lf_scratch_elems(nf, len) : 0), nullptr);
+                                                                 (inc == 1 && len > 16384) ? lf_scratch_elems(nf, len) : (inc != 1 ? strided_scratch_elems(nf, len) : 0)), nullptr);
 }
 int proxtv_prox_fibers_dev_f32(const float* in, float* out, long long nf, int len, long long inc, float lam, const float* lamv, void* stream) {
     if (!have_device("proxtv_prox_fibers_dev_f32", nullptr)) return 0;
     return cuda_ok("proxtv_prox_fibers_dev_f32", prox_fibers<float>(in, nullptr, IN_A, out, 0, FiberGeom{nf, len, inc}, lam, lamv, (Engine)g_engine, dev_scratch<float>(nf, len, inc), (cudaStream_t)stream,
-                                                                 (inc == 1 && len > 16384) ? lf_scratch_elems(nf, len) : 0), nullptr);
+                                                                 (inc == 1 && len > 16384) ? lf_scratch_elems(nf, len) : (inc != 1 ? strided_scratch_elems(nf, len) : 0)), nullptr);
 }
 int proxtv_prox_fibers_f64(const double* in, double* out, long long nf, int len, long long inc, double lam, const double* lamv) {
     return host_prox_fibers<double>("proxtv_prox_fibers_f64", in, out, nf, len, inc, lam, lamv);

@@ -26,6 +26,13 @@ template <typename T> cudaError_t gather_fibers(const T* A, const T* B, InOp op,
 template <typename T> cudaError_t scatter_fibers(const T* in, T* X, FiberGeom g, cudaStream_t st);
 template <typename T>
 cudaError_t scatter_fibers_ex(const T* in, const T* A, const T* B, const T* C, InOp op, int out_op, T* X, FiberGeom g, cudaStream_t st);
+template <typename T>
+cudaError_t prox_fibers_chunked_contig_sparse(const T* A, T* X, FiberGeom g, T lam, const T* lamv, uint32_t* Mk, T* Cv, cudaStream_t st);
+template <typename T>
+cudaError_t scatter_fibers_sparse(const T* in, const uint32_t* Mk, const T* Cv, const T* A, const T* B, const T* C, InOp op, int out_op, T* X,
+                                  FiberGeom g, cudaStream_t st);
+// elements of scratch the strided route needs for its sparse form: two staging arrays + per-chunk masks and entering values
+long long strided_scratch_elems(long long nf, long long len) { return 2 * nf * len + 2 * nf * ((len + 31) / 32) + 64; }
 
 template <typename T>
 cudaError_t prox_fibers_ex(const T* A, const T* B, const T* C, InOp op, T* X, int out_op, FiberGeom g, T lam, const T* lamv,
@@ -39,7 +46,7 @@ cudaError_t prox_fibers_ex(const T* A, const T* B, const T* C, InOp op, T* X, in
             cudaGetLastError();
             // too long for shared memory: overlapping tiles, verified stitching (long_fiber.cu); the scratch convention for
             // this case is lf_scratch_elems() elements, which the 1D host entry points provide
-            if (!lamv && scratch && scratch_elems >= lf_scratch_elems(g.nf, g.len)) {
+            if (!lamv && out_op < OUT_DR_ROWS && scratch && scratch_elems >= lf_scratch_elems(g.nf, g.len)) {
                 e = prox_long_fibers<T>(A, B, op, X, out_op, g, lam, scratch, lf_scratch_elems(g.nf, g.len), st);
                 if (e == cudaSuccess) return e;
                 if (e != cudaErrorInvalidConfiguration && e != cudaErrorNotReady) return e;
@@ -66,10 +73,17 @@ cudaError_t prox_fibers_ex(const T* A, const T* B, const T* C, InOp op, T* X, in
                 cudaError_t e;
                 { KernelSpan span(KC_ELEMENTWISE, 1, st); e = gather_fibers<T>(A, B, op, t1, g, st); }
                 if (e != cudaSuccess) return e;
+                // with enough scratch the scan leaves a sparse result (no fill phase) and the scatter expands it while it transposes
+                const bool sparse = scratch_elems >= strided_scratch_elems(g.nf, g.len);
+                const long long lpf = ((long long)g.len + 31) / 32;
+                T* Cv = scratch + 2 * n; uint32_t* Mk = reinterpret_cast<uint32_t*>(Cv + g.nf * lpf);
                 { KernelSpan span(KC_PROX_STRIDED, 1, st);
-                  e = prox_fibers_chunked_contig<T>(t1, nullptr, nullptr, IN_A, t2, OUT_X, gc, lam, nullptr, st); }
+                  e = sparse ? prox_fibers_chunked_contig_sparse<T>(t1, t2, gc, lam, nullptr, Mk, Cv, st)
+                             : prox_fibers_chunked_contig<T>(t1, nullptr, nullptr, IN_A, t2, OUT_X, gc, lam, nullptr, st); }
                 if (e == cudaSuccess) {
                     KernelSpan span(KC_ELEMENTWISE, 1, st);
+                    if (sparse) return out_op == OUT_X ? scatter_fibers_sparse<T>(t2, Mk, Cv, nullptr, nullptr, nullptr, IN_A, OUT_X, X, g, st)
+                                                       : scatter_fibers_sparse<T>(t2, Mk, Cv, A, B, C, op, out_op, X, g, st);
                     return out_op == OUT_X ? scatter_fibers<T>(t2, X, g, st) : scatter_fibers_ex<T>(t2, A, B, C, op, out_op, X, g, st);
                 }
                 if (e != cudaErrorInvalidConfiguration) return e;

@@ -45,6 +45,7 @@ template <typename T>
 cudaError_t prox_fibers_ex(const T* A, const T* B, const T* C, InOp op, T* X, int out_op, FiberGeom g, T lam, const T* lamv,
                            Engine eng, T* scratch, cudaStream_t st, long long scratch_elems = 0);
 
+long long strided_scratch_elems(long long nf, long long len);   // scratch elements that enable the sparse strided route (else 2n: dense route)
 long long lf_scratch_elems(long long nf, long long len);     // scratch elements prox_fibers needs for contiguous fibers longer than shared memory
 
 // ---- launch accounting / event timing (profile.cu) ----

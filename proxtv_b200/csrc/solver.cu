@@ -243,13 +243,13 @@ int dr2_device(size_t M, size_t N, int batch, int row_major, const T* Y, T w1, T
             PTV_TRY(prox_const_fibers<T>(t, (long long)M * N, batch, (int)M, w1, x, st));
             PTV_TRY(ew_dr_reflect_bcast<T>(t, x, s, n, (long long)M * N, gc.len, gc.inc, st));
         } else
-        PTV_TRY(prox_fibers<T>(t, nullptr, IN_A, s, 1 /*reflect: s = 2(t - prox) - t*/, gc, w1, nullptr, eng, scr, st));
+        PTV_TRY(prox_fibers<T>(t, nullptr, IN_A, s, 1 /*reflect: s = 2(t - prox) - t*/, gc, w1, nullptr, eng, scr, st, 4 * n));
         // second half fused into the row pass: in = Y - s ; tb = Y - (in - prox) ; tb = 2 tb - s ; t' = 0.5 (t + tb)
-        PTV_TRY(prox_fibers_ex<T>(Y, s, t, IN_A_MINUS_B, x, 3 /*OUT_DR_ROWS*/, gr, w2, nullptr, eng, scr, st));
+        PTV_TRY(prox_fibers_ex<T>(Y, s, t, IN_A_MINUS_B, x, 3 /*OUT_DR_ROWS*/, gr, w2, nullptr, eng, scr, st, 4 * n));
         { T* tmp = t; t = x; x = tmp; }                                       // t' was written to x: ping-pong
     }
-    PTV_TRY(prox_fibers<T>(t, nullptr, IN_A, s, 2 /*s = t - prox*/, gc, w1, nullptr, eng, scr, st));   // :427-430
-    PTV_TRY(prox_fibers_ex<T>(Y, s, nullptr, IN_A_MINUS_B, out, 4 /*OUT_DR_ROWS_FINAL*/, gr, w2, nullptr, eng, scr, st));
+    PTV_TRY(prox_fibers<T>(t, nullptr, IN_A, s, 2 /*s = t - prox*/, gc, w1, nullptr, eng, scr, st, 4 * n));   // :427-430
+    PTV_TRY(prox_fibers_ex<T>(Y, s, nullptr, IN_A_MINUS_B, out, 4 /*OUT_DR_ROWS_FINAL*/, gr, w2, nullptr, eng, scr, st, 4 * n));
     if (info) { info[INFO_ITERS] = maxit; info[INFO_RC] = RC_OK; }            // :433-436 (INFO_GAP is left untouched)
     return 0;                                                                 // :440 (the reference returns 0 on success)
 }
@@ -313,8 +313,8 @@ int drw_device(size_t M, size_t N, const T* Y, const T* W1, const T* W2, T* out,
 
 // ------------------------------------------------------------------------------------------------------------------
 template <typename T> size_t ws_bytes_pd(long long n, int npen) {
-    int arrays = 2 * npen + 4;   // PD_TV: p_i, z_i ; PD2_TV (npen <= 2): p, q, z, xl  -> 4 <= 2*2+2
-    if (arrays < 6) arrays = 6;
+    int arrays = 2 * npen + 4;   // PD_TV: p_i, z_i + 3 staging ; PD2_TV (npen <= 2): p, q, z, xl + 3 staging
+    if (arrays < 8) arrays = 8;
     return (size_t)arrays * align256((size_t)n * sizeof(T)) + SCRATCH_BYTES + align256(2 * 64 * sizeof(void*));
 }
 
@@ -347,17 +347,17 @@ int pd2_device(const T* y, const double* lambdas, const double* dims, T* x, doub
     if (n > 0) {
         char* w = (char*)ws; const size_t ab = align256((size_t)n * sizeof(T));
         T* p = (T*)w; w += ab; T* q = (T*)w; w += ab; T* z = (T*)w; w += ab; T* xl = (T*)w; w += ab;
-        T* scr = (T*)w; w += 2 * ab;
+        T* scr = (T*)w; w += 3 * ab;                 // staging of strided passes: 2 arrays + per-chunk masks / entering values
         double* scratch = (double*)w; double* dres = scratch + REDUCE_BLOCKS;
         PTV_TRY(cudaMemcpyAsync(x, y, (size_t)n * sizeof(T), cudaMemcpyDeviceToDevice, st));          // :132-137
         PTV_TRY(cudaMemsetAsync(p, 0, (size_t)n * sizeof(T), st));
         PTV_TRY(cudaMemsetAsync(q, 0, (size_t)n * sizeof(T), st));
         while (stop > STOP_PD && (npen > 1 || !iters) && iters < maxIters) {                           // :157
             PTV_TRY(cudaMemcpyAsync(xl, x, (size_t)n * sizeof(T), cudaMemcpyDeviceToDevice, st));
-            PTV_TRY(prox_fibers<T>(x, p, IN_A_PLUS_B, z, 0, g0, (T)lambdas[0], nullptr, eng, scr, st));       // :171-208
+            PTV_TRY(prox_fibers<T>(x, p, IN_A_PLUS_B, z, 0, g0, (T)lambdas[0], nullptr, eng, scr, st, 3 * n));       // :171-208
             PTV_TRY(ew_dual_update<T>(p, x, z, n, st));                                               // :211-213
             if (npen >= 2) {
-                PTV_TRY(prox_fibers<T>(z, q, IN_A_PLUS_B, x, 0, g1, (T)lambdas[1], nullptr, eng, scr, st));   // :216-258
+                PTV_TRY(prox_fibers<T>(z, q, IN_A_PLUS_B, x, 0, g1, (T)lambdas[1], nullptr, eng, scr, st, 3 * n));   // :216-258
                 PTV_TRY(ew_dual_update<T>(q, z, x, n, st));                                           // :261-263
             } else {
                 PTV_TRY(cudaMemcpyAsync(x, z, (size_t)n * sizeof(T), cudaMemcpyDeviceToDevice, st));  // :266-269
@@ -387,7 +387,7 @@ int pd_device(const T* y, const double* lam, const double* dims, T* x, double* i
         char* w = (char*)ws; const size_t ab = align256((size_t)n * sizeof(T));
         T* hp[64]; T* hz[64];
         for (int i = 0; i < npen; i++) { hp[i] = (T*)w; w += ab; hz[i] = (T*)w; w += ab; }
-        T* scr = (T*)w; w += 2 * ab;
+        T* scr = (T*)w; w += 3 * ab;
         double* scratch = (double*)w; double* dres = scratch + REDUCE_BLOCKS; w += SCRATCH_BYTES;
         T** dp = (T**)w; T** dz = dp + 64;
         PTV_TRY(cudaMemcpyAsync(dp, hp, sizeof(T*) * npen, cudaMemcpyHostToDevice, st));
@@ -397,7 +397,7 @@ int pd_device(const T* y, const double* lam, const double* dims, T* x, double* i
         for (int i = 0; i < npen; i++) PTV_TRY(cudaMemcpyAsync(hz[i], y, (size_t)n * sizeof(T), cudaMemcpyDeviceToDevice, st));
         while (stop > STOP_PD && iters < maxIters) {                                                  // :151
             for (int i = 0; i < npen; i++)
-                PTV_TRY(prox_fibers<T>(hz[i], nullptr, IN_A, hp[i], 0, g[i], (T)lam[i], nullptr, eng, scr, st));  // :171-208
+                PTV_TRY(prox_fibers<T>(hz[i], nullptr, IN_A, hp[i], 0, g[i], (T)lam[i], nullptr, eng, scr, st, 3 * n));  // :171-208
             PTV_TRY(ew_pd_combine<T>(dp, dz, hp, hz, npen, x, n, scratch, dres, st));                         // :212-227
             if (!read_stop(dres, &stop, st)) { PTV_TRY(cudaGetLastError()); PTV_TRY(cudaErrorUnknown); }
             iters++;

@@ -89,8 +89,8 @@ __global__ void k_scatter_ex(const T* __restrict__ in, const T* __restrict__ A, 
         const int k = k0 + dy; const long long r = r0 + tx;
         if (k < len && r < rlim) {
             const long long g = o * slab + (long long)k * inc + r;
-            T yin = A[g];
-            if (op == IN_A_MINUS_B) yin = yin - B[g]; else if (op == IN_A_PLUS_B) yin = yin + B[g];
+            T yin = T(0);
+            if (A) { yin = A[g]; if (op == IN_A_MINUS_B) yin = yin - B[g]; else if (op == IN_A_PLUS_B) yin = yin + B[g]; }   // A == nullptr: plain OUT_X
             T xv;
             if (EXPAND) { const uint32_t w = pm[tx] & (0xffffffffu >> (31 - dy)); xv = w ? tile[tx][high_bit(w)] : cvs[tx]; }
             else xv = tile[tx][dy];
@@ -130,11 +130,13 @@ __global__ void __launch_bounds__(256) k_gather_w(const float* __restrict__ A, c
     }
 }
 
-template <bool WOPS, bool EX>
+template <bool WOPS, bool EX, bool EXPAND>
 __global__ void __launch_bounds__(256) k_scatter_w(const float* __restrict__ in, const float* __restrict__ A, const float* __restrict__ B,
                                                   const float* __restrict__ C, int op, int out_op, float* __restrict__ X, int len, long long inc,
-                                                  long long r_begin, long long r_end) {
+                                                  long long r_begin, long long r_end, const uint32_t* __restrict__ Mk, const float* __restrict__ Cv) {
     __shared__ float tile[64][65];
+    __shared__ uint32_t pm[64][2];
+    __shared__ float cvs[64][2];
     const long long o = blockIdx.z, slab = (long long)len * inc;
     const long long r0 = r_begin + (long long)blockIdx.x * 64;
     const int k0 = blockIdx.y * 64;
@@ -144,12 +146,26 @@ __global__ void __launch_bounds__(256) k_scatter_w(const float* __restrict__ in,
         const long long r = r0 + dy; const int k = k0 + 2 * tx;
         if (k < len && r < rlim) { const F2 v = *reinterpret_cast<const F2*>(in + o * slab + r * len + k); tile[dy][2 * tx] = v.a; tile[dy][2 * tx + 1] = v.b; }
     }
+    if (EXPAND && ty < 4) {                    // sparse input: start masks / entering values of the two chunks each tile row covers
+        const int e = ty * 32 + tx, row = e >> 1, h = e & 1;
+        const long long r = r0 + row;
+        if (r < rlim && k0 + 32 * h < len) {
+            const long long q = (o * inc + r) * (long long)((len + 31) >> 5) + (k0 >> 5) + h;
+            pm[row][h] = Mk[q]; cvs[row][h] = Cv[q];
+        }
+    }
     __syncthreads();
     for (int dy = ty; dy < 64; dy += 8) {
         const int k = k0 + dy; const long long r = r0 + 2 * tx;
         if (k < len && r < rlim) {
             const long long g = o * slab + (long long)k * inc + r;
-            F2 res{tile[2 * tx][dy], tile[2 * tx + 1][dy]};
+            F2 res;
+            if (EXPAND) {
+                const int h = dy >> 5; const uint32_t below = 0xffffffffu >> (31 - (dy & 31));
+                const uint32_t w0 = pm[2 * tx][h] & below, w1 = pm[2 * tx + 1][h] & below;
+                res.a = w0 ? tile[2 * tx][32 * h + high_bit(w0)] : cvs[2 * tx][h];
+                res.b = w1 ? tile[2 * tx + 1][32 * h + high_bit(w1)] : cvs[2 * tx + 1][h];
+            } else res = F2{tile[2 * tx][dy], tile[2 * tx + 1][dy]};
             if (EX) {
                 const F2 a = *reinterpret_cast<const F2*>(A + g);
                 F2 b{0.f, 0.f};
@@ -177,16 +193,23 @@ static bool gather_wide(const float* A, const float* B, int op, float* out, int 
 }
 static bool gather_wide(const double*, const double*, int, double*, int, long long, int, int, unsigned, cudaStream_t) { return false; }
 static bool scatter_wide(const float* in, const float* A, const float* B, const float* C, int op, int out_op, bool ex, float* X, int len,
-                         long long inc, long long r_begin, long long r_end, unsigned gz, cudaStream_t st) {
+                         long long inc, long long r_begin, long long r_end, unsigned gz, cudaStream_t st, const uint32_t* Mk = nullptr,
+                         const float* Cv = nullptr) {
     if (!wide_ok(in, A, B, C, X, len, inc, r_begin, r_end)) return false;
     dim3 grid((unsigned)((r_end - r_begin + 63) / 64), (unsigned)((len + 63) / 64), gz), block(32, 8);
-    if (!ex) k_scatter_w<false, false><<<grid, block, 0, st>>>(in, A, B, C, op, out_op, X, len, inc, r_begin, r_end);
-    else if (out_op >= OUT_DRW_ROWS) k_scatter_w<true, true><<<grid, block, 0, st>>>(in, A, B, C, op, out_op, X, len, inc, r_begin, r_end);
-    else k_scatter_w<false, true><<<grid, block, 0, st>>>(in, A, B, C, op, out_op, X, len, inc, r_begin, r_end);
+    if (Mk) {
+        if (!ex) k_scatter_w<false, false, true><<<grid, block, 0, st>>>(in, A, B, C, op, out_op, X, len, inc, r_begin, r_end, Mk, Cv);
+        else if (out_op >= OUT_DRW_ROWS) k_scatter_w<true, true, true><<<grid, block, 0, st>>>(in, A, B, C, op, out_op, X, len, inc, r_begin, r_end, Mk, Cv);
+        else k_scatter_w<false, true, true><<<grid, block, 0, st>>>(in, A, B, C, op, out_op, X, len, inc, r_begin, r_end, Mk, Cv);
+    } else {
+        if (!ex) k_scatter_w<false, false, false><<<grid, block, 0, st>>>(in, A, B, C, op, out_op, X, len, inc, r_begin, r_end, nullptr, nullptr);
+        else if (out_op >= OUT_DRW_ROWS) k_scatter_w<true, true, false><<<grid, block, 0, st>>>(in, A, B, C, op, out_op, X, len, inc, r_begin, r_end, nullptr, nullptr);
+        else k_scatter_w<false, true, false><<<grid, block, 0, st>>>(in, A, B, C, op, out_op, X, len, inc, r_begin, r_end, nullptr, nullptr);
+    }
     return true;
 }
 static bool scatter_wide(const double*, const double*, const double*, const double*, int, int, bool, double*, int, long long, long long,
-                         long long, unsigned, cudaStream_t) { return false; }
+                         long long, unsigned, cudaStream_t, const uint32_t* = nullptr, const double* = nullptr) { return false; }
 
 template <typename T>
 cudaError_t scatter_fibers_ex(const T* in, const T* A, const T* B, const T* C, InOp op, int out_op, T* X, FiberGeom g, cudaStream_t st) {
@@ -258,12 +281,36 @@ template <typename T>
 cudaError_t scatter_fibers_ex_sparse_range(const T* in, const uint32_t* Mk, const T* Cv, const T* A, const T* B, const T* C, InOp op, int out_op,
                                            T* X, FiberGeom g, long long r_begin, long long r_end, cudaStream_t st) {
     if (r_end <= r_begin) return cudaSuccess;
+    if (scatter_wide(in, A, B, C, (int)op, out_op, true, X, g.len, g.inc, r_begin, r_end, 1, st, Mk, Cv)) return cudaGetLastError();
     dim3 grid((unsigned)((r_end - r_begin + 31) / 32), (unsigned)((g.len + 31) / 32), 1), block(32, 8);
     if (out_op >= OUT_DRW_ROWS) k_scatter_ex<T, true, true><<<grid, block, 0, st>>>(in, A, B, C, (int)op, out_op, X, g.len, g.inc, r_begin, r_end, Mk, Cv);
     else k_scatter_ex<T, false, true><<<grid, block, 0, st>>>(in, A, B, C, (int)op, out_op, X, g.len, g.inc, r_begin, r_end, Mk, Cv);
     return cudaGetLastError();
 }
+// whole-geometry form (any number of slabs).  A == nullptr: plain scatter of the expanded prox values (IN_A / OUT_X semantics).
+template <typename T>
+cudaError_t scatter_fibers_sparse(const T* in, const uint32_t* Mk, const T* Cv, const T* A, const T* B, const T* C, InOp op, int out_op, T* X,
+                                  FiberGeom g, cudaStream_t st) {
+    if (g.nf <= 0 || g.len <= 0) return cudaSuccess;
+    const long long outer = g.nf / g.inc, lpf = ((long long)g.len + 31) / 32;
+    const bool ex = A != nullptr;
+    dim3 grid((unsigned)((g.inc + 31) / 32), (unsigned)((g.len + 31) / 32), 1), block(32, 8);
+    for (long long o0 = 0; o0 < outer; o0 += 65535) {
+        grid.z = (unsigned)((outer - o0) < 65535 ? (outer - o0) : 65535);
+        const long long off = o0 * (long long)g.len * g.inc, moff = o0 * g.inc * lpf;
+        const T* Ao = ex ? A + off : nullptr;          // plain form: OUT_X never looks at the input
+        if (scatter_wide(in + off, Ao, (ex && B) ? B + off : nullptr, (ex && C) ? C + off : nullptr, ex ? (int)op : (int)IN_A, ex ? out_op : (int)OUT_X,
+                         ex, X + off, g.len, g.inc, 0, g.inc, grid.z, st, Mk + moff, Cv + moff)) continue;
+        if (ex && out_op >= OUT_DRW_ROWS)
+            k_scatter_ex<T, true, true><<<grid, block, 0, st>>>(in + off, Ao, B ? B + off : nullptr, C ? C + off : nullptr, (int)op, out_op, X + off, g.len, g.inc, 0, g.inc, Mk + moff, Cv + moff);
+        else
+            k_scatter_ex<T, false, true><<<grid, block, 0, st>>>(in + off, Ao, (ex && B) ? B + off : nullptr, (ex && C) ? C + off : nullptr, ex ? (int)op : (int)IN_A,
+                                                                 ex ? out_op : (int)OUT_X, X + off, g.len, g.inc, 0, g.inc, Mk + moff, Cv + moff);
+    }
+    return cudaGetLastError();
+}
 #define INST_R(T) \
+    template cudaError_t scatter_fibers_sparse<T>(const T*, const uint32_t*, const T*, const T*, const T*, const T*, InOp, int, T*, FiberGeom, cudaStream_t); \
     template cudaError_t scatter_fibers_ex_sparse_range<T>(const T*, const uint32_t*, const T*, const T*, const T*, const T*, InOp, int, T*, FiberGeom, long long, long long, cudaStream_t); \
     template cudaError_t gather_fibers_range<T>(const T*, const T*, InOp, T*, FiberGeom, int, int, cudaStream_t); \
     template cudaError_t scatter_fibers_ex_range<T>(const T*, const T*, const T*, const T*, InOp, int, T*, FiberGeom, long long, long long, cudaStream_t);

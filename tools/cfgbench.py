@@ -6,7 +6,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import proxtv_b200 as ptv
 from oracle import oracle as O
 
-def ev_time(fn, reps=3, warm=1):
+def ev_time(fn, reps=5, warm=4):      # the GPU idles (clocks drop) while the host generates data: warm up properly
     for _ in range(warm): fn()
     torch.cuda.synchronize(); e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     e0.record()
