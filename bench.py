@@ -35,13 +35,17 @@ LAM = 0.2
 
 
 def ncu_traffic():
-    """dram__bytes_read + dram__bytes_write per launch of the dominant kernel, from the committed ncu --set full capture."""
+    """dram__bytes_read + dram__bytes_write per launch of the dominant kernel, from the committed ncu --set full capture (mean of
+    the captured launches: one sparse-result row pass and one dense column pass)."""
     try:
         r = w = None
         for line in open(os.path.join(ROOT, "profiles", "r1_contig_kernel_ncu_full.csv")):
             p = line.strip().split(",")
-            if p[0] == "dram__bytes_read.sum": r = float(p[2]) * (1e6 if p[1] == "Mbyte" else 1e9 if p[1] == "Gbyte" else 1.0)
-            if p[0] == "dram__bytes_write.sum": w = float(p[2]) * (1e6 if p[1] == "Mbyte" else 1e9 if p[1] == "Gbyte" else 1.0)
+            if p[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                scale = 1e6 if p[1] == "Mbyte" else 1e9 if p[1] == "Gbyte" else 1e3 if p[1] == "Kbyte" else 1.0
+                v = sum(float(x) for x in p[2:]) / len(p[2:]) * scale
+                if p[0] == "dram__bytes_read.sum": r = v
+                else: w = v
         return r + w if r is not None and w is not None else None
     except Exception:  # noqa: BLE001
         return None
@@ -265,6 +269,7 @@ def main():
                          "algorithmic_bytes_per_launch": sweeps[dom] * M * M * 8, "peak_source": peak_src,
                          "avg_launch_ms": avg_ms, "launches_timed": int(scan_n if dom == 0 else ks[2]),
                          "timing_region": "%d additional steps right after the timed region, serial schedule, CUDA events around every launch" % args.steps,
+                         "note": "launches = column passes (dense result, fill phase) + row passes (sparse result: segment starts only, the fused scatter expands them); both counted as 1R+1W of the array",
                          "class_ms_per_step": {names[i]: kms[i] / args.steps for i in range(3)}},
             "roofline_solve": {"algorithmic_bytes": solve_bytes, "achieved": solve_bytes / (ms_step * 1e-3) / 1e9,
                                "peak": peak, "unit": "GB/s", "frac": solve_bytes / (ms_step * 1e-3) / 1e9 / peak},
