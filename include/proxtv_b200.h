@@ -50,6 +50,17 @@ int linearizedTautString_TV1(double *y, double lambda, double *x, int n);
 void TV1D_denoise(double *input, double *output, const int width, const double lambda);
 /* replaces src/TVL1Wopt.cpp:364 (src/TVopt.h:103).  lambda has n-1 entries.  Returns 1.  Bit-identical to the reference. */
 int tautString_TV1_Weighted(double *y, double *lambda, double *x, int n);
+/* The reference's other 1D TV-L1 solvers: projected Newton (src/TVL1opt.cpp:44, src/TVL1Wopt.cpp:36), Condat's taut-string
+ * variant (src/condat_fast_tv.cpp:133), Kolmogorov's (src/TVL1opt_kolmogorov.cpp) and Johnson's dynamic programming
+ * (src/johnsonRyanTV.cpp).  Same unique minimiser as the functions above (<= 4e-14 apart on random data with the compiled
+ * reference; 9e-7 for TV1D_denoise_tautstring, which truncates a slope to float), so they are served by the same exact kernel.
+ * info = {0, 0, RC_OK}; sigma and ws are ignored; weighted forms take n-1 weights. */
+int PN_TV1(double *y, double lambda, double *x, double *info, int n, double sigma, void *ws);
+int PN_TV1_Weighted(double *Y, double *W, double *X, double *info, int n, double sigma, void *ws);
+void TV1D_denoise_tautstring(double *input, double *output, int width, const double lambda);
+void SolveTVConvexQuadratic_a1_nw(int n, double *b, double w, double *solution);
+void SolveTVConvexQuadratic_a1(int n, double *b, double *w, double *solution);
+void dp(int n, double *y, double lam, double *beta);
 /* replaces src/TVgenopt.cpp:30 (src/TVopt.h:91) for p == 1 only (other norms: prints an error, RC_ERROR, returns 0).
  * ws is ignored (the reference's Python wrapper always passes NULL). */
 int TV(double *y, double lambda, double *x, double *info, int n, double p, void *ws);

