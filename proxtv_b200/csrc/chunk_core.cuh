@@ -76,12 +76,14 @@ PTV_HD int high_bit(uint32_t m) {          // m != 0
 // Walk through chunk c = q + round.  ROUND0: the lane's own chunk, entered with a cold start (no merging possible: the
 // chunk's masks are not written yet).  Otherwise a chunk to the right, entered with the lane's scan state and pending
 // start.  StV(j, v): store into the sparse value store.  Returns true if the lane is still active afterwards.
-template <typename T, bool ROUND0, class LdY, class StV, class Lam>
+// CHT: samples per chunk (32, or 16 for the weighted float64 instantiation, whose second staged row halves residency: twice
+// the lanes per fiber then restore the warps per SM); mask words stay 32 bits wide, a 16-sample chunk uses the low half.
+template <typename T, bool ROUND0, int CHT = CH, class LdY, class StV, class Lam>
 PTV_HD bool walk_chunk(int q, int round, int nchunks, int n, LdY y, StV stv, Lam lam, RcpDiv<T> div, LaneState<T>& st,
                        ChunkMasks m) {
     const int c = q + round;
     uint32_t oP = 0, oK0 = 0, oK1 = 0, P = 0, K0 = 0, K1 = 0;
-    const int cb = c * CH, ce = (cb + CH < n) ? cb + CH : n;
+    const int cb = c * CHT, ce = (cb + CHT < n) ? cb + CHT : n;
     if (ROUND0) {
         st.s.begin(cb, y, lam);            // q == 0: the true start; q > 0: speculative cold start
         st.finished = false; st.pend_a = -1; st.pend_k = K_NONE;
@@ -223,16 +225,16 @@ template <typename T> PTV_HD T apply_out_any(int op, T yin, T x, const T* A, con
 
 // carry[c] = start of the segment that covers sample c*CH when the chunk's own bit 0 is not set: the last recorded start
 // before the chunk (sample 0 always starts a segment).  Lane-parallel form: each lane looks left for a non-empty chunk.
-PTV_HD int carry_of(int c, ChunkMasks m) {
+template <int CHT = CH> PTV_HD int carry_of(int c, ChunkMasks m) {
     int c2 = c - 1;
     while (c2 >= 0 && m.P[c2] == 0) c2--;
-    return (c2 >= 0) ? c2 * CH + high_bit(m.P[c2]) : 0;
+    return (c2 >= 0) ? c2 * CHT + high_bit(m.P[c2]) : 0;
 }
 
 // start of the segment covering sample j = c*CH + b, or -1 if that segment starts before the chunk (use the carry)
-PTV_HD int seg_start_in_chunk(int c, int b, ChunkMasks m) {
+template <int CHT = CH> PTV_HD int seg_start_in_chunk(int c, int b, ChunkMasks m) {
     const uint32_t w = m.P[c] & (0xffffffffu >> (31 - b));
-    return w ? (c << 5) + high_bit(w) : -1;
+    return w ? c * CHT + high_bit(w) : -1;
 }
 
 }  // namespace ptv

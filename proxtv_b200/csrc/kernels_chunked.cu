@@ -80,8 +80,8 @@ __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; as
 #endif
 
 // One batch of the fill phase: FW consecutive 32-sample windows of one fiber, handled by one warp (see the kernel).
-template <typename T, int FW, int CL>
-__device__ __forceinline__ void fill_batch(int c0, int nchunks, int n, int lane, uint32_t below, T* __restrict__ xr, long long gb, long long x2b,
+template <typename T, int FW, int CL, int CHT>
+__device__ __forceinline__ void fill_batch(int c0, int nwin, int nchunks, int n, int lane, uint32_t below, T* __restrict__ xr, long long gb, long long x2b,
                                            const uint32_t* __restrict__ Pm, const T* __restrict__ cv, T* __restrict__ yr, int out_op,
                                            const T* __restrict__ A, const T* __restrict__ B, const T* __restrict__ C, T* __restrict__ X2,
                                            long long inc2) {
@@ -89,18 +89,19 @@ __device__ __forceinline__ void fill_batch(int c0, int nchunks, int n, int lane,
     T v[FW];
 #pragma unroll
     for (int u = 0; u < FW; u++) {
-        const int c = c0 + u;
+        const int c = c0 + u;                                      // 32-sample window c = chunk c, or chunks 2c and 2c+1 (CHT == 16)
         v[u] = T(0);
-        if (c < nchunks && (c << 5) + lane < n) {
-            const uint32_t w = Pm[c] & below;
-            v[u] = w ? __ldcg(xr + (c << 5) + high_bit(w)) : cv[c];
+        if (c < nwin && (c << 5) + lane < n) {
+            const uint32_t pw = (CHT == 32) ? Pm[c] : (Pm[2 * c] | ((2 * c + 1 < nchunks) ? (Pm[2 * c + 1] << 16) : 0u));
+            const uint32_t w = pw & below;
+            v[u] = w ? __ldcg(xr + (c << 5) + high_bit(w)) : cv[(CHT == 32) ? c : 2 * c];
         }
     }
     __syncwarp();
 #pragma unroll
     for (int u = 0; u < FW; u++) {
         const int c = c0 + u, j = (c << 5) + lane;
-        if (c < nchunks && j < n) {
+        if (c < nwin && j < n) {
             const T o = apply_out_ex<T>(out_op, yr[j + c * PADE], v[u], A, B, C, gb + j);
             xr[j] = o;
             if (CL == 0) { if (X2) X2[x2b + (long long)j * inc2] = o; }      // scattered 8-byte stores
@@ -112,7 +113,7 @@ __device__ __forceinline__ void fill_batch(int c0, int nchunks, int n, int lane,
 // CL: how the optional transposed second output X2 is produced.  0: plain 8-byte scattered stores (slow: partial-sector writes make
 // L2 read-modify-write every sector); >= 1: the finished fiber rows of CL consecutive CTAs (a thread-block cluster when CL > 1)
 // are exchanged through (distributed) shared memory so that fpb*CL adjacent fibers are written together as full 32-byte sectors.
-template <typename T, bool WEIGHTED, int MAXT, int CL>
+template <typename T, bool WEIGHTED, int MAXT, int CL, int CHT = CH>
 __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 2 : 1) k_prox_chunked_contig(const T* __restrict__ A, const T* __restrict__ B, const T* __restrict__ C, int in_op,
                                       T* __restrict__ X, int out_op,
                                       long long nf, int n, T lam, const T* __restrict__ lamv, int lpf, int fpb, int npad, int use_tma,
@@ -132,7 +133,8 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 2 : 1) k_prox_chunked_cont
     const int tid = threadIdx.x;
     const long long f0 = (long long)blockIdx.x * fpb;
     const int nfib = (int)((nf - f0) < fpb ? (nf - f0) : fpb);
-    const int nchunks = (n + CH - 1) / CH;
+    const int nchunks = (n + CHT - 1) / CHT;                     // lanes per fiber
+    const int nwin = (n + CH - 1) / CH;                          // 32-sample rows of the staged fiber == windows of the fill
 
 #ifdef PTV_PHASE_TIMING
     unsigned long long t_prev = gtime();
@@ -144,8 +146,8 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 2 : 1) k_prox_chunked_cont
         if (tid == 0) mbar_init(&mbar, 1);
         __syncthreads();
         if (tid == 0) mbar_arrive_expect_tx(&mbar, (uint32_t)((size_t)nfib * n * sizeof(T)));
-        for (int e = tid; e < nfib * nchunks; e += blockDim.x) {
-            const int fb = e / nchunks, c = e - fb * nchunks;
+        for (int e = tid; e < nfib * nwin; e += blockDim.x) {
+            const int fb = e / nwin, c = e - fb * nwin;
             const int cnt = (c * CH + CH <= n) ? CH : n - c * CH;
             tma_bulk_g2s(ys + (size_t)fb * npad + (size_t)c * (CH + PADE), A + (f0 + fb) * (long long)n + (long long)c * CH,
                          (uint32_t)(cnt * sizeof(T)), &mbar);
@@ -184,11 +186,11 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 2 : 1) k_prox_chunked_cont
 
     const int nreg = in_register(n);
     auto phases = [&](auto lamf) {
-        bool act = lane_ok ? walk_chunk<T, true>(q, 0, nchunks, nreg, y, stv, lamf, div, st, m) : false;
+        bool act = lane_ok ? walk_chunk<T, true, CHT>(q, 0, nchunks, nreg, y, stv, lamf, div, st, m) : false;
         int r = 1;
         for (; __syncthreads_or(act ? 1 : 0); r++) {
             if (r == 1) PHASE_MARK(1);
-            act = lane_ok ? walk_chunk<T, false>(q, r, nchunks, nreg, y, stv, lamf, div, st, m) : false;
+            act = lane_ok ? walk_chunk<T, false, CHT>(q, r, nchunks, nreg, y, stv, lamf, div, st, m) : false;
         }
         PHASE_MARK(2);
 #ifdef PTV_PHASE_TIMING
@@ -199,12 +201,16 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 2 : 1) k_prox_chunked_cont
     else phases(UniformLam<T>{in_register(lam)});
 
     // ---- value of the segment entering each chunk (gathered before any output is written: the store is the output) ----
-    const T cvq = lane_ok ? __ldcg(xrow + carry_of(q, m)) : T(0);
+    const T cvq = lane_ok ? __ldcg(xrow + carry_of<CHT>(q, m)) : T(0);
     if (Mk) {
         // sparse result: the output row keeps only the segment values at their start positions; the chunk's start mask and the value
         // entering it go to Mk / Cv and the consumer (the fused tiled scatter, transpose.cu) expands the segments while it
         // transposes -- the fill phase (a fifth of this CTA's life) is not run at all
-        if (lane_ok) { const long long e = (f0 + fbc) * (long long)lpf + q; Mk[e] = m.P[q]; Cv[e] = cvq; }
+        if (CHT == 32) { if (lane_ok) { const long long e = (f0 + fbc) * (long long)lpf + q; Mk[e] = m.P[q]; Cv[e] = cvq; } }
+        else if (lane_ok && !(q & 1)) {                             // per 32-sample window: the even chunk's lane writes both halves
+            const long long e = (f0 + fbc) * (long long)nwin + (q >> 1);
+            Mk[e] = m.P[q] | ((q + 1 < nchunks) ? (m.P[q + 1] << 16) : 0u); Cv[e] = cvq;
+        }
         return;
     }
     if (lane_ok) cval[(size_t)fbc * lpf + q] = cvq;
@@ -219,13 +225,13 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 2 : 1) k_prox_chunked_cont
     constexpr int FW = 8;
     const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
     const uint32_t below = 0xffffffffu >> (31 - lane);
-    const int bpf = (nchunks + FW - 1) / FW;                      // batches per fiber
+    const int bpf = (nwin + FW - 1) / FW;                         // batches per fiber
     if (bpf >= nwarps) {                                          // long fibers: every warp has work inside each fiber
         for (int fb2 = 0; fb2 < nfib; fb2++) {
             const long long gb = (f0 + fb2) * (long long)n;
             const long long x2b = X2 ? ((f0 + fb2) / inc2) * inc2 * n + (f0 + fb2) % inc2 : 0;
-            for (int c0 = warp * FW; c0 < nchunks; c0 += nwarps * FW)
-                fill_batch<T, FW, CL>(c0, nchunks, n, lane, below, X + gb, gb, x2b, mk + (size_t)fb2 * lpf, cval + (size_t)fb2 * lpf,
+            for (int c0 = warp * FW; c0 < nwin; c0 += nwarps * FW)
+                fill_batch<T, FW, CL, CHT>(c0, nwin, nchunks, n, lane, below, X + gb, gb, x2b, mk + (size_t)fb2 * lpf, cval + (size_t)fb2 * lpf,
                                       ys + (size_t)fb2 * npad, out_op, A, B, C, X2, inc2);
         }
     } else {                                                      // short fibers: deal all (fiber, batch) pairs to the warps
@@ -233,7 +239,7 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 2 : 1) k_prox_chunked_cont
             const int fb2 = bi / bpf, c0 = (bi - fb2 * bpf) * FW;
             const long long gb = (f0 + fb2) * (long long)n;
             const long long x2b = X2 ? ((f0 + fb2) / inc2) * inc2 * n + (f0 + fb2) % inc2 : 0;
-            fill_batch<T, FW, CL>(c0, nchunks, n, lane, below, X + gb, gb, x2b, mk + (size_t)fb2 * lpf, cval + (size_t)fb2 * lpf,
+            fill_batch<T, FW, CL, CHT>(c0, nwin, nchunks, n, lane, below, X + gb, gb, x2b, mk + (size_t)fb2 * lpf, cval + (size_t)fb2 * lpf,
                                   ys + (size_t)fb2 * npad, out_op, A, B, C, X2, inc2);
         }
     }
@@ -268,10 +274,14 @@ static cudaError_t launch_chunked_contig(const T* A, const T* B, const T* C, InO
     if (g.inc != 1) return cudaErrorInvalidConfiguration;
     if (g.nf <= 0 || g.len <= 0) return cudaSuccess;
     const int n = g.len;
-    const int lpf = (n + CH - 1) / CH;
+    // 16-sample chunks for weighted float64 fibers: their second staged row (the weights) limits residency to 3 CTAs of 128
+    // lanes per SM; twice the lanes per fiber bring the warps per SM back to 24
+    const bool half = lamv && sizeof(T) == 8 && !X2 && (n + 15) / 16 <= 1024;
+    const int nrows = (n + CH - 1) / CH;
+    const int lpf = half ? (n + 15) / 16 : nrows;
     if (lpf > 1024) return cudaErrorInvalidConfiguration;
-    const int npad = (n + (lpf + 1) * PadCfg<T>::PADE + PadCfg<T>::PADE - 1) / PadCfg<T>::PADE * PadCfg<T>::PADE;
-    int fpb = 128 / lpf; if (fpb < 1) fpb = 1;
+    const int npad = (n + (nrows + 1) * PadCfg<T>::PADE + PadCfg<T>::PADE - 1) / PadCfg<T>::PADE * PadCfg<T>::PADE;
+    int fpb = (half ? 256 : 128) / lpf; if (fpb < 1) fpb = 1;
     if ((long long)fpb > g.nf) fpb = (int)g.nf;
     const bool cval_aliased = (size_t)fpb * lpf <= 2 * RCP_N;          // see the kernel
     const size_t per_fiber = (size_t)npad * sizeof(T) * (lamv ? 2 : 1) + (size_t)lpf * (12 + (cval_aliased ? 0 : sizeof(T)));
@@ -292,6 +302,8 @@ static cudaError_t launch_chunked_contig(const T* A, const T* B, const T* C, InO
         else kern = k_prox_chunked_contig<T, false, 256, 0>;
     } else {
         // small CTAs (<= 256 threads) get a register budget of up to 128/thread so loop constants stay in registers
+        if (half) kern = threads <= 256 ? k_prox_chunked_contig<T, true, 256, 0, 16> : k_prox_chunked_contig<T, true, 1024, 0, 16>;
+        else
         kern = threads <= 256 ? (lamv ? k_prox_chunked_contig<T, true, 256, 0> : k_prox_chunked_contig<T, false, 256, 0>)
                               : (lamv ? k_prox_chunked_contig<T, true, 1024, 0> : k_prox_chunked_contig<T, false, 1024, 0>);
     }

@@ -11,20 +11,20 @@ using namespace ptv;
 
 template <typename T> struct PtrLd { const T* p; PTV_HD T operator()(int i) const { return p[i]; } };
 // value store that records which chunk each round writes, to assert the write discipline
-template <typename T> struct ChkSt {
+template <typename T, int CHT> struct ChkSt {
     T* p; int* owner_round; int* owner_lane; int* cur_round; int* cur_lane; int* bad;
     PTV_HD void operator()(int j, T v) const {
-        int c = j / CH;
+        int c = j / CHT;
         if (owner_round[c] == *cur_round && owner_lane[c] != *cur_lane) *bad = 1;     // two lanes wrote one chunk in a round
         owner_round[c] = *cur_round; owner_lane[c] = *cur_lane;
         p[j] = v;
     }
 };
 
-template <typename T>
+template <typename T, int CHT = CH>
 static int emu(const T* yin, int n, T lam, const T* lamv, T* x, int out_op, int* rounds_out) {
     if (n <= 0) return 0;
-    const int nchunks = (n + CH - 1) / CH;
+    const int nchunks = (n + CHT - 1) / CHT;
     std::vector<T> ys(yin, yin + n), ws(n, T(0)), cval(nchunks);
     std::vector<RcpPair<T>> rcp(RCP_N);
     for (int d = 0; d < RCP_N; d++) { rcp[d].r = d ? T(1) / T(d) : T(0); rcp[d].d = T(d); }
@@ -36,7 +36,7 @@ static int emu(const T* yin, int n, T lam, const T* lamv, T* x, int out_op, int*
     std::vector<int> orr(nchunks, -1), orl(nchunks, -1);
     int cur_round = 0, cur_lane = 0, bad = 0;
     PtrLd<T> y{ys.data()};
-    ChkSt<T> stv{x, orr.data(), orl.data(), &cur_round, &cur_lane, &bad};
+    ChkSt<T, CHT> stv{x, orr.data(), orl.data(), &cur_round, &cur_lane, &bad};
     RcpDiv<T> div{rcp.data()};
     auto run = [&](auto lamf) -> int {
         int r = 0;
@@ -49,22 +49,22 @@ static int emu(const T* yin, int n, T lam, const T* lamv, T* x, int out_op, int*
                 int c = q + r;          // the chunk lane q reads/writes this round must still hold its pre-round masks
                 if (r > 0 && st[q].active && c < nchunks && (P[c] != sP[c] || K0[c] != sK0[c] || K1[c] != sK1[c])) return -1;
                 if (r == 0) { st[q].active = false; st[q].finished = false; st[q].pend_a = -1; st[q].pend_k = K_NONE;
-                              any |= walk_chunk<T, true>(q, 0, nchunks, n, y, stv, lamf, div, st[q], m); }
-                else any |= walk_chunk<T, false>(q, r, nchunks, n, y, stv, lamf, div, st[q], m);
+                              any |= walk_chunk<T, true, CHT>(q, 0, nchunks, n, y, stv, lamf, div, st[q], m); }
+                else any |= walk_chunk<T, false, CHT>(q, r, nchunks, n, y, stv, lamf, div, st[q], m);
             }
             if (bad) return -2;
             if (!any) break;
         }
         if (rounds_out) *rounds_out = r;
-        for (int c = 0; c < nchunks; c++) cval[c] = x[carry_of(c, m)];           // gather phase (barrier after it)
+        for (int c = 0; c < nchunks; c++) cval[c] = x[carry_of<CHT>(c, m)];      // gather phase (barrier after it)
         for (int c = 0; c < nchunks; c++) {                                        // fill, one window at a time
-            T v[CH];
-            for (int b = 0; b < CH && c * CH + b < n; b++) {                       // all reads of the window ...
-                int sa = seg_start_in_chunk(c, b, m);
-                if (sa >= 0 && sa / CH != c) return -3;                            // ... stay inside the window
+            T v[CHT];
+            for (int b = 0; b < CHT && c * CHT + b < n; b++) {                     // all reads of the window ...
+                int sa = seg_start_in_chunk<CHT>(c, b, m);
+                if (sa >= 0 && sa / CHT != c) return -3;                           // ... stay inside the window
                 v[b] = sa >= 0 ? x[sa] : cval[c];
             }
-            for (int b = 0; b < CH && c * CH + b < n; b++) x[c * CH + b] = apply_out<T>(out_op, ys[c * CH + b], v[b]);
+            for (int b = 0; b < CHT && c * CHT + b < n; b++) x[c * CHT + b] = apply_out<T>(out_op, ys[c * CHT + b], v[b]);
         }
         return 0;
     };
@@ -74,6 +74,9 @@ static int emu(const T* yin, int n, T lam, const T* lamv, T* x, int out_op, int*
 
 extern "C" int emu_chunked_f64(const double* y, int n, double lam, const double* lamv, double* x, int out_op, int* rounds) {
     return emu<double>(y, n, lam, lamv, x, out_op, rounds);
+}
+extern "C" int emu_chunked_f64_ch16(const double* y, int n, double lam, const double* lamv, double* x, int out_op, int* rounds) {
+    return emu<double, 16>(y, n, lam, lamv, x, out_op, rounds);
 }
 extern "C" int emu_chunked_f32(const float* y, int n, float lam, const float* lamv, float* x, int out_op, int* rounds) {
     return emu<float>(y, n, lam, lamv, x, out_op, rounds);

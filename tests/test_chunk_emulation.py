@@ -29,12 +29,15 @@ def emu():
     lib.emu_chunked_f64.argtypes = [dp, C.c_int, C.c_double, dp, dp, C.c_int, C.POINTER(C.c_int)]
     lib.emu_check_table_division.argtypes = [C.c_long, C.c_ulonglong]; lib.emu_check_table_division.restype = C.c_long
 
-    def run(y, lam, w=None, out_op=0):
+    lib.emu_chunked_f64_ch16.argtypes = lib.emu_chunked_f64.argtypes
+
+    def run(y, lam, w=None, out_op=0, ch16=False):
         y = np.ascontiguousarray(y, dtype=np.float64); x = np.empty_like(y); r = C.c_int(0)
         wp = None
         if w is not None:
             w = np.ascontiguousarray(w, dtype=np.float64); wp = w.ctypes.data_as(dp)
-        rc = lib.emu_chunked_f64(y.ctypes.data_as(dp), y.size, float(lam), wp, x.ctypes.data_as(dp), out_op, C.byref(r))
+        fn = lib.emu_chunked_f64_ch16 if ch16 else lib.emu_chunked_f64
+        rc = fn(y.ctypes.data_as(dp), y.size, float(lam), wp, x.ctypes.data_as(dp), out_op, C.byref(r))
         assert rc == 0, "emulated CTA broke the barrier discipline (rc=%d)" % rc
         return x, r.value
     run.lib = lib
@@ -78,6 +81,10 @@ def test_emulated_weighted_and_output_ops(emu, port):
             w[10:40] = 0.0                                                 # zero weights: free jumps
         x, _ = emu(y, 0.0, w)
         assert np.array_equal(x, port.tv1_weighted(y, w)), (y.size, lam)
+        x, _ = emu(y, 0.0, w, ch16=True)                                  # 16-sample chunks (weighted float64 kernel)
+        assert np.array_equal(x, port.tv1_weighted(y, w)), (y.size, lam, "ch16")
+        x, _ = emu(y, lam, ch16=True)
+        assert np.array_equal(x, port.tv1_linearized(y, lam)), (y.size, lam, "ch16 unweighted")
     y, lam = cases()[40]
     x = port.tv1_linearized(y, lam)
     assert np.array_equal(emu(y, lam, out_op=1)[0], 2 * (y - x) - y)       # fused DR reflection
