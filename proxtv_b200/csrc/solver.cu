@@ -262,6 +262,9 @@ int dr2_device(size_t M, size_t N, int batch, int row_major, const T* Y, T w1, T
 template <typename T> cudaError_t gather_fibers(const T* A, const T* B, InOp op, T* out, FiberGeom g, cudaStream_t st);
 template <typename T>
 cudaError_t scatter_fibers_ex(const T* in, const T* A, const T* B, const T* C, InOp op, int out_op, T* X, FiberGeom g, cudaStream_t st);
+template <typename T>
+cudaError_t scatter_fibers_sparse(const T* in, const uint32_t* Mk, const T* Cv, const T* A, const T* B, const T* C, InOp op, int out_op, T* X,
+                                  FiberGeom g, cudaStream_t st);
 
 template <typename T>
 int drw_device(size_t M, size_t N, const T* Y, const T* W1, const T* W2, T* out, int maxit, double* info, void* ws, Engine eng,
@@ -275,7 +278,9 @@ int drw_device(size_t M, size_t N, const T* Y, const T* W1, const T* W2, T* out,
     T* x = (T*)w; w += align256(n * sizeof(T));
     T* t1 = (T*)w; w += align256(n * sizeof(T));
     T* t2 = (T*)w; w += align256(n * sizeof(T));
-    T* w2t = (T*)w; w += 2 * align256(n * sizeof(T));
+    T* w2t = (T*)w; w += align256(n * sizeof(T));
+    T* Cv = (T*)w; uint32_t* Mk = reinterpret_cast<uint32_t*>(Cv + (long long)M * (((long long)N + 31) / 32));   // sparse row results
+    w += align256(n * sizeof(T));
     double* scratch = (double*)w;
     const FiberGeom gc{(long long)N, (int)M, 1}, gr{(long long)M, (int)N, (long long)M}, grc{(long long)M, (int)N, 1};
     bool fast_rows = eng != ENGINE_SEQ && N >= 64 && M >= 1;
@@ -294,13 +299,13 @@ int drw_device(size_t M, size_t N, const T* Y, const T* W1, const T* W2, T* out,
             { KernelSpan sp(KC_ELEMENTWISE, 1, st); PTV_TRY(gather_fibers<T>(Y, s, IN_A_MINUS_B, t1, gr, st)); }
             cudaError_t e;
             { KernelSpan sp(KC_PROX_STRIDED, 1, st);
-              e = prox_fibers_chunked_contig<T>(t1, nullptr, nullptr, IN_A, t2, 0, grc, T(0), w2t, st);
+              e = prox_fibers_chunked_contig_sparse<T>(t1, t2, grc, T(0), w2t, Mk, Cv, st);       // no fill: the scatter expands
               if (e == cudaErrorInvalidConfiguration) sp.cancel(); }
             if (e == cudaErrorInvalidConfiguration) { cudaGetLastError(); fast_rows = false; }
             else {
                 PTV_TRY(e);
                 KernelSpan sp(KC_ELEMENTWISE, 1, st);
-                PTV_TRY(scatter_fibers_ex<T>(t2, Y, s, t, IN_A_MINUS_B, oop, dst, gr, st));
+                PTV_TRY(scatter_fibers_sparse<T>(t2, Mk, Cv, Y, s, t, IN_A_MINUS_B, oop, dst, gr, st));
                 done = true;
             }
         }
