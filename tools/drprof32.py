@@ -11,7 +11,14 @@ out = torch.empty_like(imgs); info = np.zeros(3)
 def solve(): lib.proxtv_DR2_TV_dev_f32(H, H, Bn, 1, C.c_void_p(imgs.data_ptr()), C.c_float(0.2), C.c_float(0.2), C.c_void_p(out.data_ptr()), 0, C.c_void_p(info.ctypes.data), None)
 solve(); torch.cuda.synchronize()
 e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True); e0.record(); solve(); e1.record(); torch.cuda.synchronize()
+if hasattr(lib, "proxtv_debug_phase_read"):
+    ph = (C.c_ulonglong * 8)(); lib.proxtv_debug_phase_read(ph, 1)
 lib.proxtv_profile_reset(); lib.proxtv_profile_enable(1); solve(); torch.cuda.synchronize(); lib.proxtv_profile_enable(0)
 kms = (C.c_double * 3)(); kl = (C.c_longlong * 3)(); ks = (C.c_longlong * 3)(); lib.proxtv_profile_read(kms, kl, ks)
 print("DR2 f32 %dx%d^2 row-major: %.1f ms; class ms:" % (Bn, H, e0.elapsed_time(e1)), [round(kms[i], 2) for i in range(3)], "spans:", [ks[i] for i in range(3)],
       "avg us:", [round(1e3 * kms[i] / max(ks[i], 1), 1) for i in range(3)])
+if hasattr(lib, "proxtv_debug_phase_read"):               # debug build: phases of ALL contig-kernel launches of the profiled solve
+    ph = (C.c_ulonglong * 8)(); lib.proxtv_debug_phase_read(ph, 1)
+    tot = sum(ph[k] for k in range(5))
+    print("    contig-kernel phases (CTA-time share) stage/round0/rounds/cval/fill: " + " ".join(f"{100*ph[k]/tot:.1f}%" for k in range(5))
+          + f"  mean CTA life {tot/ph[7]/1e3:.1f} us, rounds {ph[6]/ph[7]:.2f}")
