@@ -57,6 +57,23 @@ static int emu(const T* yin, int n, T lam, const T* lamv, T* x, int out_op, int*
         }
         if (rounds_out) *rounds_out = r;
         for (int c = 0; c < nchunks; c++) cval[c] = x[carry_of<CHT>(c, m)];      // gather phase (barrier after it)
+        if (out_op == -1) {
+            // SPARSE result (kernels_chunked.cu, Mk / Cv) expanded the way the fused scatter does it (transpose.cu, EXPAND): per
+            // 32-sample window one start mask (two 16-bit halves when CHT == 16) and the value entering the window; the segment
+            // values stay in x at their start positions.  Expansion goes to a separate array first: x is its own source.
+            const int nwin = (n + 31) / 32;
+            std::vector<T> dense(n);
+            for (int w = 0; w < nwin; w++) {
+                const uint32_t mk = (CHT == 32) ? P[w] : (P[2 * w] | ((2 * w + 1 < nchunks) ? (P[2 * w + 1] << 16) : 0u));
+                const T cv = cval[(CHT == 32) ? w : 2 * w];
+                for (int b = 0; b < 32 && w * 32 + b < n; b++) {
+                    const uint32_t ww = mk & (0xffffffffu >> (31 - b));
+                    dense[w * 32 + b] = ww ? x[w * 32 + high_bit(ww)] : cv;
+                }
+            }
+            for (int j = 0; j < n; j++) x[j] = dense[j];
+            return 0;
+        }
         for (int c = 0; c < nchunks; c++) {                                        // fill, one window at a time
             T v[CHT];
             for (int b = 0; b < CHT && c * CHT + b < n; b++) {                     // all reads of the window ...

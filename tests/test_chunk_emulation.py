@@ -71,6 +71,19 @@ def test_emulated_cta_is_bit_identical_to_sequential_scan(emu, port):
     assert worst_rounds >= 3        # the adversarial cases really exercised the multi-round path
 
 
+def test_emulated_sparse_result_expansion(emu, port):
+    """The sparse result (segment values at their starts + per-window start mask and entering value) expanded the way the fused
+    scatter does it equals the dense result, for 32- and 16-sample chunks."""
+    rng = np.random.default_rng(9)
+    for y, lam in cases():
+        x, _ = emu(y, lam, out_op=-1)
+        assert np.array_equal(x, port.tv1_linearized(y, lam)), (y.size, lam)
+        if y.size >= 2:
+            w = rng.uniform(0, 2 * max(lam, 0.1), y.size - 1)
+            x, _ = emu(y, 0.0, w, out_op=-1, ch16=True)
+            assert np.array_equal(x, port.tv1_weighted(y, w)), (y.size, lam, "ch16")
+
+
 def test_emulated_weighted_and_output_ops(emu, port):
     rng = np.random.default_rng(7)
     for y, lam in cases():
