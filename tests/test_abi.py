@@ -69,3 +69,19 @@ def test_python_surface_asserts_like_reference():
         proxtv_b200.tv1_2d(np.zeros((4, 4)), 0.1, method="nope")
     with pytest.raises(AssertionError):
         proxtv_b200.tvgen(np.zeros((4, 4)), [1.0], [1, 2], [1])
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/proxtv_b200.h is the boundary a C / cgo / cffi binding would consume: it must compile as C99 and link."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if not gcc:
+        pytest.skip("gcc not available")
+    src = tmp_path / "hdr_check.c"
+    src.write_text('#include "proxtv_b200.h"\nint main(void) { return proxtv_device_count() < 0; }\n')
+    exe = tmp_path / "hdr_check"
+    libdir = os.path.join(ROOT, "proxtv_b200")
+    subprocess.check_call([gcc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                           "-L", libdir, "-lproxtv_b200", "-Wl,-rpath," + libdir])
+    assert subprocess.call([str(exe)]) == 0
