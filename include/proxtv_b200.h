@@ -84,7 +84,8 @@ int PD_TV(double *y, double *lambdas, double *norms, double *dims, double *x, do
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Part 2 -- extensions.  *_dev functions take DEVICE pointers and a cudaStream_t passed as void* (NULL = default
- * stream); they enqueue work and return without synchronising unless stated.  Return value: 1 ok / 0 error, except the
+ * stream); they run on the CURRENT device (cudaSetDevice), which must own the pointers and the stream -- workspaces, streams and
+ * captured graphs are kept per device; they enqueue work and return without synchronising unless stated.  Return value: 1 ok / 0 error, except the
  * DR2 family which follows DR2_TV (always 0; check info[2]).
  * ------------------------------------------------------------------------------------------------------------------ */
 

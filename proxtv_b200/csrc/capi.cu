@@ -33,7 +33,13 @@ struct Arena {
     }
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
-Arena g_ws, g_io;     // solver workspace ; staging of host arrays
+// solver workspace ; staging of host arrays -- one pair per device, so that a process that works on several devices in turn
+// (torch tensors on cuda:0 and cuda:1) never hands one device's memory to kernels running on another
+constexpr int MAX_DEV = 64;
+Arena g_ws_d[MAX_DEV], g_io_d[MAX_DEV];
+int cur_dev() { int d = 0; if (cudaGetDevice(&d) != cudaSuccess) { cudaGetLastError(); d = 0; } return (d < 0 || d >= MAX_DEV) ? 0 : d; }
+#define g_ws (g_ws_d[cur_dev()])
+#define g_io (g_io_d[cur_dev()])
 
 bool fail(const char* fn, const char* msg, double* info) {
     g_err = std::string(fn) + ": " + msg;
@@ -181,7 +187,7 @@ void proxtv_host_free(void* p) { if (p) cudaFreeHost(p); }
 void proxtv_profile_enable(int on) { profile_enable(on); }
 void proxtv_profile_reset(void) { profile_reset(); }
 void proxtv_profile_read(double* ms, long long* launches, long long* spans) { profile_read(ms, launches, spans); }
-void proxtv_release_workspace(void) { std::lock_guard<std::mutex> lk(g_mu); g_ws.release(); g_io.release(); }
+void proxtv_release_workspace(void) { std::lock_guard<std::mutex> lk(g_mu); for (int d = 0; d < MAX_DEV; d++) { g_ws_d[d].release(); g_io_d[d].release(); } }
 
 // ---- Part 1: drop-in symbols ----
 void hybridTautString_TV1(double* y, int n, double lambda, double* x) {

@@ -65,7 +65,11 @@ struct DrPipe {
         return ok = true;
     }
 };
-static DrPipe g_pipe;     // calls are serialised by the C-ABI mutex
+// streams, events and the captured graph belong to one device: one set per device (calls are serialised by the C-ABI mutex)
+static constexpr int MAX_DEV = 64;
+static DrPipe g_pipe_d[MAX_DEV];
+static int cur_dev() { int d = 0; if (cudaGetDevice(&d) != cudaSuccess) { cudaGetLastError(); d = 0; } return (d < 0 || d >= MAX_DEV) ? 0 : d; }
+#define g_pipe (g_pipe_d[cur_dev()])
 
 // one iteration (or the final projection pair when `final`): t -> s (cols) -> x (rows); returns false on a CUDA error.
 // Each pass is cut into p.parts pieces issued alternately on two compute streams; the transpose of a piece is queued on
@@ -157,7 +161,8 @@ struct DrGraphKey {
     }
 };
 struct DrGraph { cudaGraphExec_t exec = nullptr; DrGraphKey key{}; long long launches[KC_COUNT] = {0, 0, 0}; };
-static DrGraph g_dr_graph;
+static DrGraph g_dr_graph_d[MAX_DEV];
+#define g_dr_graph (g_dr_graph_d[cur_dev()])
 
 // ------------------------------------------------------------------------------------------------------------------
 template <typename T> size_t ws_bytes_dr2(size_t M, size_t N, int batch) {
