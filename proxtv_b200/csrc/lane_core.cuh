@@ -1,0 +1,330 @@
+// lane_core.cuh -- the lane-per-fiber streaming engine of the exact 1D TV-L1 prox (host+device: the same source runs in the
+// CUDA kernel, kernels_lane.cu, and lane by lane on the CPU, tests/emu/emu_lane.cu).
+//
+// What it computes: x = argmin 1/2 |x - y|^2 + lam * sum |x_i - x_{i+1}| for every fiber -- the minimiser the reference
+// obtains with src/TVL1opt_hybridtautstring.cpp:56-235 (== src/TVL1opt.cpp:359-564, linearized taut string).  The scan is the
+// same taut-string walk (same break decisions, same backtracking to the last touch point, same closing rule with the 1e-10
+// tolerance at the last sample, :176,:201), but carried in SLOPE FORM: instead of the heights of the two candidate lines over
+// the tube centre, updated incrementally (`mnHeight += mn - y[i]`, :84), it keeps the cumulative sum S since the anchor of
+// the current segment and compares slopes,
+//        cl = (S - lam - A) / k      slope from the anchor to the tube floor at sample i     (A = anchor height, k = i - last)
+//        ch = (S + lam - A) / k      slope from the anchor to the tube ceiling
+//        ceiling violation  <=>  lo > ch        floor violation  <=>  hi < cl        touches:  lo = max(lo, cl), hi = min(hi, ch)
+// which is the same mathematics with 8 instead of 20 float64 operations per step and no division (k is a small integer: a table
+// of correctly rounded reciprocals).  Results agree with the reference to a few ulp (not bit for bit: the rounding sequence
+// differs), jump sets are identical away from exact ties; the bit-faithful kernels (kernels_chunked.cu) remain the ones behind
+// the 1D entry points.  With Z = S - lam - A the anchor only sets the initial Z of a segment: fiber start -lam, after a
+// ceiling break 0, after a floor break -2 lam -- the scan state after a break is a pure function of (position, kind), the
+// renewal property that makes speculative starts exact once they meet the true scan.
+//
+// B200 mapping.  One LANE owns one fiber (or one chunk of it), a warp owns 32 ADJACENT fibers, and the samples stream through a
+// circular shared-memory window laid out [row = sample][lane = fiber]: lane j only ever touches column j, so every shared
+// access of the scan is bank-conflict free no matter how far the lanes' positions diverge, warps never wait for each other
+// (no CTA barrier in the scan), and for fibers that are adjacent in memory (every dimension but the first of a column-major
+// array) a window row is one contiguous 256-byte line -- the strided pass needs no transpose at all.  Finished segments
+// leave their value at their first row (the slot is dead by then) plus a one-byte flag; a lock-step sweep expands them
+// and hands finished rows to the drain.  Long fibers (one image = only 4096 fibers) are cut into chunks of a few hundred
+// samples that start cold `halo` samples early; a chunk is exact iff the (start, kind) of its segment covering its first row
+// equals the predecessor's record of the same segment, which the last warp of a fiber group to finish verifies; a mismatch
+// (or a segment too long for the window) is repaired by an exact sequential continuation from the last verified renewal state.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#ifndef PTV_HD
+#define PTV_HD __host__ __device__ __forceinline__
+#endif
+
+namespace ptvl {
+
+constexpr int LANES = 32;
+enum : int { LK_CEIL = 0, LK_FLOOR = 1, LK_BEGIN = 2 };          // kind of a segment start (how its anchor was set)
+constexpr int REC_NONE = -1;                                     // record: no valid (start, kind)
+PTV_HD int rec_pack(int pos, int kind) { return pos * 4 + kind; }
+PTV_HD int rec_pos(int r) { return r >> 2; }
+PTV_HD int rec_kind(int r) { return r & 3; }
+
+template <typename T> struct LaneEps { };
+template <> struct LaneEps<double> { static PTV_HD double v() { return 1e-10; } };    // src/general.h:64
+template <> struct LaneEps<float>  { static PTV_HD float  v() { return 1e-10f; } };
+
+template <typename T> PTV_HD T z_of_kind(int kind, T lam) { return kind == LK_CEIL ? T(0) : (kind == LK_FLOOR ? T(-2) * lam : -lam); }
+
+// ------------------------------------------------------------------------------------------------------------------
+// Exact sequential scan in slope form from a renewal state, generic over how samples are read and results written.
+// Used by the repair path of the kernel (global memory), the tail of a fiber (window) and the CPU tests.
+//   ld(i)              sample i of the fiber
+//   seg(f, e, v, kind) called for every finished segment [f, e] with value v whose start has `kind`; returns true to stop
+// Starts at position `pos` with a segment of kind `kind` beginning there; runs to the end of the fiber (n) unless stopped.
+template <typename T, class Ld, class Seg>
+PTV_HD void slope_seq(int n, T lam, int pos, int kind, Ld ld, Seg seg) {
+    const T lam2 = T(2) * lam;
+    int last = pos - 1, i = pos, blo = pos, bhi = pos, kcur = kind;
+    T Z = z_of_kind<T>(kind, lam), lo = T(0), hi = T(0);
+    while (i < n) {
+        Z += ld(i);
+        const int k = i - last;
+        const T r = T(1) / T(k);
+        if (i < n - 1) {
+            const T cl = Z * r, ch = (Z + lam2) * r;
+            if (k == 1) { lo = cl; hi = ch; blo = bhi = i; i++; continue; }
+            if (lo > ch) {                                   // ceiling violation (hybridtautstring.cpp:93-111)
+                if (seg(last + 1, blo, lo, kcur)) return;
+                last = blo; i = blo + 1; Z = T(0); kcur = LK_CEIL; continue;
+            }
+            if (hi < cl) {                                   // floor violation (:119-137)
+                if (seg(last + 1, bhi, hi, kcur)) return;
+                last = bhi; i = bhi + 1; Z = -lam2; kcur = LK_FLOOR; continue;
+            }
+            if (cl >= lo) { lo = cl; blo = i; }              // (:153-160)
+            if (ch <= hi) { hi = ch; bhi = i; }              // (:143-150)
+            i++;
+        } else {                                             // last sample: the tube closes on its centre (:169-224)
+            const T c = Z + lam;
+            if (k == 1) { seg(last + 1, i, c, kcur); return; }
+            const T hl = lo * T(k) - c, hh = hi * T(k) - c;
+            if (hl > LaneEps<T>::v()) {
+                if (seg(last + 1, blo, lo, kcur)) return;
+                last = blo; i = blo + 1; Z = T(0); kcur = LK_CEIL; continue;
+            }
+            if (hh < -LaneEps<T>::v()) {
+                if (seg(last + 1, bhi, hi, kcur)) return;
+                last = bhi; i = bhi + 1; Z = -lam2; kcur = LK_FLOOR; continue;
+            }
+            if (hl <= T(0)) lo = c * r;
+            seg(last + 1, i, lo, kcur);
+            return;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Shared-memory window of one warp: W rows (power of two) of 32 samples + one flag byte per slot.
+template <typename T, int W> struct Window {
+    T* win;            // [W][32]
+    uint8_t* flg;      // [W][32]
+    PTV_HD T ld(int row, int lane) const { return win[((row & (W - 1)) << 5) + lane]; }
+    PTV_HD void st(int row, int lane, T v) const { win[((row & (W - 1)) << 5) + lane] = v; }
+    PTV_HD uint8_t flag(int row, int lane) const { return flg[((row & (W - 1)) << 5) + lane]; }
+    PTV_HD void set_flag(int row, int lane, uint8_t f) const { flg[((row & (W - 1)) << 5) + lane] = f; }
+};
+
+// What one warp task covers: rows [cs, ce) of 32 adjacent fibers of length n, entered with a cold start at p0 <= cs.
+struct TaskGeom {
+    int n;          // samples per fiber
+    int cs, ce;     // rows this task owns (ce == n: the chunk ends the fiber)
+    int p0;         // cold-start row (0: the true start of the fiber)
+};
+
+// Scan state of one lane.
+template <typename T> struct Lane {
+    T Z, lo, hi;
+    int i, last, blo, bhi;
+    int kind;             // kind of the current (open) segment's start
+    int in_rec, out_rec;  // (start, kind) of the first emitted segment / of the finished segment that covers row ce
+    bool done;            // finished (or retired); nothing more to scan
+    bool valid;           // the lane has a fiber
+    bool retired;         // gave up: a segment did not fit the window; ovf_rec = renewal state to continue from
+    int ovf_rec;
+    T xcur;               // value carried by the sweep
+
+    PTV_HD void init(const TaskGeom& g, T lam, bool is_valid) {
+        i = g.p0; last = g.p0 - 1; blo = bhi = g.p0; kind = LK_BEGIN;
+        Z = -lam; lo = hi = T(0);
+        in_rec = out_rec = ovf_rec = REC_NONE;
+        valid = is_valid; done = !is_valid; retired = false; xcur = T(0);
+    }
+
+    // a finished segment [f, e] with value v: leave the value at its first owned row
+    template <int W>
+    PTV_HD void emit(const Window<T, W>& w, int lane, const TaskGeom& g, int f, int e, T v) {
+        if (e >= g.cs) {
+            if (in_rec == REC_NONE) in_rec = rec_pack(f, kind);
+            const int fe = f > g.cs ? f : g.cs;
+            w.st(fe, lane, v); w.set_flag(fe, lane, 1);
+            if (e >= g.ce) { done = true; out_rec = rec_pack(f, kind); }
+        }
+    }
+
+    // up to `niter` scan steps on rows below `lim` (lim <= n - 1: the last sample is never processed here)
+    template <int W>
+    PTV_HD void run(const Window<T, W>& w, int lane, const TaskGeom& g, const T* __restrict__ rcp, T lam2, int lim, int niter) {
+        for (int it = 0; it < niter; it++) {
+            if (done || i >= lim) break;              // a lane that reached the frontier cannot move again this epoch
+            Z += w.ld(i, lane);
+            const int k = i - last;
+            const T r = rcp[k];
+            const T cl = Z * r, ch = (Z + lam2) * r;
+            const bool first = (k == 1);
+            const bool cbk = !first && (lo > ch);
+            const bool fbk = !first && !cbk && (hi < cl);
+            if (cbk | fbk) {
+                const int e = cbk ? blo : bhi;
+                emit<W>(w, lane, g, last + 1, e, cbk ? lo : hi);
+                kind = cbk ? LK_CEIL : LK_FLOOR;
+                last = e; i = e + 1; Z = cbk ? T(0) : -lam2;
+            } else {
+                if (first || cl >= lo) { lo = cl; blo = i; }
+                if (first || ch <= hi) { hi = ch; bhi = i; }
+                i++;
+            }
+        }
+    }
+
+    // the fiber's last sample is inside the window and this lane waits in front of it: finish sequentially (closing rule)
+    template <int W>
+    PTV_HD void finish_tail(const Window<T, W>& w, int lane, const TaskGeom& g, T lam) {
+        if (done) return;
+        Lane<T>* self = this;
+        // continue from the renewal state of the open segment: exact, and short (the open segment lies inside the window)
+        slope_seq<T>(g.n, lam, last + 1, kind,
+                     [&](int r) { return w.ld(r, lane); },
+                     [&](int f, int e, T v, int k) { self->kind = k; self->template emit<W>(w, lane, g, f, e, v); return self->done; });
+        done = true;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------------------------
+// One warp task.  Env supplies the lanes and the warp collectives (device: registers + shuffles/votes; host: a loop), Feed
+// brings rows into the window (request(row0): rows [row0, row0+R) ; ready(row0, block)), Drain takes finished rows.
+//   Env:   each(f(Lane&, lane)) ; rmin(f) ; rmax(f) ; any(f) ; sync()
+//   Feed:  R (rows per tile) ; request(env, row0) ; bool landed(env, row0, block)
+//   Drain: row(env, r, lane, x) called inside each() for every owned row in order ; flush(env, upto) ; hold() first row still needed
+struct TaskStats { int epochs, retired, tail; };
+
+template <typename T, int W, int TITER, class Env, class Feed, class Drain>
+PTV_HD void warp_task(Env& env, Feed& feed, Drain& drain, const Window<T, W>& w, const T* __restrict__ rcp, const TaskGeom g, T lam,
+                      int ahead, TaskStats* stats) {
+    constexpr int R = Feed::R;
+    const T lam2 = T(2) * lam;
+    int row_lo = g.p0;                // first row still held by the window
+    int row_req = g.p0;               // rows below have been requested
+    int row_hi = g.p0;                // rows below are in the window, ready for the scan
+    int fill_pos = g.cs;              // next owned row to sweep
+    const int BIG = 0x3fffffff;
+    for (int epoch = 0;; epoch++) {
+        // ---- feed: keep `ahead` rows in front of the fastest lane, never more than the window holds ----
+        {
+            const int maxi = env.rmax([&](Lane<T>& L, int) { return L.done ? -1 : L.i; });
+            int want = maxi + ahead;
+            const int cap = g.ce + R;                                    // beyond the chunk only on demand (overrun of the last segment)
+            if (want > cap) {
+                const bool starving = env.any([&](Lane<T>& L, int) { return !L.done && L.i >= row_hi; });
+                want = starving ? (maxi + 1 > cap ? maxi + 1 : cap) : (cap > row_hi ? cap : row_hi);
+            }
+            if (want > g.n) want = g.n;
+            while (row_req < want && row_req + R <= row_lo + W) { feed.request(env, row_req); row_req += R; }
+            // take over what has landed; block only if nobody can move otherwise
+            while (row_hi < row_req) {
+                const int lim0 = row_hi < g.n - 1 ? row_hi : g.n - 1;
+                const bool can_move = env.any([&](Lane<T>& L, int) { return !L.done && L.i < lim0; });
+                if (!feed.landed(env, row_hi, !can_move)) break;
+                row_hi += R;
+            }
+        }
+        const int lim = row_hi < g.n - 1 ? row_hi : g.n - 1;
+        // ---- scan ----
+        env.each([&](Lane<T>& L, int lane) { L.template run<W>(w, lane, g, rcp, lam2, lim, TITER); });
+        env.sync();
+        // ---- sweep finished rows, slide the window ----
+        int low = env.rmin([&](Lane<T>& L, int) { return L.done ? BIG : L.last + 1; });
+        const bool all_done = (low == BIG);
+        {
+            int upto = low < g.ce ? low : g.ce;
+            if (upto > row_hi) upto = row_hi;          // only retired lanes leave owned rows outside the window (repaired later)
+            if (upto > fill_pos) {
+                const int a = fill_pos;
+                env.each([&](Lane<T>& L, int lane) {
+                    for (int r = a; r < upto; r++) {
+                        if (w.flag(r, lane)) { L.xcur = w.ld(r, lane); w.set_flag(r, lane, 0); }
+                        drain.row(w, r, lane, L.xcur, L.valid);
+                    }
+                });
+                fill_pos = upto;
+                env.sync();
+                drain.flush(env, w, fill_pos, false);
+            }
+            int nlo = all_done ? row_hi : low;
+            const int hold = drain.hold(fill_pos, g.ce);
+            if (nlo > hold) nlo = hold;
+            if (nlo > row_lo) row_lo = nlo;
+        }
+        if (all_done) break;
+        // ---- lanes that wait in front of the last sample: finish them when nobody else can move ----
+        const bool movable = env.any([&](Lane<T>& L, int) { return !L.done && L.i < g.n - 1; });
+        if (!movable) {
+            // every remaining lane sits at row n-1 (which must be in the window)
+            if (row_hi >= g.n) {
+                env.each([&](Lane<T>& L, int lane) { L.template finish_tail<W>(w, lane, g, lam); });
+                env.sync();
+                if (stats) stats->tail++;
+                continue;      // next epoch sweeps the rest and leaves through all_done
+            }
+        }
+        // ---- deadlock: nobody can move, nothing more fits -> retire the lanes that pin the window ----
+        {
+            const bool can_move = env.any([&](Lane<T>& L, int) { return !L.done && L.i < lim; });
+            const bool can_feed = (row_req < g.n) && (row_req + R <= row_lo + W);
+            const bool pending = row_hi < row_req;
+            if (!can_move && !can_feed && !pending && !(row_hi >= g.n)) {
+                env.each([&](Lane<T>& L, int) {
+                    if (!L.done && L.last + 1 == low) { L.done = true; L.retired = true; L.ovf_rec = rec_pack(L.last + 1, L.kind); }
+                });
+                if (stats) stats->retired++;
+            } else if (!can_move && !can_feed && !pending && row_hi >= g.n) {
+                // the fiber end is in the window but a lane's open segment started before the window could hold it together
+                // with row n-1: cannot happen (row_lo <= last+1 always), kept as a guard against an endless loop
+                env.each([&](Lane<T>& L, int) { if (!L.done && L.i >= g.n - 1) { /* handled by finish_tail above */ } });
+            }
+        }
+        if (stats) stats->epochs = epoch + 1;
+    }
+    drain.flush(env, w, fill_pos, true);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Chunking of a fiber: nchunks chunks of `clen` rows (the last one takes the remainder), each entered `halo` rows early.
+struct ChunkPlan {
+    int n, clen, nchunks, halo;
+    PTV_HD int cs(int c) const { return c * clen; }
+    PTV_HD int ce(int c) const { return c + 1 >= nchunks ? n : (c + 1) * clen; }
+    PTV_HD TaskGeom geom(int c) const {
+        TaskGeom g; g.n = n; g.cs = cs(c); g.ce = ce(c);
+        g.p0 = g.cs - halo > 0 ? g.cs - halo : 0;
+        return g;
+    }
+};
+
+// Verification and repair of ONE fiber after all its chunks have been scanned (run by the last warp of the fiber group to
+// finish).  rin/rout/rovf(c): the chunk's records for this fiber.  A chunk is exact on entry iff the (start, kind) of its
+// first emitted segment equals the predecessor's record of the segment that covers the chunk's first row (both scans are then
+// in the identical renewal state from that start on).  Otherwise -- or when a lane retired inside the chunk -- the exact
+// sequential scan continues from the last verified renewal state, writing results directly, until one of its finished
+// segments coincides with the first segment of a later chunk (merge) or the fiber ends.  Returns the number of repair scans.
+template <typename T, class RecIn, class RecOut, class RecOvf, class Ld, class St>
+PTV_HD int verify_repair_fiber(const ChunkPlan& pl, T lam, RecIn rin, RecOut rout, RecOvf rovf, Ld ld, St st) {
+    int repairs = 0, c = 0;
+    bool entry_ok = true;                 // chunk c is known to be exact on entry (chunk 0; or established by a merge)
+    while (c < pl.nchunks) {
+        int cur = REC_NONE, cnext = c + 1;
+        // when the loop arrives here through `c++`, chunk c-1 was exact to its end, so rout(c-1) is a true record
+        if (!entry_ok && rin(c) != rout(c - 1)) { cur = rout(c - 1); cnext = c; }
+        else if (rovf(c) != REC_NONE) cur = rovf(c);
+        if (cur == REC_NONE) { c++; entry_ok = false; continue; }
+        repairs++;
+        int resume = pl.nchunks;
+        slope_seq<T>(pl.n, lam, rec_pos(cur), rec_kind(cur), ld,
+                     [&](int f, int e, T v, int kind) {
+                         for (int r = f; r <= e; r++) st(r, v);
+                         while (cnext < pl.nchunks && pl.cs(cnext) <= e) {     // chunk starts covered by this segment
+                             if (pl.cs(cnext) >= f && rin(cnext) == rec_pack(f, kind)) { resume = cnext; return true; }
+                             cnext++;
+                         }
+                         return false;
+                     });
+        c = resume; entry_ok = true;      // merged into chunk `resume` (or reached the end of the fiber)
+    }
+    return repairs;
+}
+
+}  // namespace ptvl
