@@ -13,6 +13,14 @@
 #include <vector>
 
 using namespace ptv;
+namespace ptvl {
+void* lane_scratch(long long nf, int len);
+void lane_set_tuning(int clen, int halo, int variant);
+unsigned long long lane_read_stats(int reset);
+template <typename T>
+cudaError_t lane_prox_strided(int op, const T* A, const T* B, const T* C, T* X, long long nf, int len, long long inc, T lam, void* scratch,
+                              cudaStream_t st);
+}
 
 namespace {
 
@@ -188,6 +196,26 @@ void proxtv_profile_enable(int on) { profile_enable(on); }
 void proxtv_profile_reset(void) { profile_reset(); }
 void proxtv_profile_read(double* ms, long long* launches, long long* spans) { profile_read(ms, launches, spans); }
 void proxtv_release_workspace(void) { std::lock_guard<std::mutex> lk(g_mu); for (int d = 0; d < MAX_DEV; d++) { g_ws_d[d].release(); g_io_d[d].release(); } }
+
+// ---- experimental: the lane-per-fiber streaming engine (kernels_lane.cu), device pointers ----
+int proxtv_lane_prox_dev_f64(int op, const double* A, const double* B, const double* C, double* X, long long nf, int len, long long inc,
+                             double lam, void* stream) {
+    void* scr = ptvl::lane_scratch(nf, len);
+    if (!scr) return 0;
+    cudaError_t e = ptvl::lane_prox_strided<double>(op, A, B, C, X, nf, len, inc, lam, scr, (cudaStream_t)stream);
+    if (e != cudaSuccess) { cudaGetLastError(); g_err = std::string("proxtv_lane_prox_dev_f64: ") + cudaGetErrorString(e); return 0; }
+    return 1;
+}
+int proxtv_lane_prox_dev_f32(int op, const float* A, const float* B, const float* C, float* X, long long nf, int len, long long inc,
+                             float lam, void* stream) {
+    void* scr = ptvl::lane_scratch(nf, len);
+    if (!scr) return 0;
+    cudaError_t e = ptvl::lane_prox_strided<float>(op, A, B, C, X, nf, len, inc, lam, scr, (cudaStream_t)stream);
+    if (e != cudaSuccess) { cudaGetLastError(); g_err = std::string("proxtv_lane_prox_dev_f32: ") + cudaGetErrorString(e); return 0; }
+    return 1;
+}
+void proxtv_lane_tuning(int clen, int halo, int variant) { ptvl::lane_set_tuning(clen, halo, variant); }
+unsigned long long proxtv_lane_stats(int reset) { return ptvl::lane_read_stats(reset); }
 
 // ---- Part 1: drop-in symbols ----
 void hybridTautString_TV1(double* y, int n, double lambda, double* x) {

@@ -99,17 +99,26 @@ PTV_HD void slope_seq(int n, T lam, int pos, int kind, Ld ld, Seg seg) {
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// Shared-memory window of one warp: W rows (power of two) of 32 samples + one flag byte per slot.
+// Shared-memory window of one warp: W rows (power of two) of 32 samples [row][lane], and one flag byte per slot kept per
+// lane ([lane][row], lane pitch W + 8 bytes: a lane's 8 consecutive flags are one aligned 8-byte word and the 32 lanes' words
+// of the same row group fall into 32 different banks).
 template <typename T, int W> struct Window {
+    static constexpr int FP = W + 8;       // flag pitch per lane (bytes): 8-byte aligned rows, 18-word lane stride spreads the banks
     T* win;            // [W][32]
-    uint8_t* flg;      // [W][32]
+    uint8_t* flg;      // [32][FP]
     PTV_HD T ld(int row, int lane) const { return win[((row & (W - 1)) << 5) + lane]; }
     PTV_HD void st(int row, int lane, T v) const { win[((row & (W - 1)) << 5) + lane] = v; }
-    PTV_HD uint8_t flag(int row, int lane) const { return flg[((row & (W - 1)) << 5) + lane]; }
-    PTV_HD void set_flag(int row, int lane, uint8_t f) const { flg[((row & (W - 1)) << 5) + lane] = f; }
+    PTV_HD void set_flag(int row, int lane) const { flg[lane * FP + (row & (W - 1))] = 1; }
+    // the 8 flags of the aligned row group that starts at row0 (row0 % 8 == 0), and clearing them
+    PTV_HD unsigned long long flags8(int row0, int lane) const {
+        return *reinterpret_cast<const unsigned long long*>(flg + lane * FP + (row0 & (W - 1)));
+    }
+    PTV_HD void clear8(int row0, int lane) const { *reinterpret_cast<unsigned long long*>(flg + lane * FP + (row0 & (W - 1))) = 0ull; }
+    static constexpr size_t flag_bytes() { return (size_t)LANES * FP; }
 };
 
 // What one warp task covers: rows [cs, ce) of 32 adjacent fibers of length n, entered with a cold start at p0 <= cs.
+// cs and p0 are multiples of 8 (the sweep and the feed work on aligned groups of 8 rows).
 struct TaskGeom {
     int n;          // samples per fiber
     int cs, ce;     // rows this task owns (ce == n: the chunk ends the fiber)
@@ -121,6 +130,7 @@ template <typename T> struct Lane {
     T Z, lo, hi;
     int i, last, blo, bhi;
     int kind;             // kind of the current (open) segment's start
+    int lprev, kprev;     // `last` and `kind` before the most recent break: start and kind of the most recently finished segment
     int in_rec, out_rec;  // (start, kind) of the first emitted segment / of the finished segment that covers row ce
     bool done;            // finished (or retired); nothing more to scan
     bool valid;           // the lane has a fiber
@@ -129,46 +139,60 @@ template <typename T> struct Lane {
     T xcur;               // value carried by the sweep
 
     PTV_HD void init(const TaskGeom& g, T lam, bool is_valid) {
-        i = g.p0; last = g.p0 - 1; blo = bhi = g.p0; kind = LK_BEGIN;
+        i = g.p0; last = g.p0 - 1; blo = bhi = g.p0; kind = LK_BEGIN; lprev = last; kprev = LK_BEGIN;
         Z = -lam; lo = hi = T(0);
         in_rec = out_rec = ovf_rec = REC_NONE;
         valid = is_valid; done = !is_valid; retired = false; xcur = T(0);
     }
 
-    // a finished segment [f, e] with value v: leave the value at its first owned row
-    template <int W>
-    PTV_HD void emit(const Window<T, W>& w, int lane, const TaskGeom& g, int f, int e, T v) {
-        if (e >= g.cs) {
-            if (in_rec == REC_NONE) in_rec = rec_pack(f, kind);
-            const int fe = f > g.cs ? f : g.cs;
-            w.st(fe, lane, v); w.set_flag(fe, lane, 1);
-            if (e >= g.ce) { done = true; out_rec = rec_pack(f, kind); }
+    // `niter` scan steps, no bounds checks: the caller guarantees i + niter <= frontier (and <= n - 1: the last sample is never
+    // processed here).  Straight-line and branch-free by design -- every lane of a warp executes the same instructions whether it
+    // advances, touches or breaks (a break is a handful of selects plus one predicated store), so the lanes of a warp never diverge.
+    // Once the segment that covers row ce is finished (last >= ce) breaks are disabled and the lane only coasts; the epoch loop
+    // retires it.  PH1: the lane may still be in front of its first owned segment (clip to cs, record the entry state).
+    template <bool PH1, int W>
+    PTV_HD void run(const Window<T, W>& w, int lane, const TaskGeom& g, const T* __restrict__ rcp, T lam2, int niter) {
+        T Z_ = Z, lo_ = lo, hi_ = hi;
+        int i_ = i, last_ = last, blo_ = blo, bhi_ = bhi, kind_ = kind, lprev_ = lprev, kprev_ = kprev, in_ = in_rec;
+        const T nlam2 = -lam2;
+        for (int it = 0; it < niter; it++) {
+            const T y = w.ld(i_, lane);
+            const int k = i_ - last_;
+            const T r = rcp[k];
+            Z_ += y;
+            const T cl = Z_ * r, ch = (Z_ + lam2) * r;
+            const bool first = (k == 1);
+            const bool can = !first & (last_ < g.ce);
+            const bool cbk = can & (lo_ > ch);
+            const bool fbk = can & !cbk & (hi_ < cl);
+            const bool brk = cbk | fbk;
+            const int e = cbk ? blo_ : bhi_;
+            const T v = cbk ? lo_ : hi_;
+            const int f = last_ + 1;
+            if (PH1) {
+                if (brk & (e >= g.cs)) {
+                    if (in_ == REC_NONE) in_ = rec_pack(f, kind_);
+                    const int fe = f > g.cs ? f : g.cs;
+                    w.st(fe, lane, v); w.set_flag(fe, lane);
+                }
+            } else {
+                if (brk) { w.st(f, lane, v); w.set_flag(f, lane); }
+            }
+            const bool tlo = first | (cl >= lo_), thi = first | (ch <= hi_);
+            lo_ = tlo ? cl : lo_; blo_ = tlo ? i_ : blo_;
+            hi_ = thi ? ch : hi_; bhi_ = thi ? i_ : bhi_;
+            lprev_ = brk ? last_ : lprev_; kprev_ = brk ? kind_ : kprev_;
+            kind_ = cbk ? (int)LK_CEIL : (fbk ? (int)LK_FLOOR : kind_);
+            Z_ = cbk ? T(0) : (fbk ? nlam2 : Z_);
+            i_ = brk ? e + 1 : i_ + 1;
+            last_ = brk ? e : last_;
         }
+        Z = Z_; lo = lo_; hi = hi_; i = i_; last = last_; blo = blo_; bhi = bhi_; kind = kind_; lprev = lprev_; kprev = kprev_; in_rec = in_;
     }
 
-    // up to `niter` scan steps on rows below `lim` (lim <= n - 1: the last sample is never processed here)
-    template <int W>
-    PTV_HD void run(const Window<T, W>& w, int lane, const TaskGeom& g, const T* __restrict__ rcp, T lam2, int lim, int niter) {
-        for (int it = 0; it < niter; it++) {
-            if (done || i >= lim) break;              // a lane that reached the frontier cannot move again this epoch
-            Z += w.ld(i, lane);
-            const int k = i - last;
-            const T r = rcp[k];
-            const T cl = Z * r, ch = (Z + lam2) * r;
-            const bool first = (k == 1);
-            const bool cbk = !first && (lo > ch);
-            const bool fbk = !first && !cbk && (hi < cl);
-            if (cbk | fbk) {
-                const int e = cbk ? blo : bhi;
-                emit<W>(w, lane, g, last + 1, e, cbk ? lo : hi);
-                kind = cbk ? LK_CEIL : LK_FLOOR;
-                last = e; i = e + 1; Z = cbk ? T(0) : -lam2;
-            } else {
-                if (first || cl >= lo) { lo = cl; blo = i; }
-                if (first || ch <= hi) { hi = ch; bhi = i; }
-                i++;
-            }
-        }
+    // after run(): has the segment that covers row ce been finished?
+    PTV_HD void settle(const TaskGeom& g) {
+        if (!done && last >= g.ce) { done = true; out_rec = rec_pack(lprev + 1, kprev); }
     }
 
     // the fiber's last sample is inside the window and this lane waits in front of it: finish sequentially (closing rule)
@@ -179,65 +203,98 @@ template <typename T> struct Lane {
         // continue from the renewal state of the open segment: exact, and short (the open segment lies inside the window)
         slope_seq<T>(g.n, lam, last + 1, kind,
                      [&](int r) { return w.ld(r, lane); },
-                     [&](int f, int e, T v, int k) { self->kind = k; self->template emit<W>(w, lane, g, f, e, v); return self->done; });
+                     [&](int f, int e, T v, int k) {
+                         if (e >= g.cs) {
+                             if (self->in_rec == REC_NONE) self->in_rec = rec_pack(f, k);
+                             const int fe = f > g.cs ? f : g.cs;
+                             w.st(fe, lane, v); w.set_flag(fe, lane);
+                             if (e >= g.ce) { self->done = true; self->out_rec = rec_pack(f, k); }
+                         }
+                         return self->done; });
         done = true;
     }
 };
 
 // ------------------------------------------------------------------------------------------------------------------
 // One warp task.  Env supplies the lanes and the warp collectives (device: registers + shuffles/votes; host: a loop), Feed
-// brings rows into the window (request(row0): rows [row0, row0+R) ; ready(row0, block)), Drain takes finished rows.
-//   Env:   each(f(Lane&, lane)) ; rmin(f) ; rmax(f) ; any(f) ; sync()
-//   Feed:  R (rows per tile) ; request(env, row0) ; bool landed(env, row0, block)
-//   Drain: row(env, r, lane, x) called inside each() for every owned row in order ; flush(env, upto) ; hold() first row still needed
-struct TaskStats { int epochs, retired, tail; };
+// brings rows into the window, Drain takes finished rows.
+//   Env:   each(f(Lane&, lane)) ; rmin(f) ; rmax(f) ; any(f) ; sync() ; scan(L, w, lane, g, rcp, lam2, ph1, niter)
+//   Feed:  R rows per tile (8) ; MAXQ tiles that may be outstanding ; request(env, row0) ; bool landed(env, row0, block)
+//   Drain: rows8(w, r0, cnt, lane, xs, valid) inside each() for every aligned group of 8 owned rows, in order ; flush(env, w,
+//          upto, final) ; hold(): first row the window still has to keep for it
+struct TaskStats { int epochs, retired, tail, iters; };
 
 template <typename T, int W, int TITER, class Env, class Feed, class Drain>
 PTV_HD void warp_task(Env& env, Feed& feed, Drain& drain, const Window<T, W>& w, const T* __restrict__ rcp, const TaskGeom g, T lam,
                       int ahead, TaskStats* stats) {
     constexpr int R = Feed::R;
+    constexpr int DMIN = 8;           // lanes closer than this to the frontier sit an epoch out rather than shorten it for everybody
     const T lam2 = T(2) * lam;
     int row_lo = g.p0;                // first row still held by the window
     int row_req = g.p0;               // rows below have been requested
     int row_hi = g.p0;                // rows below are in the window, ready for the scan
-    int fill_pos = g.cs;              // next owned row to sweep
+    int fill_pos = g.cs;              // next owned row to sweep (multiple of 8)
+    bool ph1 = true;                  // some lane has not emitted its first owned segment yet
     const int BIG = 0x3fffffff;
     for (int epoch = 0;; epoch++) {
         // ---- feed: keep `ahead` rows in front of the fastest lane, never more than the window holds ----
+        const int maxi = env.rmax([&](Lane<T>& L, int) { return L.done ? -1 : L.i; });
         {
-            const int maxi = env.rmax([&](Lane<T>& L, int) { return L.done ? -1 : L.i; });
             int want = maxi + ahead;
             const int cap = g.ce + R;                                    // beyond the chunk only on demand (overrun of the last segment)
-            if (want > cap) {
-                const bool starving = env.any([&](Lane<T>& L, int) { return !L.done && L.i >= row_hi; });
-                want = starving ? (maxi + 1 > cap ? maxi + 1 : cap) : (cap > row_hi ? cap : row_hi);
-            }
+            if (want > cap) want = (maxi + DMIN + 1 > cap) ? maxi + DMIN + 1 : cap;
             if (want > g.n) want = g.n;
-            while (row_req < want && row_req + R <= row_lo + W) { feed.request(env, row_req); row_req += R; }
-            // take over what has landed; block only if nobody can move otherwise
-            while (row_hi < row_req) {
-                const int lim0 = row_hi < g.n - 1 ? row_hi : g.n - 1;
-                const bool can_move = env.any([&](Lane<T>& L, int) { return !L.done && L.i < lim0; });
-                if (!feed.landed(env, row_hi, !can_move)) break;
-                row_hi += R;
-            }
+            while (row_req < want && row_req + R <= row_lo + W && row_req - row_hi < Feed::MAXQ * R) { feed.request(env, row_req); row_req += R; }
         }
-        const int lim = row_hi < g.n - 1 ? row_hi : g.n - 1;
+        int lim, niter;
+        for (;;) {
+            lim = row_hi < g.n - 1 ? row_hi : g.n - 1;
+            // iterations every participating lane can run without reaching the frontier
+            const int dmin = env.rmin([&](Lane<T>& L, int) { const int d = lim - L.i; return (L.done || d < DMIN) ? BIG : d; });
+            niter = dmin < TITER ? dmin : TITER;
+            if (dmin == BIG) {           // nobody has DMIN rows in front of it: take what there is
+                const int d1 = env.rmin([&](Lane<T>& L, int) { const int d = lim - L.i; return (L.done || d < 1) ? BIG : d; });
+                niter = d1 == BIG ? 0 : (d1 < TITER ? d1 : TITER);
+            }
+            // take over tiles that have landed; wait for one only if nothing can run
+            if (row_hi < row_req && feed.landed(env, row_hi, niter == 0)) { row_hi += R; continue; }
+            break;
+        }
         // ---- scan ----
-        env.each([&](Lane<T>& L, int lane) { L.template run<W>(w, lane, g, rcp, lam2, lim, TITER); });
-        env.sync();
-        // ---- sweep finished rows, slide the window ----
-        int low = env.rmin([&](Lane<T>& L, int) { return L.done ? BIG : L.last + 1; });
+        if (niter > 0) {
+            const int lim_ = lim, niter_ = niter; const bool ph1_ = ph1;
+            env.each([&](Lane<T>& L, int lane) {
+                const int d = lim_ - L.i;
+                if (!L.done && d >= niter_) {
+                    env.scan(L, w, lane, g, rcp, lam2, ph1_, niter_);      // Lane::run, or the kernel's equivalent device form
+                    L.settle(g);
+                }
+            });
+            env.sync();
+            if (ph1) ph1 = env.any([&](Lane<T>& L, int) { return !L.done && L.in_rec == REC_NONE; });
+            if (stats) stats->iters += niter;
+        }
+        // ---- sweep finished rows (aligned groups of 8), slide the window ----
+        const int low = env.rmin([&](Lane<T>& L, int) { return L.done ? BIG : L.last + 1; });
         const bool all_done = (low == BIG);
         {
             int upto = low < g.ce ? low : g.ce;
             if (upto > row_hi) upto = row_hi;          // only retired lanes leave owned rows outside the window (repaired later)
+            if (upto < g.ce) upto &= ~7;               // whole groups only, except at the very end of the chunk
             if (upto > fill_pos) {
                 const int a = fill_pos;
                 env.each([&](Lane<T>& L, int lane) {
-                    for (int r = a; r < upto; r++) {
-                        if (w.flag(r, lane)) { L.xcur = w.ld(r, lane); w.set_flag(r, lane, 0); }
-                        drain.row(w, r, lane, L.xcur, L.valid);
+                    for (int r = a; r < upto; r += 8) {
+                        T xs[8];
+                        const int cnt = upto - r < 8 ? upto - r : 8;
+                        const unsigned long long fl = w.flags8(r, lane);
+#pragma unroll
+                        for (int u = 0; u < 8; u++) {
+                            if ((fl >> (8 * u)) & 0xffull) L.xcur = w.ld(r + u, lane);
+                            xs[u] = L.xcur;
+                        }
+                        w.clear8(r, lane);
+                        drain.rows8(w, r, cnt, lane, xs, L.valid);
                     }
                 });
                 fill_pos = upto;
@@ -245,39 +302,30 @@ PTV_HD void warp_task(Env& env, Feed& feed, Drain& drain, const Window<T, W>& w,
                 drain.flush(env, w, fill_pos, false);
             }
             int nlo = all_done ? row_hi : low;
+            if (nlo > fill_pos && fill_pos < g.ce) nlo = fill_pos;      // rows not swept yet (partial group) stay
             const int hold = drain.hold(fill_pos, g.ce);
             if (nlo > hold) nlo = hold;
             if (nlo > row_lo) row_lo = nlo;
         }
         if (all_done) break;
-        // ---- lanes that wait in front of the last sample: finish them when nobody else can move ----
-        const bool movable = env.any([&](Lane<T>& L, int) { return !L.done && L.i < g.n - 1; });
-        if (!movable) {
-            // every remaining lane sits at row n-1 (which must be in the window)
-            if (row_hi >= g.n) {
-                env.each([&](Lane<T>& L, int lane) { L.template finish_tail<W>(w, lane, g, lam); });
-                env.sync();
-                if (stats) stats->tail++;
-                continue;      // next epoch sweeps the rest and leaves through all_done
-            }
-        }
-        // ---- deadlock: nobody can move, nothing more fits -> retire the lanes that pin the window ----
-        {
-            const bool can_move = env.any([&](Lane<T>& L, int) { return !L.done && L.i < lim; });
-            const bool can_feed = (row_req < g.n) && (row_req + R <= row_lo + W);
-            const bool pending = row_hi < row_req;
-            if (!can_move && !can_feed && !pending && !(row_hi >= g.n)) {
-                env.each([&](Lane<T>& L, int) {
-                    if (!L.done && L.last + 1 == low) { L.done = true; L.retired = true; L.ovf_rec = rec_pack(L.last + 1, L.kind); }
-                });
-                if (stats) stats->retired++;
-            } else if (!can_move && !can_feed && !pending && row_hi >= g.n) {
-                // the fiber end is in the window but a lane's open segment started before the window could hold it together
-                // with row n-1: cannot happen (row_lo <= last+1 always), kept as a guard against an endless loop
-                env.each([&](Lane<T>& L, int) { if (!L.done && L.i >= g.n - 1) { /* handled by finish_tail above */ } });
-            }
-        }
         if (stats) stats->epochs = epoch + 1;
+        if (niter > 0) continue;
+        // ---- nothing could run.  Lanes that wait in front of the last sample: finish them once it is in the window ----
+        const bool movable = env.any([&](Lane<T>& L, int) { return !L.done && L.i < g.n - 1; });
+        if (!movable && row_hi >= g.n) {
+            env.each([&](Lane<T>& L, int lane) { L.template finish_tail<W>(w, lane, g, lam); });
+            env.sync();
+            if (stats) stats->tail++;
+            continue;          // the next epoch sweeps the rest and leaves through all_done
+        }
+        // ---- stuck: nothing pending, nothing more fits -> retire the lanes that pin the window ----
+        const bool can_feed = (row_req < g.n) && (row_req + R <= row_lo + W) && (row_req - row_hi < Feed::MAXQ * R);
+        if (row_hi >= row_req && !can_feed) {
+            env.each([&](Lane<T>& L, int) {
+                if (!L.done && L.last + 1 == low) { L.done = true; L.retired = true; L.ovf_rec = rec_pack(L.last + 1, L.kind); }
+            });
+            if (stats) stats->retired++;
+        }
     }
     drain.flush(env, w, fill_pos, true);
 }

@@ -17,6 +17,9 @@ template <typename T> struct HostEnv {
     template <class F> int rmax(F f) { int m = f(L[0], 0); for (int l = 1; l < LANES; l++) { int v = f(L[l], l); if (v > m) m = v; } return m; }
     template <class F> bool any(F f) { for (int l = 0; l < LANES; l++) if (f(L[l], l)) return true; return false; }
     void sync() {}
+    template <int W> void scan(Lane<T>& L, const Window<T, W>& w, int lane, const TaskGeom& g, const T* rcp, T lam2, bool ph1, int niter) {
+        if (ph1) L.template run<true, W>(w, lane, g, rcp, lam2, niter); else L.template run<false, W>(w, lane, g, rcp, lam2, niter);
+    }
 };
 
 // fused input / output arithmetic of a pass (kernels_lane.cu has the same three forms)
@@ -40,6 +43,7 @@ template <typename T> struct Fibers {          // 32 adjacent fibers of a group
 
 template <typename T, int W, int RT> struct HostFeed {
     static constexpr int R = RT;
+    static constexpr int MAXQ = 2;
     const Window<T, W>* w; const Op<T>* op; const Fibers<T>* fb; int n; long long* rows_fed;
     template <class Env> void request(Env&, int row0) {
         for (int r = row0; r < row0 + R && r < n; r++)
@@ -52,7 +56,9 @@ template <typename T, int W, int RT> struct HostFeed {
 // direct drain: every swept row goes straight out (the strided pass of the kernel)
 template <typename T, int W> struct HostDrainDirect {
     const Op<T>* op; const Fibers<T>* fb;
-    void row(const Window<T, W>&, int r, int lane, T x, bool valid) { if (valid) op->out(fb->base[lane] + (long long)r * fb->stride, x); }
+    void rows8(const Window<T, W>&, int r0, int cnt, int lane, const T* xs, bool valid) {
+        if (valid) for (int u = 0; u < cnt; u++) op->out(fb->base[lane] + (long long)(r0 + u) * fb->stride, xs[u]);
+    }
     template <class Env> void flush(Env&, const Window<T, W>&, int, bool) {}
     int hold(int, int) const { return 0x3fffffff; }
 };
@@ -60,7 +66,7 @@ template <typename T, int W> struct HostDrainDirect {
 // which transposes a box through a staging tile and stores it with TMA); the window may not slide past an unstored box
 template <typename T, int W, int BOX> struct HostDrainBoxed {
     const Op<T>* op; const Fibers<T>* fb; int stored; int ce;
-    void row(const Window<T, W>& w, int r, int lane, T x, bool) { w.st(r, lane, x); }
+    void rows8(const Window<T, W>& w, int r0, int cnt, int lane, const T* xs, bool) { for (int u = 0; u < cnt; u++) w.st(r0 + u, lane, xs[u]); }
     template <class Env> void flush(Env&, const Window<T, W>& w, int upto, bool final) {
         while (stored + BOX <= upto || (final && stored < upto)) {
             const int b1 = stored + BOX < upto ? stored + BOX : upto;
@@ -82,7 +88,8 @@ static int run_all(int opkind, const T* A, const T* B, const T* C, T* X, long lo
     ChunkPlan pl; pl.n = len; pl.halo = halo;
     if (clen <= 0 || clen >= len) { pl.clen = len; pl.nchunks = 1; } else { pl.clen = clen; pl.nchunks = (len + clen - 1) / clen; }
     std::vector<T> win((size_t)W * LANES), rcp(W + 2);
-    std::vector<uint8_t> flg((size_t)W * LANES);
+    std::vector<unsigned long long> flg8((Window<T, W>::flag_bytes() + 7) / 8 + 1);
+    uint8_t* flgp = reinterpret_cast<uint8_t*>(flg8.data());
     for (int k = 1; k < W + 2; k++) rcp[k] = T(1) / T(k);
     const long long slabs = inc > 1 ? nf / inc : 1, per_slab = inc > 1 ? inc : nf;
     const long long gps = (per_slab + LANES - 1) / LANES;
@@ -98,13 +105,13 @@ static int run_all(int opkind, const T* A, const T* B, const T* C, T* X, long lo
             }
             for (int c = 0; c < pl.nchunks; c++) {
                 const TaskGeom g = pl.geom(c);
-                Window<T, W> w{win.data(), flg.data()};
-                memset(flg.data(), 0, flg.size());
+                Window<T, W> w{win.data(), flgp};
+                memset(flgp, 0, Window<T, W>::flag_bytes());
                 HostEnv<T> env;
                 for (int l = 0; l < LANES; l++) env.L[l].init(g, lam, fb.valid[l]);
                 long long fed = 0;
                 HostFeed<T, W, RT> feed{&w, &op, &fb, len, &fed};
-                TaskStats ts{0, 0, 0};
+                TaskStats ts{0, 0, 0, 0};
                 if (boxed) {
                     HostDrainBoxed<T, W, 16> drain{&op, &fb, g.cs, g.ce};
                     warp_task<T, W, TITER>(env, feed, drain, w, rcp.data(), g, lam, TITER + RT, &ts);
@@ -117,7 +124,7 @@ static int run_all(int opkind, const T* A, const T* B, const T* C, T* X, long lo
                     rovf[(size_t)c * LANES + l] = env.L[l].retired ? env.L[l].ovf_rec : REC_NONE;
                     if (env.L[l].retired) es->retired_lanes++;
                 }
-                es->tasks++; es->epochs += ts.epochs; es->retired_events += ts.retired; es->tails += ts.tail; es->rows_fed += fed;
+                es->tasks++; es->steps_max += ts.iters; es->epochs += ts.epochs; es->retired_events += ts.retired; es->tails += ts.tail; es->rows_fed += fed;
             }
             for (int l = 0; l < LANES; l++) {
                 if (!fb.valid[l]) continue;
