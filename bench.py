@@ -204,7 +204,7 @@ def main():
     launches_timed_region = int(sum(kl[i] for i in range(3)))
     # ---- per-kernel timing for the roofline: K more steps with CUDA events around EVERY launch, on the serial schedule
     #      (engine 'chunked': same kernels, no stream overlap) so that a launch's duration is the kernel's own ----
-    ptv.set_engine("chunked" if args.engine == "auto" else args.engine)
+    ptv.set_engine("lane" if args.engine == "auto" else args.engine)
     lib.proxtv_profile_reset(); lib.proxtv_profile_enable(1)
     for _ in range(args.steps):
         solve()

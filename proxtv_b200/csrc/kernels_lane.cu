@@ -31,6 +31,13 @@ __device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
                  : "=r"(ok) : "r"(s32(bar)), "r"(parity) : "memory");
     return ok != 0;
 }
+// non-blocking poll (try_wait may suspend the thread for a while before it reports failure; test_wait never does)
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(s32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
@@ -41,6 +48,7 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void*
                  ::"l"(map), "r"(s32(src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 
 // ---------------------------------------------------------------- kernel arguments
@@ -136,8 +144,9 @@ __device__ __forceinline__ void run_dev(Lane<T>& L, const DevWin<T, W> dw, const
         const T cl = Z * r, ch = (Z + lam2) * r;
         const bool first = (ka == ROWB);
         const bool can = !first & (la < cea);
-        const bool cbk = can & (lo > ch);
-        const bool fbk = can & !cbk & (hi < cl);
+        const bool craw = lo > ch, fraw = hi < cl;          // both compares issue back to back (neither waits for the other)
+        const bool cbk = can & craw;
+        const bool fbk = can & !craw & fraw;
         const bool brk = cbk | fbk;
         const int ea = cbk ? bloa : bhia;
         const T v = cbk ? lo : hi;
@@ -204,7 +213,7 @@ template <typename T, int W, int RT, int OP> struct FeedStrided {
         const uint32_t parity = (uint32_t)((q / NBAR) & 1);
         // the decision must be warp-uniform (it steers the task's control flow), and every lane needs the acquire of its own
         // successful wait before it reads the tile: all lanes poll, the vote decides
-        bool ok = __all_sync(0xffffffffu, mbar_try(b, parity));
+        bool ok = __all_sync(0xffffffffu, mbar_test(b, parity));
         if (!ok && !block) return false;
         while (!ok) ok = __all_sync(0xffffffffu, mbar_try(b, parity));
         if (OP != LOP_PLAIN) {
@@ -220,33 +229,135 @@ template <typename T, int W, int RT, int OP> struct FeedStrided {
 
 template <typename T, int W, int OP> struct DrainStrided {
     const T* __restrict__ B; const T* __restrict__ C; T* __restrict__ X; long long gbase, stride;     // gbase includes the lane
+    // operands of the fused Douglas-Rachford drain for the group of rows that will be swept next, fetched one epoch ahead
+    // (they were read by this warp's feeder a window ago: L2 hits, whose latency would otherwise be exposed once per epoch)
+    T pb[8], pc[8]; int pf_row;
+    __device__ __forceinline__ void prefetch(int r0, int ce, bool valid) {
+        if (OP != LOP_DR_B || !valid || r0 + 8 > ce || r0 == pf_row) return;
+        const long long g0 = gbase + (long long)r0 * stride;
+        const T* __restrict__ qb = B + g0; const T* __restrict__ qc = C + g0;
+#pragma unroll
+        for (int u = 0; u < 8; u++) { pb[u] = __ldg(qb); pc[u] = __ldg(qc); qb += stride; qc += stride; }
+        pf_row = r0;
+    }
     __device__ __forceinline__ void rows8(const Window<T, W>&, int r0, int cnt, int, const T* xs, bool valid) {
         if (!valid) return;
         const long long g0 = gbase + (long long)r0 * stride;
-        if (OP == LOP_DR_B) {
-            T b[8], c[8];
+        T* __restrict__ px = X + g0;
+        if (cnt == 8) {                                  // whole group: one pointer, bumped by the row stride
+            if (OP == LOP_DR_B) {
+                if (r0 != pf_row) {
+                    const T* __restrict__ qb = B + g0; const T* __restrict__ qc = C + g0;
 #pragma unroll
-            for (int u = 0; u < 8; u++) if (u < cnt) { b[u] = __ldg(B + g0 + u * stride); c[u] = __ldg(C + g0 + u * stride); }
+                    for (int u = 0; u < 8; u++) { pb[u] = __ldg(qb); pc[u] = __ldg(qc); qb += stride; qc += stride; }
+                }
 #pragma unroll
-            for (int u = 0; u < 8; u++) if (u < cnt) X[g0 + u * stride] = PassOp<T, OP>::out(xs[u], b[u], c[u]);
-        } else {
+                for (int u = 0; u < 8; u++) { *px = PassOp<T, OP>::out(xs[u], pb[u], pc[u]); px += stride; }
+                pf_row = -1;
+            } else {
 #pragma unroll
-            for (int u = 0; u < 8; u++) if (u < cnt) X[g0 + u * stride] = xs[u];
+                for (int u = 0; u < 8; u++) { *px = xs[u]; px += stride; }
+            }
+            return;
+        }
+        for (int u = 0; u < cnt; u++) {                  // the last, partial group of a fiber
+            const long long g = g0 + u * stride;
+            X[g] = OP == LOP_DR_B ? PassOp<T, OP>::out(xs[u], B[g], C[g]) : xs[u];
         }
     }
     __device__ __forceinline__ void flush(DevEnv<T, W>&, const Window<T, W>&, int, bool) {}
     __device__ __forceinline__ int hold(int, int) const { return 0x3fffffff; }
 };
 
+// ---------------------------------------------------------------- CONTIG layout: feed and drain
+// Fibers are contiguous in memory (element stride 1), 32 consecutive fibers form a group.  A TMA box = BR rows x 32 fibers with
+// BR * sizeof(T) = 128 bytes, so that every fiber contributes one full 128-byte line; it is written fiber-major with the 128-byte
+// hardware swizzle (16-byte chunk c of fiber j sits at chunk c ^ (j & 7)) straight into the window region of those BR rows (4 KB,
+// 1 KB aligned) and transposed IN PLACE through registers: lane j reads its own fiber's 128 bytes (8 conflict-free 16-byte loads),
+// the warp synchronises, lane j writes its window column.  On the way out the sweep hands each lane 8 consecutive results of its
+// fiber; they go straight into a swizzled staging box (conflict-free 16-byte stores) that leaves with one TMA store per BR rows.
+template <typename T> struct Vec16 { };
+template <> struct Vec16<double> {
+    static __device__ __forceinline__ void ld(uint32_t a, double* v) { asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v[0]), "=d"(v[1]) : "r"(a)); }
+    static __device__ __forceinline__ void st(uint32_t a, const double* v) { asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(v[0]), "d"(v[1]) : "memory"); }
+};
+template <> struct Vec16<float> {
+    static __device__ __forceinline__ void ld(uint32_t a, float* v) { asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(a)); }
+    static __device__ __forceinline__ void st(uint32_t a, const float* v) { asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory"); }
+};
+
+template <typename T, int W> struct FeedContig {
+    static constexpr int R = 128 / (int)sizeof(T);          // rows per box: 16 (f64) / 32 (f32)
+    static constexpr int MAXQ = W / R;
+    static constexpr int NBAR = W / R;
+    static constexpr int EPC = 16 / (int)sizeof(T);          // elements per 16-byte chunk
+    const LaneArgs<T>* a; T* win; uint64_t* bar; int f0, q0, lane;
+    __device__ __forceinline__ void request(DevEnv<T, W>&, int row0) {
+        __syncwarp();
+        if (lane == 0) {
+            fence_proxy_async();
+            const int q = row0 / R - q0;
+            uint64_t* b = bar + (q % NBAR);
+            mbar_expect_tx(b, 4096u);
+            tma_load_3d(win + ((row0 & (W - 1)) << 5), &a->tmA, row0, f0, 0, b);
+        }
+    }
+    __device__ __forceinline__ bool landed(DevEnv<T, W>&, int row0, bool block) {
+        const int q = row0 / R - q0;
+        uint64_t* b = bar + (q % NBAR);
+        const uint32_t parity = (uint32_t)((q / NBAR) & 1);
+        bool ok = __all_sync(0xffffffffu, mbar_test(b, parity));
+        if (!ok && !block) return false;
+        while (!ok) ok = __all_sync(0xffffffffu, mbar_try(b, parity));
+        // in-place transpose of the 4 KB region: [fiber][row] swizzled  ->  [row][fiber]
+        T* reg = win + ((row0 & (W - 1)) << 5);
+        const uint32_t src = s32(reg) + (uint32_t)lane * 128u;
+        T v[R];
+#pragma unroll
+        for (int c = 0; c < 8; c++) Vec16<T>::ld(src + (uint32_t)((c ^ (lane & 7)) << 4), v + c * EPC);
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < R; i++) reg[i * LANES + lane] = v[i];
+        __syncwarp();
+        return true;
+    }
+};
+
+template <typename T, int W> struct DrainContig {
+    static constexpr int R = 128 / (int)sizeof(T);
+    static constexpr int EPC = 16 / (int)sizeof(T);
+    const LaneArgs<T>* a; T* stg; int f0, lane, ce;
+    // xs: results of rows r0 .. r0+7 of this lane's fiber (r0 % 8 == 0); rows beyond the fiber are clipped by the TMA store
+    __device__ __forceinline__ void rows8(const Window<T, W>&, int r0, int cnt, int, const T* xs, bool) {
+        const int off = r0 & (R - 1);
+        if (off == 0) { if (lane == 0) bulk_wait_read<0>(); __syncwarp(); }      // the previous box has left the staging tile
+        const uint32_t dst = s32(stg) + (uint32_t)lane * 128u;
+        const int c0 = off / EPC;
+#pragma unroll
+        for (int c = 0; c < 8 / EPC; c++) Vec16<T>::st(dst + (uint32_t)(((c0 + c) ^ (lane & 7)) << 4), xs + c * EPC);
+        if (off + 8 == R || r0 + cnt >= ce) {                                  // box complete (or the chunk ends inside it)
+            __syncwarp();
+            if (lane == 0) { fence_proxy_async(); tma_store_3d(&a->tmX, stg, r0 - off, f0, 0); bulk_commit(); }
+        }
+    }
+    __device__ __forceinline__ void prefetch(int, int, bool) {}
+    __device__ __forceinline__ void flush(DevEnv<T, W>&, const Window<T, W>&, int, bool final) {
+        if (final) { if (lane == 0) bulk_wait_all(); __syncwarp(); }            // results are in global memory before the records go out
+    }
+    __device__ __forceinline__ int hold(int, int) const { return 0x3fffffff; }
+};
+
 // ---------------------------------------------------------------- the kernel
-template <typename T, int W, int RT, int OP> struct LaneSmem {
+enum LaneLayout { LAY_STRIDED = 0, LAY_CONTIG = 1 };
+template <typename T, int W, int RT, int OP, int LAY> struct LaneSmem {
     static constexpr int NST = 2;
     static constexpr size_t win_bytes = (size_t)W * LANES * sizeof(T);
-    static constexpr size_t stg_bytes = (OP == LOP_PLAIN) ? 0 : (size_t)2 * NST * RT * LANES * sizeof(T);
+    static constexpr size_t stg_bytes = LAY == LAY_CONTIG ? 4096 : ((OP == LOP_PLAIN) ? 0 : (size_t)2 * NST * RT * LANES * sizeof(T));
     static constexpr size_t flg_bytes = ((size_t)LANES * (W + 8) + 127) / 128 * 128;
     static constexpr size_t bar_bytes = 128;            // W / RT <= 16 barriers
-    static constexpr size_t per_warp = win_bytes + stg_bytes + flg_bytes + bar_bytes;
-    static constexpr size_t rcp_bytes = ((W + 2) * sizeof(T) + 127) / 128 * 128;
+    static constexpr size_t align = LAY == LAY_CONTIG ? 1024 : 128;       // swizzled boxes need 1 KB aligned tiles
+    static constexpr size_t per_warp = (win_bytes + stg_bytes + flg_bytes + bar_bytes + align - 1) / align * align;
+    static constexpr size_t rcp_bytes = ((W + 2) * sizeof(T) + align - 1) / align * align;
 };
 
 // repair: exact sequential continuation in global memory (rare; kept out of line so it does not cost the scan registers)
@@ -266,16 +377,16 @@ __device__ __noinline__ int repair_fiber(const LaneArgs<T>* a, long long fiber, 
                           X[g] = OP == LOP_DR_B ? PassOp<T, OP>::out(v, B[g], C[g]) : v; });
 }
 
-template <typename T, int W, int RT, int TITER, int OP, int NW>
-__global__ void __launch_bounds__(NW * 32) k_lane_strided(const __grid_constant__ LaneArgs<T> a) {
-    using SM = LaneSmem<T, W, RT, OP>;
+template <typename T, int W, int RT, int TITER, int OP, int NW, int LAY>
+__global__ void __launch_bounds__(NW * 32) k_lane(const __grid_constant__ LaneArgs<T> a) {
+    using SM = LaneSmem<T, W, RT, OP, LAY>;
     extern __shared__ __align__(1024) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     T* rcp = reinterpret_cast<T*>(smem);
     unsigned char* wb = smem + SM::rcp_bytes + (size_t)warp * SM::per_warp;
     T* win = reinterpret_cast<T*>(wb);
     T* stB = reinterpret_cast<T*>(wb + SM::win_bytes);
-    T* stC = stB + SM::NST * RT * LANES;
+    T* stC = stB + (LAY == LAY_CONTIG ? 0 : SM::NST * RT * LANES);
     uint8_t* flg = wb + SM::win_bytes + SM::stg_bytes;
     uint64_t* bar = reinterpret_cast<uint64_t*>(wb + SM::win_bytes + SM::stg_bytes + SM::flg_bytes);
 
@@ -297,16 +408,24 @@ __global__ void __launch_bounds__(NW * 32) k_lane_strided(const __grid_constant_
     const int x0 = (int)(group - (long long)z * a.gps) * LANES;
     const TaskGeom g = pl.geom(chunk);
     const bool valid = (long long)x0 + lane < a.per_slab;
-    const long long gbase = (long long)z * a.inc * pl.n + x0 + lane;        // element (row 0) of this lane's fiber
+    // element (row 0) of this lane's fiber, and its element stride
+    const long long gbase = LAY == LAY_CONTIG ? ((long long)x0 + lane) * pl.n : (long long)z * a.inc * pl.n + x0 + lane;
+    const long long gstride = LAY == LAY_CONTIG ? 1 : a.inc;
     const long long nfp = (long long)a.slabs * a.gps * LANES;
     const long long fiber = group * LANES + lane;
 
     DevEnv<T, W> env; env.lane = lane; env.L.init(g, a.lam, valid);
     env.dw.wbase = s32(win); env.dw.lane8 = lane * (uint32_t)sizeof(T); env.dw.flg = s32(flg) + lane * (uint32_t)Window<T, W>::FP; env.dw.rcp = s32(rcp);
     Window<T, W> w{win, flg};
-    FeedStrided<T, W, RT, OP> feed{&a, win, stB, stC, bar, x0, z, g.p0 / RT, lane};
-    DrainStrided<T, W, OP> drain{a.B, a.C, a.X, gbase, a.inc};
-    warp_task<T, W, TITER>(env, feed, drain, w, rcp, g, a.lam, TITER + RT, (TaskStats*)nullptr);
+    if (LAY == LAY_CONTIG) {
+        FeedContig<T, W> feed{&a, win, bar, x0, g.p0 / FeedContig<T, W>::R, lane};
+        DrainContig<T, W> drain{&a, stB, x0, lane, g.ce};
+        warp_task<T, W, TITER>(env, feed, drain, w, rcp, g, a.lam, TITER + TITER / 2 + FeedContig<T, W>::R, (TaskStats*)nullptr);
+    } else {
+        FeedStrided<T, W, RT, OP> feed{&a, win, stB, stC, bar, x0, z, g.p0 / RT, lane};
+        DrainStrided<T, W, OP> drain; drain.B = a.B; drain.C = a.C; drain.X = a.X; drain.gbase = gbase; drain.stride = a.inc; drain.pf_row = -1;
+        warp_task<T, W, TITER>(env, feed, drain, w, rcp, g, a.lam, TITER + TITER / 2 + RT, (TaskStats*)nullptr);
+    }
 
     // ---- chunk records; the last warp of the fiber group to finish verifies (and repairs) its 32 fibers ----
     int* rec = a.rec;
@@ -334,7 +453,7 @@ __global__ void __launch_bounds__(NW * 32) k_lane_strided(const __grid_constant_
         }
     }
     if (bad) {
-        const int n = repair_fiber<T, OP>(&a, fiber, gbase, a.inc, nfp);
+        const int n = repair_fiber<T, OP>(&a, fiber, gbase, gstride, nfp);
         if (n) atomicAdd(a.stats, (unsigned long long)n);
     }
 }
@@ -378,11 +497,11 @@ long long lane_scratch_bytes(long long nf, int len) {
     return 3 * maxchunks * nfp * 4 + (nfp / 32 + 128) * 4 + 64;
 }
 
-// launch one variant; with nchunks <= 0 only report how many warp tasks the device can hold at once
-template <typename T, int W, int RT, int TITER, int OP, int NW>
-static cudaError_t launch_strided_v(LaneArgs<T>& a, cudaStream_t st, int* slots) {
-    using SM = LaneSmem<T, W, RT, OP>;
-    auto kern = k_lane_strided<T, W, RT, TITER, OP, NW>;
+// launch one instantiation; with `slots` only report how many warp tasks the device can hold at once
+template <typename T, int W, int RT, int TITER, int OP, int NW, int LAY>
+static cudaError_t launch_v(LaneArgs<T>& a, cudaStream_t st, int* slots) {
+    using SM = LaneSmem<T, W, RT, OP, LAY>;
+    auto kern = k_lane<T, W, RT, TITER, OP, NW, LAY>;
     const size_t smem = SM::rcp_bytes + (size_t)NW * SM::per_warp;
     static int s_slots = 0;                      // per instantiation: resident warps on the current device
     if (!s_slots) {
@@ -401,47 +520,65 @@ static cudaError_t launch_strided_v(LaneArgs<T>& a, cudaStream_t st, int* slots)
     return cudaGetLastError();
 }
 
-template <typename T, int OP>
-static cudaError_t launch_strided_variant(int variant, LaneArgs<T>& a, cudaStream_t st, int* slots) {
+// tuning variants (window rows, steps per epoch, warps per CTA); 0 is the default
+template <typename T, int OP, int LAY>
+static cudaError_t launch_variant(int variant, LaneArgs<T>& a, cudaStream_t st, int* slots) {
     switch (variant) {
-        case 1: return launch_strided_v<T, 32, 8, 8, OP, 4>(a, st, slots);
-        case 2: return launch_strided_v<T, 64, 8, 8, OP, 4>(a, st, slots);
-        case 3: return launch_strided_v<T, 64, 8, 16, OP, 2>(a, st, slots);
-        case 4: return launch_strided_v<T, 64, 8, 16, OP, 1>(a, st, slots);
-        case 5: return launch_strided_v<T, 32, 8, 8, OP, 1>(a, st, slots);
-        case 6: return launch_strided_v<T, 32, 8, 16, OP, 1>(a, st, slots);
-        default: return launch_strided_v<T, 64, 8, 16, OP, 4>(a, st, slots);
+        case 1: return launch_v<T, 64, 8, 16, OP, 4, LAY>(a, st, slots);
+        case 2: return launch_v<T, 32, 8, 8, OP, 1, LAY>(a, st, slots);
+        case 3: return launch_v<T, 64, 8, 24, OP, 1, LAY>(a, st, slots);
+        case 4: return launch_v<T, 64, 8, 8, OP, 1, LAY>(a, st, slots);
+        case 5: return launch_v<T, 128, 8, 16, OP, 1, LAY>(a, st, slots);
+        case 6: return launch_v<T, 128, 8, 32, OP, 1, LAY>(a, st, slots);
+        default: return launch_v<T, 64, 8, 16, OP, 1, LAY>(a, st, slots);
     }
 }
-
-// x = prox over fibers with element stride inc > 1 (fibers adjacent in memory).  scratch: lane_scratch_bytes(), zero-initialised
-// once (the group counters reset themselves).  Returns cudaErrorInvalidConfiguration when the shape does not suit TMA tiling.
 template <typename T>
-cudaError_t lane_prox_strided(int op, const T* A, const T* B, const T* C, T* X, long long nf, int len, long long inc, T lam, void* scratch,
-                              cudaStream_t st) {
-    if (inc <= 1 || nf % inc != 0) return cudaErrorInvalidConfiguration;
-    if ((inc * sizeof(T)) % 16 != 0 || ((uintptr_t)A & 15) || (B && ((uintptr_t)B & 15)) || (C && ((uintptr_t)C & 15)))
+static cudaError_t launch_any(int lay, int op, int variant, LaneArgs<T>& a, cudaStream_t st, int* slots) {
+    if (lay == LAY_CONTIG) return launch_variant<T, LOP_PLAIN, LAY_CONTIG>(variant, a, st, slots);
+    return op == LOP_PLAIN ? launch_variant<T, LOP_PLAIN, LAY_STRIDED>(variant, a, st, slots)
+         : op == LOP_DR_B  ? launch_variant<T, LOP_DR_B, LAY_STRIDED>(variant, a, st, slots)
+                           : launch_variant<T, LOP_DR_B_FINAL, LAY_STRIDED>(variant, a, st, slots);
+}
+
+// x = prox_{lam TV}(in) over the fibers (nf, len, inc) of an array (the reference's slicing rule, src/TVNDopt.cpp:184-188).
+//   inc > 1: STRIDED layout, any op (in / out arithmetic of PassOp);   inc == 1: CONTIG layout, plain op only.
+// scratch: lane_scratch() (records, group counters).  Returns cudaErrorInvalidConfiguration when the shape does not suit TMA
+// tiling (unaligned base, row pitch not a multiple of 16 bytes, tiny fibers) -- the caller then uses the chunked engine.
+template <typename T>
+cudaError_t lane_prox(int op, const T* A, const T* B, const T* C, T* X, long long nf, int len, long long inc, T lam, void* scratch,
+                      cudaStream_t st) {
+    if (nf <= 0 || len < 2 || !(lam > T(0))) return cudaErrorInvalidConfiguration;
+    const int lay = inc == 1 ? LAY_CONTIG : LAY_STRIDED;
+    if (lay == LAY_CONTIG && op != LOP_PLAIN) return cudaErrorInvalidConfiguration;
+    if (lay == LAY_STRIDED && nf % inc != 0) return cudaErrorInvalidConfiguration;
+    const long long pitch = (lay == LAY_CONTIG ? (long long)len : inc) * (long long)sizeof(T);
+    if (pitch % 16 != 0 || ((uintptr_t)A & 15) || ((uintptr_t)X & 15) || (B && ((uintptr_t)B & 15)) || (C && ((uintptr_t)C & 15)))
         return cudaErrorInvalidConfiguration;
-    if (len < 2 || !(lam > T(0))) return cudaErrorInvalidConfiguration;
     LaneArgs<T> a;
     memset(&a, 0, sizeof(a));
-    const long long slabs = nf / inc;
-    if (slabs > 0x7fffffff) return cudaErrorInvalidConfiguration;
-    const int RT = 8;
-    if (!make_map<T>(&a.tmA, A, inc, len, slabs, LANES, RT, CU_TENSOR_MAP_SWIZZLE_NONE)) return cudaErrorInvalidConfiguration;
-    if (op != LOP_PLAIN) {
-        if (!make_map<T>(&a.tmB, B, inc, len, slabs, LANES, RT, CU_TENSOR_MAP_SWIZZLE_NONE)) return cudaErrorInvalidConfiguration;
-        if (!make_map<T>(&a.tmC, C, inc, len, slabs, LANES, RT, CU_TENSOR_MAP_SWIZZLE_NONE)) return cudaErrorInvalidConfiguration;
+    a.A = A; a.B = B; a.C = C; a.X = X; a.lam = lam;
+    const int BR = 128 / (int)sizeof(T);
+    if (lay == LAY_CONTIG) {
+        if (nf > 0x7fffffff) return cudaErrorInvalidConfiguration;
+        if (!make_map<T>(&a.tmA, A, len, nf, 1, BR, LANES, CU_TENSOR_MAP_SWIZZLE_128B)) return cudaErrorInvalidConfiguration;
+        if (!make_map<T>(&a.tmX, X, len, nf, 1, BR, LANES, CU_TENSOR_MAP_SWIZZLE_128B)) return cudaErrorInvalidConfiguration;
+        a.inc = 1; a.per_slab = nf; a.slabs = 1; a.gps = (int)((nf + LANES - 1) / LANES);
+    } else {
+        const long long slabs = nf / inc;
+        if (slabs > 0x7fffffff) return cudaErrorInvalidConfiguration;
+        if (!make_map<T>(&a.tmA, A, inc, len, slabs, LANES, 8, CU_TENSOR_MAP_SWIZZLE_NONE)) return cudaErrorInvalidConfiguration;
+        if (op != LOP_PLAIN) {
+            if (!make_map<T>(&a.tmB, B, inc, len, slabs, LANES, 8, CU_TENSOR_MAP_SWIZZLE_NONE)) return cudaErrorInvalidConfiguration;
+            if (!make_map<T>(&a.tmC, C, inc, len, slabs, LANES, 8, CU_TENSOR_MAP_SWIZZLE_NONE)) return cudaErrorInvalidConfiguration;
+        }
+        a.inc = inc; a.per_slab = inc; a.slabs = (int)slabs; a.gps = (int)((inc + LANES - 1) / LANES);
     }
-    a.A = A; a.B = B; a.C = C; a.X = X; a.inc = inc; a.per_slab = inc; a.slabs = (int)slabs; a.gps = (int)((inc + LANES - 1) / LANES);
-    a.lam = lam;
-    // chunking: whole fibers when there are enough of them to fill the machine; else as many chunks (multiples of 16 rows) as
-    // there are resident warp slots, so that the whole pass is ONE wave of warp tasks
-    const long long groups = slabs * a.gps;
+    // chunking: whole fibers when there are enough of them to fill the machine; else as many chunks as there are resident warp
+    // slots, so that the whole pass is ONE wave of warp tasks.  Chunk boundaries are multiples of 32 rows (TMA boxes).
+    const long long groups = (long long)a.slabs * a.gps;
     int slots = 0;
-    cudaError_t e = op == LOP_PLAIN ? launch_strided_variant<T, LOP_PLAIN>(g_tune.variant, a, st, &slots)
-                  : op == LOP_DR_B ? launch_strided_variant<T, LOP_DR_B>(g_tune.variant, a, st, &slots)
-                                   : launch_strided_variant<T, LOP_DR_B_FINAL>(g_tune.variant, a, st, &slots);
+    cudaError_t e = launch_any<T>(lay, op, g_tune.variant, a, st, &slots);
     if (e != cudaSuccess) return e;
     int clen = g_tune.clen, halo = g_tune.halo;
     if (clen <= 0) {
@@ -449,7 +586,7 @@ cudaError_t lane_prox_strided(int op, const T* A, const T* B, const T* C, T* X, 
         clen = (int)((len + c - 1) / c);
         if (clen < 64) clen = 64;
     }
-    clen = (clen + 15) / 16 * 16; halo = (halo + 7) / 8 * 8;
+    clen = (clen + 31) / 32 * 32; halo = (halo + 31) / 32 * 32;
     a.plan.n = len; a.plan.halo = halo;
     if (clen >= len) { a.plan.clen = len; a.plan.nchunks = 1; } else { a.plan.clen = clen; a.plan.nchunks = (len + clen - 1) / clen; }
     if (a.plan.nchunks > len / 64 + 2) return cudaErrorInvalidConfiguration;
@@ -458,9 +595,16 @@ cudaError_t lane_prox_strided(int op, const T* A, const T* B, const T* C, T* X, 
     a.group_count = (int*)((char*)scratch + 64);
     a.rec = a.group_count + ((groups + 63) / 64) * 64;
     a.ntasks = groups * a.plan.nchunks;
-    return op == LOP_PLAIN ? launch_strided_variant<T, LOP_PLAIN>(g_tune.variant, a, st, nullptr)
-         : op == LOP_DR_B ? launch_strided_variant<T, LOP_DR_B>(g_tune.variant, a, st, nullptr)
-                          : launch_strided_variant<T, LOP_DR_B_FINAL>(g_tune.variant, a, st, nullptr);
+    return launch_any<T>(lay, op, g_tune.variant, a, st, nullptr);
+}
+
+bool lane_shape_ok(long long nf, int len, long long inc, size_t elem, const void* const* ptrs, int nptrs) {
+    if (nf <= 0 || len < 2) return false;
+    if (inc > 1 && nf % inc != 0) return false;
+    const long long pitch = (inc == 1 ? (long long)len : inc) * (long long)elem;
+    if (pitch % 16 != 0) return false;
+    for (int i = 0; i < nptrs; i++) if (ptrs[i] && ((uintptr_t)ptrs[i] & 15)) return false;
+    return encode_fn() != nullptr;
 }
 
 // per-device scratch for the records (grow-only, zero-initialised: the group counters must start at 0 and reset themselves)
@@ -486,9 +630,7 @@ unsigned long long lane_read_stats(int reset) {
     return v;
 }
 
-template cudaError_t lane_prox_strided<double>(int, const double*, const double*, const double*, double*, long long, int, long long, double,
-                                               void*, cudaStream_t);
-template cudaError_t lane_prox_strided<float>(int, const float*, const float*, const float*, float*, long long, int, long long, float, void*,
-                                              cudaStream_t);
+template cudaError_t lane_prox<double>(int, const double*, const double*, const double*, double*, long long, int, long long, double, void*, cudaStream_t);
+template cudaError_t lane_prox<float>(int, const float*, const float*, const float*, float*, long long, int, long long, float, void*, cudaStream_t);
 
 }  // namespace ptvl

@@ -220,7 +220,7 @@ template <typename T> struct Lane {
 // brings rows into the window, Drain takes finished rows.
 //   Env:   each(f(Lane&, lane)) ; rmin(f) ; rmax(f) ; any(f) ; sync() ; scan(L, w, lane, g, rcp, lam2, ph1, niter)
 //   Feed:  R rows per tile (8) ; MAXQ tiles that may be outstanding ; request(env, row0) ; bool landed(env, row0, block)
-//   Drain: rows8(w, r0, cnt, lane, xs, valid) inside each() for every aligned group of 8 owned rows, in order ; flush(env, w,
+//   Drain: prefetch(r0, ce, valid) ; rows8(w, r0, cnt, lane, xs, valid) inside each() for every aligned group of 8 owned rows, in order ; flush(env, w,
 //          upto, final) ; hold(): first row the window still has to keep for it
 struct TaskStats { int epochs, retired, tail, iters; };
 
@@ -236,47 +236,13 @@ PTV_HD void warp_task(Env& env, Feed& feed, Drain& drain, const Window<T, W>& w,
     int fill_pos = g.cs;              // next owned row to sweep (multiple of 8)
     bool ph1 = true;                  // some lane has not emitted its first owned segment yet
     const int BIG = 0x3fffffff;
+    // One epoch = sweep what is final, slide the window, ask for more rows, take over what has landed, run as many scan steps as
+    // every participating lane can take without a bounds check.  Three warp reductions and one barrier poll in the steady state.
     for (int epoch = 0;; epoch++) {
-        // ---- feed: keep `ahead` rows in front of the fastest lane, never more than the window holds ----
         const int maxi = env.rmax([&](Lane<T>& L, int) { return L.done ? -1 : L.i; });
-        {
-            int want = maxi + ahead;
-            const int cap = g.ce + R;                                    // beyond the chunk only on demand (overrun of the last segment)
-            if (want > cap) want = (maxi + DMIN + 1 > cap) ? maxi + DMIN + 1 : cap;
-            if (want > g.n) want = g.n;
-            while (row_req < want && row_req + R <= row_lo + W && row_req - row_hi < Feed::MAXQ * R) { feed.request(env, row_req); row_req += R; }
-        }
-        int lim, niter;
-        for (;;) {
-            lim = row_hi < g.n - 1 ? row_hi : g.n - 1;
-            // iterations every participating lane can run without reaching the frontier
-            const int dmin = env.rmin([&](Lane<T>& L, int) { const int d = lim - L.i; return (L.done || d < DMIN) ? BIG : d; });
-            niter = dmin < TITER ? dmin : TITER;
-            if (dmin == BIG) {           // nobody has DMIN rows in front of it: take what there is
-                const int d1 = env.rmin([&](Lane<T>& L, int) { const int d = lim - L.i; return (L.done || d < 1) ? BIG : d; });
-                niter = d1 == BIG ? 0 : (d1 < TITER ? d1 : TITER);
-            }
-            // take over tiles that have landed; wait for one only if nothing can run
-            if (row_hi < row_req && feed.landed(env, row_hi, niter == 0)) { row_hi += R; continue; }
-            break;
-        }
-        // ---- scan ----
-        if (niter > 0) {
-            const int lim_ = lim, niter_ = niter; const bool ph1_ = ph1;
-            env.each([&](Lane<T>& L, int lane) {
-                const int d = lim_ - L.i;
-                if (!L.done && d >= niter_) {
-                    env.scan(L, w, lane, g, rcp, lam2, ph1_, niter_);      // Lane::run, or the kernel's equivalent device form
-                    L.settle(g);
-                }
-            });
-            env.sync();
-            if (ph1) ph1 = env.any([&](Lane<T>& L, int) { return !L.done && L.in_rec == REC_NONE; });
-            if (stats) stats->iters += niter;
-        }
-        // ---- sweep finished rows (aligned groups of 8), slide the window ----
         const int low = env.rmin([&](Lane<T>& L, int) { return L.done ? BIG : L.last + 1; });
         const bool all_done = (low == BIG);
+        // ---- sweep finished rows (aligned groups of 8), slide the window ----
         {
             int upto = low < g.ce ? low : g.ce;
             if (upto > row_hi) upto = row_hi;          // only retired lanes leave owned rows outside the window (repaired later)
@@ -288,9 +254,12 @@ PTV_HD void warp_task(Env& env, Feed& feed, Drain& drain, const Window<T, W>& w,
                         T xs[8];
                         const int cnt = upto - r < 8 ? upto - r : 8;
                         const unsigned long long fl = w.flags8(r, lane);
+                        T t[8];
+#pragma unroll
+                        for (int u = 0; u < 8; u++) t[u] = w.ld(r + u, lane);       // unconditional: straight-line, loads overlap
 #pragma unroll
                         for (int u = 0; u < 8; u++) {
-                            if ((fl >> (8 * u)) & 0xffull) L.xcur = w.ld(r + u, lane);
+                            L.xcur = ((fl >> (8 * u)) & 0xffull) ? t[u] : L.xcur;
                             xs[u] = L.xcur;
                         }
                         w.clear8(r, lane);
@@ -309,22 +278,55 @@ PTV_HD void warp_task(Env& env, Feed& feed, Drain& drain, const Window<T, W>& w,
         }
         if (all_done) break;
         if (stats) stats->epochs = epoch + 1;
-        if (niter > 0) continue;
-        // ---- nothing could run.  Lanes that wait in front of the last sample: finish them once it is in the window ----
-        const bool movable = env.any([&](Lane<T>& L, int) { return !L.done && L.i < g.n - 1; });
-        if (!movable && row_hi >= g.n) {
-            env.each([&](Lane<T>& L, int lane) { L.template finish_tail<W>(w, lane, g, lam); });
-            env.sync();
-            if (stats) stats->tail++;
-            continue;          // the next epoch sweeps the rest and leaves through all_done
+        env.each([&](Lane<T>& L, int) { drain.prefetch(fill_pos, g.ce, L.valid); });     // operands of the next group to be swept
+        // ---- feed: keep `ahead` rows in front of the fastest lane, never more than the window holds ----
+        {
+            int want = maxi + ahead;
+            const int cap = g.ce + R;                                    // beyond the chunk only on demand (overrun of the last segment)
+            if (want > cap) want = (maxi + DMIN + 1 > cap) ? maxi + DMIN + 1 : cap;
+            if (want > g.n) want = g.n;
+            while (row_req < want && row_req + R <= row_lo + W && row_req - row_hi < Feed::MAXQ * R) { feed.request(env, row_req); row_req += R; }
+            while (row_hi < row_req && feed.landed(env, row_hi, false)) row_hi += R;      // take over what has landed
         }
-        // ---- stuck: nothing pending, nothing more fits -> retire the lanes that pin the window ----
-        const bool can_feed = (row_req < g.n) && (row_req + R <= row_lo + W) && (row_req - row_hi < Feed::MAXQ * R);
-        if (row_hi >= row_req && !can_feed) {
-            env.each([&](Lane<T>& L, int) {
-                if (!L.done && L.last + 1 == low) { L.done = true; L.retired = true; L.ovf_rec = rec_pack(L.last + 1, L.kind); }
+        // ---- how many steps can every participating lane take? ----
+        const int lim = row_hi < g.n - 1 ? row_hi : g.n - 1;
+        int niter = env.rmin([&](Lane<T>& L, int) { const int d = lim - L.i; return (L.done || d < DMIN) ? BIG : d; });
+        if (niter == BIG) {              // nobody has DMIN rows in front of it: take what there is
+            niter = env.rmin([&](Lane<T>& L, int) { const int d = lim - L.i; return (L.done || d < 1) ? BIG : d; });
+            if (niter == BIG) {          // nobody can move
+                if (row_hi < row_req) { feed.landed(env, row_hi, true); row_hi += R; continue; }        // wait for the next tile
+                // lanes that wait in front of the fiber's last sample: finish them once it is in the window
+                const bool movable = env.any([&](Lane<T>& L, int) { return !L.done && L.i < g.n - 1; });
+                if (!movable && row_hi >= g.n) {
+                    env.each([&](Lane<T>& L, int lane) { L.template finish_tail<W>(w, lane, g, lam); });
+                    env.sync();
+                    if (stats) stats->tail++;
+                    continue;
+                }
+                // stuck: nothing pending, nothing more fits -> retire the lanes that pin the window
+                const bool can_feed = (row_req < g.n) && (row_req + R <= row_lo + W) && (row_req - row_hi < Feed::MAXQ * R);
+                if (!can_feed) {
+                    env.each([&](Lane<T>& L, int) {
+                        if (!L.done && L.last + 1 == low) { L.done = true; L.retired = true; L.ovf_rec = rec_pack(L.last + 1, L.kind); }
+                    });
+                    if (stats) stats->retired++;
+                }
+                continue;
+            }
+        }
+        if (niter > TITER) niter = TITER;
+        // ---- scan ----
+        {
+            const int lim_ = lim, niter_ = niter; const bool ph1_ = ph1;
+            env.each([&](Lane<T>& L, int lane) {
+                if (!L.done && lim_ - L.i >= niter_) {
+                    env.scan(L, w, lane, g, rcp, lam2, ph1_, niter_);      // Lane::run, or the kernel's equivalent device form
+                    L.settle(g);
+                }
             });
-            if (stats) stats->retired++;
+            env.sync();
+            if (ph1) ph1 = env.any([&](Lane<T>& L, int) { return !L.done && L.in_rec == REC_NONE; });
+            if (stats) stats->iters += niter;
         }
     }
     drain.flush(env, w, fill_pos, true);

@@ -26,7 +26,8 @@ struct FiberGeom {
 enum InOp { IN_A = 0, IN_A_MINUS_B = 1, IN_A_PLUS_B = 2 };
 
 // Which kernel family prox_fibers() may use.
-enum Engine { ENGINE_AUTO = 0, ENGINE_SEQ = 1, ENGINE_CHUNKED = 2, ENGINE_CHUNKED_STRIDED = 3, ENGINE_PIPELINED = 4, ENGINE_TSPACE = 5, ENGINE_TPOSE = 6 };
+enum Engine { ENGINE_AUTO = 0, ENGINE_SEQ = 1, ENGINE_CHUNKED = 2, ENGINE_CHUNKED_STRIDED = 3, ENGINE_PIPELINED = 4, ENGINE_TSPACE = 5, ENGINE_TPOSE = 6,
+              ENGINE_LANE = 7 /* lane-per-fiber streaming engine (kernels_lane.cu); what AUTO uses when the shape suits TMA tiling */ };
 
 struct ProxStats {           // filled asynchronously on the device; optional
     unsigned long long fallback_fibers;
@@ -94,3 +95,16 @@ template <typename T> int pd_device(const T* y, const double* lambdas_scaled, co
                                     const int* ns, int nds, int npen, int maxIters, void* ws, Engine eng, cudaStream_t st);
 
 }  // namespace ptv
+
+// ---- lane-per-fiber streaming engine (kernels_lane.cu): slope-form scan, TMA-tiled windows, no transposed copies ----
+namespace ptvl {
+enum { LANE_PLAIN = 0, LANE_DR_B = 1, LANE_DR_B_FINAL = 2 };      // fused pass arithmetic (PassOp in kernels_lane.cu)
+// prox over the fibers (nf, len, inc); returns cudaErrorInvalidConfiguration when the shape does not suit (caller falls back)
+template <typename T>
+cudaError_t lane_prox(int op, const T* A, const T* B, const T* C, T* X, long long nf, int len, long long inc, T lam, void* scratch,
+                      cudaStream_t st);
+void* lane_scratch(long long nf, int len);          // per-device records / counters (allocates: call outside stream capture)
+bool lane_shape_ok(long long nf, int len, long long inc, size_t elem, const void* const* ptrs, int nptrs);
+void lane_set_tuning(int clen, int halo, int variant);
+unsigned long long lane_read_stats(int reset);
+}  // namespace ptvl

@@ -149,6 +149,36 @@ static int dr2_piped_body(size_t M, size_t N, const T* Y, T w1, T w2, T* out, in
 #undef BTRY
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Douglas-Rachford on the lane-per-fiber engine (kernels_lane.cu): two kernels per iteration, no transposed copies, 6 array
+// sweeps per iteration (the algorithmic count).  With x1 = prox_cols(t), x2 = prox_rows(Y - s):
+//     columns   x1 = prox(t)                                    1 read + 1 write      CONTIG layout (TMA box in, TMA box out)
+//     rows      s = 2 (t - x1) - t ; in = Y - s                 3 reads               STRIDED layout, formed in the feeder
+//               t' = 0.5 (t + s + 2 x2) = (t - x1) + x2         1 write               formed in the drain
+// (src/TV2Dopt.cpp:403-423; the last form is the reference's :419-422 with tb substituted, equal up to rounding), and the
+// final projection pair (:427-430) s = t - x1 ; out = prox_rows(Y - s).  The first column pass sees the constant image
+// 2 * mean, whose prox is that constant.
+template <typename T>
+static int dr2_lane_body(size_t M, size_t N, int batch, const T* Y, T w1, T w2, T* out, int maxit, T* t, T* t2, T* x1, double* scratch,
+                         void* lscr, cudaStream_t st) {
+#define LTRY(expr) do { cudaError_t e__ = (expr); if (e__ == cudaErrorInvalidConfiguration) { cudaGetLastError(); return 2; } \
+    if (e__ != cudaSuccess) { fprintf(stderr, "proxtv_b200: CUDA error %s at %s:%d\n", cudaGetErrorString(e__), __FILE__, __LINE__); return 1; } } while (0)
+    const long long n = (long long)M * N * batch;
+    LTRY(ew_image_means_x2<T>(Y, (long long)M * N, batch, t, scratch, st));                                   // t = 2 mean (:390-395)
+    for (int it = 0; it <= maxit; it++) {
+        const bool final = it == maxit, first = it == 0 && maxit > 0;
+        if (first) LTRY(cudaMemcpyAsync(x1, t, (size_t)n * sizeof(T), cudaMemcpyDeviceToDevice, st));
+        else { KernelSpan sp(KC_PROX_CONTIG, 1, st);
+               LTRY(ptvl::lane_prox<T>(ptvl::LANE_PLAIN, t, nullptr, nullptr, x1, (long long)N * batch, (int)M, 1, w1, lscr, st)); }
+        { KernelSpan sp(KC_PROX_STRIDED, 1, st);
+          LTRY(ptvl::lane_prox<T>(final ? ptvl::LANE_DR_B_FINAL : ptvl::LANE_DR_B, Y, x1, t, final ? out : t2, (long long)M * batch, (int)N,
+                                  (long long)M, w2, lscr, st)); }
+        if (!final) { T* tmp = t; t = t2; t2 = tmp; }
+    }
+    return 0;
+#undef LTRY
+}
+
 template <typename T>
 int dr2_tspace_body(size_t M, size_t N, int batch, const T* Y, T w1, T w2, T* out, int maxit, void* ws, double* scratch, cudaStream_t st,
                     bool plain_transposes);
@@ -196,12 +226,23 @@ int dr2_device(size_t M, size_t N, int batch, int row_major, const T* Y, T w1, T
     const bool tspace = (eng == ENGINE_TSPACE || tpose) && !row_major && M >= 64 && N >= 64 && g_pipe.init();
     const bool piped = (eng == ENGINE_AUTO || eng == ENGINE_PIPELINED) && !row_major && batch == 1 && M >= 1024 && N >= 1024 && M % 2 == 0 && N % 2 == 0 &&
                        (size_t)((M > N ? M : N) * sizeof(T)) <= 96 * 1024 && g_pipe.init();
-    if (tspace || piped) {
+    // lane-per-fiber engine: column-major images whose row pitch suits TMA tiling, positive weights
+    const void* lane_ptrs[3] = {Y, out, ws};
+    void* lscr = nullptr;
+    bool lane = (eng == ENGINE_AUTO || eng == ENGINE_LANE) && !row_major && w1 > T(0) && w2 > T(0) && M >= 2 && N >= 2 && g_pipe.init() &&
+                ptvl::lane_shape_ok((long long)N * batch, (int)M, 1, sizeof(T), lane_ptrs, 3) &&
+                ptvl::lane_shape_ok((long long)M * batch, (int)N, (long long)M, sizeof(T), lane_ptrs, 3);
+    if (lane) {
+        void* a1 = ptvl::lane_scratch((long long)N * batch, (int)M); void* a2 = ptvl::lane_scratch((long long)M * batch, (int)N);
+        lscr = a2; lane = a1 && a2;                 // the second call returns the (possibly grown) buffer both passes use
+    }
+    if (lane || tspace || piped) {
         auto body = [&](cudaStream_t bs) -> int {
+            if (lane) return dr2_lane_body<T>(M, N, batch, Y, w1, w2, out, maxit, t, s, x, scratch, lscr, bs);
             return tspace ? dr2_tspace_body<T>(M, N, batch, Y, w1, w2, out, maxit, ws, scratch, bs, tpose)
                           : dr2_piped_body<T>(M, N, Y, w1, w2, out, maxit, t, s, x, scr, scratch, gc, n, eng == ENGINE_AUTO && sizeof(T) == 8, bs);
         };
-        DrGraphKey key{sizeof(T) + (tspace ? 100u : 0u) + (tpose ? 200u : 0u) + (eng == ENGINE_AUTO ? 400u : 0u) + 1000u * (size_t)batch, M, N, (const void*)Y, (void*)out, ws, (double)w1,
+        DrGraphKey key{sizeof(T) + (tspace ? 100u : 0u) + (tpose ? 200u : 0u) + (eng == ENGINE_AUTO ? 400u : 0u) + (lane ? 800u : 0u) + 1000u * (size_t)batch, M, N, (const void*)Y, (void*)out, ws, (double)w1,
                        (double)w2, maxit};
         int rc = -1;
         if (!profile_is_enabled()) {

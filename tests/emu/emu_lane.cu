@@ -59,6 +59,7 @@ template <typename T, int W> struct HostDrainDirect {
     void rows8(const Window<T, W>&, int r0, int cnt, int lane, const T* xs, bool valid) {
         if (valid) for (int u = 0; u < cnt; u++) op->out(fb->base[lane] + (long long)(r0 + u) * fb->stride, xs[u]);
     }
+    void prefetch(int, int, bool) {}
     template <class Env> void flush(Env&, const Window<T, W>&, int, bool) {}
     int hold(int, int) const { return 0x3fffffff; }
 };
@@ -67,6 +68,7 @@ template <typename T, int W> struct HostDrainDirect {
 template <typename T, int W, int BOX> struct HostDrainBoxed {
     const Op<T>* op; const Fibers<T>* fb; int stored; int ce;
     void rows8(const Window<T, W>& w, int r0, int cnt, int lane, const T* xs, bool) { for (int u = 0; u < cnt; u++) w.st(r0 + u, lane, xs[u]); }
+    void prefetch(int, int, bool) {}
     template <class Env> void flush(Env&, const Window<T, W>& w, int upto, bool final) {
         while (stored + BOX <= upto || (final && stored < upto)) {
             const int b1 = stored + BOX < upto ? stored + BOX : upto;

@@ -17,7 +17,7 @@ from conftest import jumps, relerr
 from oracle import oracle as O
 
 pytestmark = pytest.mark.gpu
-ENGINES = ["seq", "auto", "chunked", "chunked-strided"]
+ENGINES = ["seq", "auto", "chunked", "chunked-strided", "lane"]
 
 
 @pytest.fixture(params=ENGINES)
@@ -316,21 +316,26 @@ def test_long_fibers_config1(ptv, port):
         assert np.array_equal(Gb[b], port.tv1_linearized(Xb[b], 0.5))
 
 
-def test_pipelined_schedule_equals_serial_schedule(ptv, port):
-    """The default Douglas-Rachford schedule (dr_tspace.cu: no standalone transposes, every kernel writes both layouts, whole
-    solve replayed from a CUDA graph) and the 'pipelined' schedule (overlapped gather/scatter) must give bit-identical
-    results to the plain serial schedule (engine 'chunked'), call after call, and match the oracle."""
+def test_schedules_agree(ptv, port):
+    """The Douglas-Rachford schedules of the bit-faithful chunked family ('chunked' serial, 'pipelined' overlapped gather/scatter,
+    'tspace' / 'tpose' transposeless) must give bit-identical results, call after call (graph replay).  The default ('auto' =
+    the lane-per-fiber engine in slope form, a different rounding sequence) must agree with them to ~1e-13 and with the oracle,
+    with identical jump sets on every fiber of the final pass."""
     Y = O.gen_cfg2(1024, 1536, seed=5)
     a = ptv.tv1_2d(Y, 0.2)
     a2 = ptv.tv1_2d(Y, 0.2)                       # second call: graph replay
     res = {}
-    for e in ("chunked", "pipelined", "tspace", "tpose"):
+    for e in ("chunked", "pipelined", "tspace", "tpose", "lane"):
         prev = ptv.set_engine(e)
         try:
             res[e] = ptv.tv1_2d(Y, 0.2)
         finally:
             ptv.set_engine(prev)
-    assert np.array_equal(a, a2) and np.array_equal(a, res["chunked"]) and np.array_equal(a, res["pipelined"]) and np.array_equal(a, res["tspace"]) and np.array_equal(a, res["tpose"])
+    assert np.array_equal(a, a2) and np.array_equal(a, res["lane"])
+    assert np.array_equal(res["chunked"], res["pipelined"]) and np.array_equal(res["chunked"], res["tspace"]) and np.array_equal(res["chunked"], res["tpose"])
+    assert relerr(a, res["chunked"]) <= 1e-10
+    for r in range(0, 1024, 37):                  # jump sets of final-pass (row) fibers
+        assert np.array_equal(jumps(a[r, :], 1e-9), jumps(res["chunked"][r, :], 1e-9)), r
     Z = O.gen_cfg2(200, 136, seed=6, block=8)     # small, odd-ish shape through the same default schedule
     assert relerr(ptv.tv1_2d(Z, 0.3), port.dr2_tv(Z, 0.3)[0]) <= 1e-9
     S = np.asfortranarray(Y[:, :1024])
