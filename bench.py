@@ -34,16 +34,19 @@ B_PER_PIXEL_SOLVE = lambda b, maxit=35: b * (1 + 6 * maxit + 5)      # noqa: E73
 LAM = 0.2
 
 
-def ncu_traffic():
-    """dram__bytes_read + dram__bytes_write per launch of the dominant kernel, from the committed ncu --set full capture (mean of
-    the captured launches: one sparse-result row pass and one dense column pass)."""
+def ncu_traffic(cls=-1):
+    """dram__bytes_read + dram__bytes_write per launch of the dominant kernel from the committed ncu --set full capture.
+    cls 0 / 1: the lane engine's column / row pass (profiles/r2_lane_ncu_full.csv, columns launch0 / launch1);
+    -1: round 1's chunked scan (mean of its two captured launches)."""
     try:
+        path = "r1_contig_kernel_ncu_full.csv" if cls < 0 else "r2_lane_ncu_full.csv"
         r = w = None
-        for line in open(os.path.join(ROOT, "profiles", "r1_contig_kernel_ncu_full.csv")):
+        for line in open(os.path.join(ROOT, "profiles", path)):
             p = line.strip().split(",")
             if p[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
                 scale = 1e6 if p[1] == "Mbyte" else 1e9 if p[1] == "Gbyte" else 1e3 if p[1] == "Kbyte" else 1.0
-                v = sum(float(x) for x in p[2:]) / len(p[2:]) * scale
+                vals = [float(x) for x in p[2:]]
+                v = (sum(vals) / len(vals) if cls < 0 else vals[cls]) * scale
                 if p[0] == "dram__bytes_read.sum": r = v
                 else: w = v
         return r + w if r is not None and w is not None else None
@@ -102,6 +105,36 @@ class ClockSampler:
         return out
 
 
+def host_threads():
+    """Threads this process may use: scheduler affinity, capped by the cgroup CPU quota when there is one."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = max(1, min(n, int(float(q) / float(per) + 0.5)))
+    except Exception:  # noqa: BLE001
+        pass
+    return max(1, n)
+
+
+def best_threads(R, Y, lam):
+    """The reference's OpenMP DR2_TV is not fastest with every hardware thread (oversubscription, NUMA): time one solve of a
+    4096 x 512 strip (full-length first-pass fibers) per candidate thread count and keep the best."""
+    nmax = host_threads()
+    cands = sorted({c for c in (8, 16, 32, 64, nmax) if c <= nmax} | {nmax})
+    S = np.asfortranarray(Y[:, :max(Y.shape[1] // 8, 8)])
+    best, sweep = None, {}
+    for c in cands:
+        t0 = time.perf_counter(); R.dr2_tv(S, lam, n_threads=c); dt = time.perf_counter() - t0
+        sweep[c] = S.size / dt / 1e6
+        if best is None or sweep[c] > sweep[best]:
+            best = c
+    return best, sweep
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's own CPU implementation (OpenMP DR2_TV), all host cores, rank 0 only."""
     if rank != 0:
@@ -111,18 +144,11 @@ def run_reference(args, rank, world):
         R = O.Ref(); kind = "reference"
     except Exception:  # noqa: BLE001
         R = O.Port(); kind = "port"
-    cores = os.cpu_count() or 1
     M = args.size
     Y = O.gen_cfg2(M, M, seed=0)
-    # bounded sample: a strip of full-length columns (fibers of the first pass keep their length M); pick the widest strip
-    # (number of columns) that keeps the whole run within ~2.5 minutes, from a quick probe.
-    probe_cols = max(M // 16, 8)
-    t0 = time.perf_counter(); R.dr2_tv(np.asfortranarray(Y[:, :probe_cols]), LAM, n_threads=cores); tp = time.perf_counter() - t0
-    budget = 150.0 / max(args.steps + args.warmup, 1)
-    cols = M
-    while cols > probe_cols and tp * (cols / probe_cols) > budget:
-        cols //= 2
-    S = np.asfortranarray(Y[:, :cols])
+    # the FULL image, every step; thread count chosen once from a short sweep (stated in cpu_baseline)
+    cores, sweep = best_threads(R, Y, LAM)
+    S = Y
     for _ in range(args.warmup):
         R.dr2_tv(S, LAM, n_threads=cores)
     t0 = time.perf_counter()
@@ -130,7 +156,8 @@ def run_reference(args, rank, world):
         R.dr2_tv(S, LAM, n_threads=cores)
     dt = (time.perf_counter() - t0) / max(args.steps, 1)
     v = S.size / dt / 1e6
-    sample = "%dx%d strip of the %dx%d image per step (all %d columns)" % (M, cols, M, M, cols) if cols < M else "full %dx%d image per step" % (M, M)
+    sample = "full %dx%d image per step; %d OpenMP threads (best of sweep %s on a %dx%d strip; %d threads available)" % (
+        M, M, cores, {k: round(x, 2) for k, x in sweep.items()}, M, max(M // 8, 8), host_threads())
     print(json.dumps({
         "impl": "reference", "metric": "tv1_2d Mpixels/s", "value": v, "unit": "Mpixels/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
@@ -237,6 +264,15 @@ def main():
     if world > 1:
         dist.all_reduce(et, op=dist.ReduceOp.MAX)
     e2e_value = world * M * M / (float(et.item()) / args.steps * 1e-3) / 1e6
+    # the numpy drop-in: prox_tv.tv1_2d's surface on a pageable F-ordered ndarray (what a prox_tv user calls)
+    ptv.tv1_2d(Yh, LAM)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res_np = ptv.tv1_2d(Yh, LAM)
+    np_t = torch.tensor([(time.perf_counter() - t0) * 1e3], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(np_t, op=dist.ReduceOp.MAX)
+    e2e_numpy = world * M * M / (float(np_t.item()) / args.steps * 1e-3) / 1e6
     clk = clocks.stop()
     res = np.ctypeslib.as_array(C.cast(hout, C.POINTER(C.c_double)), shape=(M * M,))
     same = bool(np.array_equal(res, out.cpu().numpy().ravel()))
@@ -245,36 +281,47 @@ def main():
     if rank == 0:
         peak, peak_src = peaks()
         names = ["prox_contiguous_fibers", "prox_strided_fibers", "elementwise"]
-        # algorithmic bytes per launch of each kernel class for this workload (DESIGN.md "Kernels"): f64 sweeps of the image
-        # both prox classes are the chunked scan kernel over one image-sized array (the strided pass scans the gathered
-        # copy): 1R + 1W = 2 sweeps per launch; the tiled gather (2R+1W) and scatter+combine (4R+1W) average 4 sweeps
-        sweeps = {0: 2.0, 1: 2.0, 2: 4.0}
-        # classes 0 and 1 are the SAME kernel (the chunked scan; class 1 = its launches on the gathered row fibers): the dominant
-        # kernel is decided on their sum
-        scan_ms, scan_n = kms[0] + kms[1], ks[0] + ks[1]
-        dom = 0 if scan_ms >= kms[2] else 2
-        avg_ms = (scan_ms / max(scan_n, 1)) if dom == 0 else kms[2] / max(ks[2], 1)
+        lane = args.engine in ("auto", "lane")
+        # algorithmic bytes per launch of each kernel class for this workload (DESIGN.md "Kernels"), in f64 sweeps of the image.
+        # lane engine: class 0 = k_lane CONTIG (column pass: 1R + 1W), class 1 = k_lane STRIDED with the fused Douglas-Rachford
+        # arithmetic (row pass: reads Y, t, x_cols, writes t': 3R + 1W; the final projection pass has the same traffic).
+        # chunked engines: both prox classes are the chunked scan (1R + 1W); gather (2R+1W) / scatter+combine (4R+1W) average 4.
+        sweeps = {0: 2.0, 1: 4.0 if lane else 2.0, 2: 4.0}
+        kname = {0: "k_lane<CONTIG, plain> (column pass)" if lane else "k_prox_chunked_contig",
+                 1: "k_lane<STRIDED, fused Douglas-Rachford> (row pass)" if lane else "k_prox_chunked_contig (on gathered rows)", 2: "elementwise"}
+        if lane:
+            dom = max(range(3), key=lambda i: kms[i])
+            avg_ms = kms[dom] / max(ks[dom], 1)
+        else:
+            scan_ms, scan_n = kms[0] + kms[1], ks[0] + ks[1]
+            dom = 0 if scan_ms >= kms[2] else 2
+            avg_ms = (scan_ms / max(scan_n, 1)) if dom == 0 else kms[2] / max(ks[2], 1)
         ach = sweeps[dom] * M * M * 8 / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
+        per_class = {names[i]: {"kernel": kname[i], "ms_per_step": kms[i] / args.steps, "launches_per_step": ks[i] / args.steps,
+                                "avg_launch_ms": kms[i] / max(ks[i], 1),
+                                "achieved_GBs": (sweeps[i] * M * M * 8 / (kms[i] / max(ks[i], 1) * 1e-3) / 1e9) if kms[i] > 0 else 0.0,
+                                "frac": (sweeps[i] * M * M * 8 / (kms[i] / max(ks[i], 1) * 1e-3) / 1e9 / peak) if kms[i] > 0 else 0.0}
+                     for i in range(3)}
         solve_bytes = B_PER_PIXEL_SOLVE(8) * M * M
         line = {
             "metric": "tv1_2d Mpixels/s", "value": value, "unit": "Mpixels/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "tv1_2d DR2_TV %dx%d f64 lambda=%.1f, 35 iterations + final projection, one image per GPU"
-                                   % (M, M, LAM), "engine": args.engine,
+                                   % (M, M, LAM), "engine": args.engine + (" (lane-per-fiber slope-form engine, kernels_lane.cu)" if lane else ""),
                        "l2": "working set 4 x %d MiB > 126 MB L2 (inputs larger than L2, no flush)" % (nbytes >> 20)},
-            "roofline": {"bound": "hbm", "kernel": "k_prox_chunked_contig (chunked speculative scan)" if dom == 0 else names[dom], "achieved": ach, "peak": peak, "unit": "GB/s",
-                         "frac": ach / peak, "traffic": ncu_traffic() if (dom == 0 and M == 4096) else None,
-                         "traffic_source": "profiles/r1_contig_kernel_ncu_full.csv (ncu --set full, same kernel and shape)",
+            "roofline": {"bound": "hbm", "kernel": kname[dom], "achieved": ach, "peak": peak, "unit": "GB/s",
+                         "frac": ach / peak, "traffic": ncu_traffic(dom if lane else -1) if M == 4096 else None,
+                         "traffic_source": "profiles/r2_lane_ncu_full.csv (ncu --set full, same kernels and shape)" if lane else "profiles/r1_contig_kernel_ncu_full.csv",
                          "algorithmic_bytes_per_launch": sweeps[dom] * M * M * 8, "peak_source": peak_src,
-                         "avg_launch_ms": avg_ms, "launches_timed": int(scan_n if dom == 0 else ks[2]),
-                         "timing_region": "%d additional steps right after the timed region, serial schedule, CUDA events around every launch" % args.steps,
-                         "note": "launches = column passes (dense result, fill phase) + row passes (sparse result: segment starts only, the fused scatter expands them); both counted as 1R+1W of the array",
-                         "class_ms_per_step": {names[i]: kms[i] / args.steps for i in range(3)}},
+                         "avg_launch_ms": avg_ms, "launches_timed": int(ks[dom]),
+                         "timing_region": "%d additional steps right after the timed region, same kernels launched one by one (no graph replay), CUDA events around every launch" % args.steps,
+                         "classes": per_class},
             "roofline_solve": {"algorithmic_bytes": solve_bytes, "achieved": solve_bytes / (ms_step * 1e-3) / 1e9,
                                "peak": peak, "unit": "GB/s", "frac": solve_bytes / (ms_step * 1e-3) / 1e9 / peak},
             "e2e": {"value": e2e_value, "unit": "Mpixels/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
-                    "api": "DR2_TV() C ABI, pinned host buffers", "matches_device_path": same},
+                    "api": "DR2_TV() C ABI, pinned host buffers", "matches_device_path": same,
+                    "numpy_dropin_value": e2e_numpy, "numpy_dropin_api": "proxtv_b200.tv1_2d(ndarray): pageable memory, allocates its result"},
             "gpu_launches": launches_timed_region,
             "clocks": clk,
         }
@@ -283,12 +330,11 @@ def main():
                 R = O.Ref(); kind = "reference"
             except Exception:  # noqa: BLE001
                 R = O.Port(); kind = "port"
-            cores = os.cpu_count() or 1
-            cols = max(M // 4, 8)                     # bounded sample: a quarter-width strip, full-length first-pass fibers
-            S = np.asfortranarray(Yh[:, :cols])
-            t0 = time.perf_counter(); R.dr2_tv(S, LAM, n_threads=cores); dt = time.perf_counter() - t0
-            line["cpu_baseline"] = {"value": S.size / dt / 1e6, "unit": "Mpixels/s", "cores": cores, "kind": kind,
-                                    "sample": "one DR2_TV solve of a %dx%d strip of the image, %d OpenMP threads" % (M, cols, cores)}
+            cores, sweep = best_threads(R, Yh, LAM)
+            t0 = time.perf_counter(); R.dr2_tv(Yh, LAM, n_threads=cores); dt = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": Yh.size / dt / 1e6, "unit": "Mpixels/s", "cores": cores, "kind": kind,
+                                    "sample": "one DR2_TV solve of the full %dx%d image, %d OpenMP threads (best of sweep %s Mpixels/s on a %dx%d strip; %d threads available)"
+                                              % (M, M, cores, {k: round(x, 2) for k, x in sweep.items()}, M, max(M // 8, 8), host_threads())}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -113,7 +113,7 @@ template <typename T, int W> struct DevWin {
     static constexpr int ROWB = LANES * (int)sizeof(T);          // bytes per window row
     static constexpr uint32_t MASK = (uint32_t)(W * ROWB - 1) & ~(uint32_t)(ROWB - 1);
     static constexpr int SH = (ROWB == 256) ? 5 : 5;             // (k * ROWB) >> SH == k * sizeof(T): 256 >> 5 = 8, 128 >> 5 = 4
-    static constexpr int FSH = (ROWB == 256) ? 8 : 7;            // scaled position -> row
+    static constexpr int FSH = (ROWB == 256) ? 8 : 7;            // scaled position -> row (positions are exact multiples: arithmetic shift)
     uint32_t wbase;    // shared address of the warp's window (a kernel constant when the CTA is a single warp: folds into the access)
     uint32_t lane8;    // byte offset of this lane's column inside a window row
     uint32_t flg;      // shared address of this lane's flag bytes
@@ -130,9 +130,9 @@ __device__ __forceinline__ void run_dev(Lane<T>& L, const DevWin<T, W> dw, const
     using DW = DevWin<T, W>;
     constexpr int ROWB = DW::ROWB;
     T Z = L.Z, lo = L.lo, hi = L.hi;
-    int ia = L.i * ROWB, la = L.last * ROWB, bloa = L.blo * ROWB, bhia = L.bhi * ROWB;
-    int kind = L.kind, lprev = L.lprev * ROWB, kprev = L.kprev, in_ = L.in_rec;
-    const int cea = g.ce * ROWB, csa = g.cs * ROWB;
+    int ia = L.i << DW::FSH, la = L.last << DW::FSH, bloa = L.blo << DW::FSH, bhia = L.bhi << DW::FSH;
+    int kind = L.kind, lprev = L.lprev << DW::FSH, kprev = L.kprev, in_ = L.in_rec;
+    const int cea = g.ce << DW::FSH, csa = g.cs << DW::FSH;
     T nlam2 = -lam2;
     opaque(nlam2);                                     // keep -2 lam in a register (else it is re-negated every iteration)
 #pragma unroll 1
@@ -141,7 +141,7 @@ __device__ __forceinline__ void run_dev(Lane<T>& L, const DevWin<T, W> dw, const
         const int ka = ia - la;
         const T r = SmemIO<T>::ld(dw.rcp + ((uint32_t)ka >> DW::SH));
         Z += y;
-        const T cl = Z * r, ch = (Z + lam2) * r;
+        const T cl = Z * r, ch = fma(lam2, r, cl);                  // (Z + 2 lam) r, one operation shorter
         const bool first = (ka == ROWB);
         const bool can = !first & (la < cea);
         const bool craw = lo > ch, fraw = hi < cl;          // both compares issue back to back (neither waits for the other)
@@ -156,7 +156,7 @@ __device__ __forceinline__ void run_dev(Lane<T>& L, const DevWin<T, W> dw, const
         if (PH1) {
             em = brk & (ea >= csa);
             fea = fa > csa ? fa : csa;
-            in_ = (em & (in_ == REC_NONE)) ? rec_pack(fa / ROWB, kind) : in_;
+            in_ = (em & (in_ == REC_NONE)) ? rec_pack(fa >> DW::FSH, kind) : in_;
         }
         const uint32_t va = dw.at(fea);
         const uint32_t fla = dw.flg + (((uint32_t)fea >> DW::FSH) & (uint32_t)(W - 1));
@@ -170,11 +170,207 @@ __device__ __forceinline__ void run_dev(Lane<T>& L, const DevWin<T, W> dw, const
         ia = (brk ? ea : ia) + ROWB;
         la = brk ? ea : la;
     }
-    L.Z = Z; L.lo = lo; L.hi = hi; L.i = ia / ROWB; L.last = la / ROWB; L.blo = bloa / ROWB; L.bhi = bhia / ROWB;
-    L.kind = kind; L.lprev = lprev / ROWB; L.kprev = kprev; L.in_rec = in_;
+    L.Z = Z; L.lo = lo; L.hi = hi; L.i = ia >> DW::FSH; L.last = la >> DW::FSH; L.blo = bloa >> DW::FSH; L.bhi = bhia >> DW::FSH;
+    L.kind = kind; L.lprev = lprev >> DW::FSH; L.kprev = kprev; L.in_rec = in_;
 }
 
-template <typename T, int W> struct DevEnv {
+// The steady-state loop (all lanes past their first owned segment) written in PTX.  On this architecture a scheduler issues one
+// instruction per cycle, but the integer/logic pipe (SEL, FSEL, LOP3, ISETP ...) and the FMA pipe (IMAD, FFMA ...) each accept a
+// warp instruction only every second cycle (B300_MICROARCH.md "fma vs alu split": rt_SMSP = 2).  The C++ form of the step
+// compiles to ~36 integer/logic-pipe instructions out of 53 -- 72 of the ~100 cycles a step takes.  Here every state update of
+// the form `x = p ? a : x` is a PREDICATED MOVE, which the assembler is free to issue on the FMA pipe (IMAD.MOV), so the two
+// pipes share the work and the step approaches the issue limit.  Same arithmetic, same decisions as run_dev<false>.
+template <typename T> struct StepAsm;
+template <> struct StepAsm<double> {
+    static __device__ __forceinline__ void step(double& Z, double& lo, double& hi, int& ia, int& la, int& bloa, int& bhia, int& kind,
+                                                int& lprev, int& kprev, double lam2, double nlam2, int cea, uint32_t mask, uint32_t lw,
+                                                uint32_t rcp, uint32_t flg, uint32_t wm1) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred first, can, cbk, fbk, brk, tlo, thi;\n\t"
+            ".reg .u32 ad, ka, ra, fa, va, fl;\n\t"
+            ".reg .f64 y, r, cl, ch;\n\t"
+            "lop3.b32 ad, %3, %14, 0, 0xC0;\n\t"            // ad = ia & mask
+            "add.u32 ad, ad, %15;\n\t"                       //    + lane/window base
+            "ld.shared.f64 y, [ad];\n\t"
+            "sub.s32 ka, %3, %4;\n\t"                        // ka = ia - la
+            "shr.u32 ra, ka, 5;\n\t"
+            "add.u32 ra, ra, %16;\n\t"
+            "ld.shared.f64 r, [ra];\n\t"
+            "add.s32 fa, %4, 256;\n\t"                       // first row of the open segment
+            "add.f64 %0, %0, y;\n\t"                         // Z += y
+            "mul.f64 cl, %0, r;\n\t"
+            "fma.rn.f64 ch, %11, r, cl;\n\t"
+            "setp.eq.s32 first, ka, 256;\n\t"
+            "setp.lt.and.s32 can, %4, %13, !first;\n\t"      // breaks allowed: not the first step, segment covering ce not finished
+            "setp.gt.and.f64 cbk, %1, ch, can;\n\t"          // ceiling violation: lo > ch
+            "setp.lt.and.f64 fbk, %2, cl, can;\n\t"          // floor violation:   hi < cl
+            "and.pred fbk, fbk, !cbk;\n\t"
+            "or.pred brk, cbk, fbk;\n\t"
+            "lop3.b32 va, fa, %14, 0, 0xC0;\n\t"
+            "add.u32 va, va, %15;\n\t"
+            "@cbk st.shared.f64 [va], %1;\n\t"               // the finished segment's value at its first row
+            "@fbk st.shared.f64 [va], %2;\n\t"
+            "shr.u32 fl, fa, 8;\n\t"
+            "and.b32 fl, fl, %18;\n\t"
+            "add.u32 fl, fl, %17;\n\t"
+            "@brk st.shared.u8 [fl], 1;\n\t"
+            "setp.ge.or.f64 tlo, cl, %1, first;\n\t"         // touches (evaluated against the old lines)
+            "setp.le.or.f64 thi, ch, %2, first;\n\t"
+            "@brk mov.b32 %8, %4;\n\t"                       // lprev = la ; kprev = kind
+            "@brk mov.b32 %9, %7;\n\t"
+            "@cbk mov.b32 %4, %5;\n\t"                       // la = last touch of the broken line
+            "@fbk mov.b32 %4, %6;\n\t"
+            "@cbk mov.b32 %7, 0;\n\t"                        // kind of the new segment
+            "@fbk mov.b32 %7, 1;\n\t"
+            "@tlo mov.f64 %1, cl;\n\t"
+            "@tlo mov.b32 %5, %3;\n\t"
+            "@thi mov.f64 %2, ch;\n\t"
+            "@thi mov.b32 %6, %3;\n\t"
+            "@brk mov.b32 %3, %4;\n\t"                       // restart right after the break point ...
+            "add.s32 %3, %3, 256;\n\t"                       // ... or advance
+            "@cbk mov.f64 %0, 0d0000000000000000;\n\t"
+            "@fbk mov.f64 %0, %12;\n\t"
+            "}"
+            : "+d"(Z), "+d"(lo), "+d"(hi), "+r"(ia), "+r"(la), "+r"(bloa), "+r"(bhia), "+r"(kind), "+r"(lprev), "+r"(kprev)
+            : "r"(0), "d"(lam2), "d"(nlam2), "r"(cea), "r"(mask), "r"(lw), "r"(rcp), "r"(flg), "r"(wm1)
+            : "memory");
+    }
+};
+template <> struct StepAsm<float> {
+    static __device__ __forceinline__ void step(float& Z, float& lo, float& hi, int& ia, int& la, int& bloa, int& bhia, int& kind,
+                                                int& lprev, int& kprev, float lam2, float nlam2, int cea, uint32_t mask, uint32_t lw,
+                                                uint32_t rcp, uint32_t flg, uint32_t wm1) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred first, can, cbk, fbk, brk, tlo, thi;\n\t"
+            ".reg .u32 ad, ka, ra, fa, va, fl;\n\t"
+            ".reg .f32 y, r, cl, ch;\n\t"
+            "lop3.b32 ad, %3, %14, 0, 0xC0;\n\t"
+            "add.u32 ad, ad, %15;\n\t"
+            "ld.shared.f32 y, [ad];\n\t"
+            "sub.s32 ka, %3, %4;\n\t"
+            "shr.u32 ra, ka, 5;\n\t"
+            "add.u32 ra, ra, %16;\n\t"
+            "ld.shared.f32 r, [ra];\n\t"
+            "add.s32 fa, %4, 128;\n\t"
+            "add.f32 %0, %0, y;\n\t"
+            "mul.f32 cl, %0, r;\n\t"
+            "fma.rn.f32 ch, %11, r, cl;\n\t"
+            "setp.eq.s32 first, ka, 128;\n\t"
+            "setp.lt.and.s32 can, %4, %13, !first;\n\t"
+            "setp.gt.and.f32 cbk, %1, ch, can;\n\t"
+            "setp.lt.and.f32 fbk, %2, cl, can;\n\t"
+            "and.pred fbk, fbk, !cbk;\n\t"
+            "or.pred brk, cbk, fbk;\n\t"
+            "lop3.b32 va, fa, %14, 0, 0xC0;\n\t"
+            "add.u32 va, va, %15;\n\t"
+            "@cbk st.shared.f32 [va], %1;\n\t"
+            "@fbk st.shared.f32 [va], %2;\n\t"
+            "shr.u32 fl, fa, 7;\n\t"
+            "and.b32 fl, fl, %18;\n\t"
+            "add.u32 fl, fl, %17;\n\t"
+            "@brk st.shared.u8 [fl], 1;\n\t"
+            "setp.ge.or.f32 tlo, cl, %1, first;\n\t"
+            "setp.le.or.f32 thi, ch, %2, first;\n\t"
+            "@brk mov.b32 %8, %4;\n\t"
+            "@brk mov.b32 %9, %7;\n\t"
+            "@cbk mov.b32 %4, %5;\n\t"
+            "@fbk mov.b32 %4, %6;\n\t"
+            "@cbk mov.b32 %7, 0;\n\t"
+            "@fbk mov.b32 %7, 1;\n\t"
+            "@tlo mov.f32 %1, cl;\n\t"
+            "@tlo mov.b32 %5, %3;\n\t"
+            "@thi mov.f32 %2, ch;\n\t"
+            "@thi mov.b32 %6, %3;\n\t"
+            "@brk mov.b32 %3, %4;\n\t"
+            "add.s32 %3, %3, 128;\n\t"
+            "@cbk mov.f32 %0, 0f00000000;\n\t"
+            "@fbk mov.f32 %0, %12;\n\t"
+            "}"
+            : "+f"(Z), "+f"(lo), "+f"(hi), "+r"(ia), "+r"(la), "+r"(bloa), "+r"(bhia), "+r"(kind), "+r"(lprev), "+r"(kprev)
+            : "r"(0), "f"(lam2), "f"(nlam2), "r"(cea), "r"(mask), "r"(lw), "r"(rcp), "r"(flg), "r"(wm1)
+            : "memory");
+    }
+};
+
+template <typename T, int W>
+__device__ __forceinline__ void run_dev_asm(Lane<T>& L, const DevWin<T, W> dw, const TaskGeom& g, T lam2, int niter) {
+    using DW = DevWin<T, W>;
+    T Z = L.Z, lo = L.lo, hi = L.hi;
+    int ia = L.i << DW::FSH, la = L.last << DW::FSH, bloa = L.blo << DW::FSH, bhia = L.bhi << DW::FSH;
+    int kind = L.kind, lprev = L.lprev << DW::FSH, kprev = L.kprev;
+    const int cea = g.ce << DW::FSH;
+    const T nlam2 = -lam2;
+    const uint32_t lw = dw.lane8 + dw.wbase;
+#pragma unroll 1
+    for (int it = 0; it < niter; it++)
+        StepAsm<T>::step(Z, lo, hi, ia, la, bloa, bhia, kind, lprev, kprev, lam2, nlam2, cea, DW::MASK, lw, dw.rcp, dw.flg, (uint32_t)(W - 1));
+    L.Z = Z; L.lo = lo; L.hi = hi; L.i = ia >> DW::FSH; L.last = la >> DW::FSH; L.blo = bloa >> DW::FSH; L.bhi = bhia >> DW::FSH;
+    L.kind = kind; L.lprev = lprev >> DW::FSH; L.kprev = kprev;
+}
+
+// The same loop with the sample and the reciprocal of the NEXT step fetched one step ahead.  The next position is one of three
+// -- the row after the current one (no break), the row after the last floor touch (ceiling break) or after the last ceiling touch
+// (floor break) -- and all three are known at the top of a step, so their loads are issued there and the step ends by selecting
+// among the three values: the shared-memory latency leaves the loop-carried dependency chain (address -> load -> add -> multiply ->
+// compare -> select -> address), which is what bounds a warp's issue rate at two or three resident warps per scheduler.
+template <bool PH1, typename T, int W>
+__device__ __forceinline__ void run_dev_spec(Lane<T>& L, const DevWin<T, W> dw, const TaskGeom& g, T lam2, int niter) {
+    using DW = DevWin<T, W>;
+    constexpr int ROWB = DW::ROWB;
+    T Z = L.Z, lo = L.lo, hi = L.hi;
+    int ia = L.i << DW::FSH, la = L.last << DW::FSH, bloa = L.blo << DW::FSH, bhia = L.bhi << DW::FSH;
+    int kind = L.kind, lprev = L.lprev << DW::FSH, kprev = L.kprev, in_ = L.in_rec;
+    const int cea = g.ce << DW::FSH, csa = g.cs << DW::FSH;
+    T nlam2 = -lam2;
+    opaque(nlam2);
+    T y = SmemIO<T>::ld(dw.at(ia));
+    T r = SmemIO<T>::ld(dw.rcp + ((uint32_t)(ia - la) >> DW::SH));
+#pragma unroll 1
+    for (int it = 0; it < niter; it++) {
+        const int ka = ia - la;
+        // candidates for the next step (addresses depend on nothing computed in this step)
+        const T ynb = SmemIO<T>::ld(dw.at(ia + ROWB));
+        const T ylo = SmemIO<T>::ld(dw.at(bloa + ROWB));
+        const T yhi = SmemIO<T>::ld(dw.at(bhia + ROWB));
+        const T rnb = SmemIO<T>::ld(dw.rcp + ((uint32_t)ka >> DW::SH) + (uint32_t)sizeof(T));
+        Z += y;
+        const T cl = Z * r, ch = fma(lam2, r, cl);
+        const bool first = (ka == ROWB);
+        const bool can = !first & (la < cea);
+        const bool craw = lo > ch, fraw = hi < cl;
+        const bool cbk = can & craw;
+        const bool fbk = can & !craw & fraw;
+        const bool brk = cbk | fbk;
+        const int ea = cbk ? bloa : bhia;
+        const T v = cbk ? lo : hi;
+        const int fa = la + ROWB;
+        bool em = brk; int fea = fa;
+        if (PH1) {
+            em = brk & (ea >= csa);
+            fea = fa > csa ? fa : csa;
+            in_ = (em & (in_ == REC_NONE)) ? rec_pack(fa >> DW::FSH, kind) : in_;
+        }
+        const uint32_t va = dw.at(fea);
+        const uint32_t fla = dw.flg + (((uint32_t)fea >> DW::FSH) & (uint32_t)(W - 1));
+        sts_pred(va, v, fla, em);
+        const bool tlo = first | (cl >= lo), thi = first | (ch <= hi);
+        lo = tlo ? cl : lo; bloa = tlo ? ia : bloa;
+        hi = thi ? ch : hi; bhia = thi ? ia : bhia;
+        lprev = brk ? la : lprev; kprev = brk ? kind : kprev;
+        kind = cbk ? (int)LK_CEIL : (fbk ? (int)LK_FLOOR : kind);
+        Z = cbk ? T(0) : (fbk ? nlam2 : Z);
+        y = cbk ? ylo : (fbk ? yhi : ynb);
+        r = brk ? T(1) : rnb;
+        ia = (brk ? ea : ia) + ROWB;
+        la = brk ? ea : la;
+    }
+    L.Z = Z; L.lo = lo; L.hi = hi; L.i = ia >> DW::FSH; L.last = la >> DW::FSH; L.blo = bloa >> DW::FSH; L.bhi = bhia >> DW::FSH;
+    L.kind = kind; L.lprev = lprev >> DW::FSH; L.kprev = kprev; L.in_rec = in_;
+}
+
+template <typename T, int W, bool SPEC> struct DevEnv {
     Lane<T> L; int lane; DevWin<T, W> dw;
     template <class F> __device__ __forceinline__ void each(F f) { f(L, lane); }
     template <class F> __device__ __forceinline__ int rmin(F f) { return __reduce_min_sync(0xffffffffu, f(L, lane)); }
@@ -182,7 +378,8 @@ template <typename T, int W> struct DevEnv {
     template <class F> __device__ __forceinline__ bool any(F f) { return __any_sync(0xffffffffu, f(L, lane)); }
     __device__ __forceinline__ void sync() { __syncwarp(); }
     __device__ __forceinline__ void scan(Lane<T>& l, const Window<T, W>&, int, const TaskGeom& g, const T*, T lam2, bool ph1, int niter) {
-        if (ph1) run_dev<true, T, W>(l, dw, g, lam2, niter); else run_dev<false, T, W>(l, dw, g, lam2, niter);
+        if (SPEC) { if (ph1) run_dev<true, T, W>(l, dw, g, lam2, niter); else run_dev_asm<T, W>(l, dw, g, lam2, niter); }
+        else { if (ph1) run_dev<true, T, W>(l, dw, g, lam2, niter); else run_dev<false, T, W>(l, dw, g, lam2, niter); }
     }
 };
 
@@ -193,12 +390,12 @@ template <typename T, int W, int RT, int OP> struct FeedStrided {
     static constexpr int MAXQ = (OP == LOP_PLAIN) ? W / RT : NST;
     static constexpr int NBAR = W / RT;
     const LaneArgs<T>* a; T* win; T* stB; T* stC; uint64_t* bar; int x0, z, q0, lane;
-    __device__ __forceinline__ void request(DevEnv<T, W>&, int row0) {
+    template <class Env> __device__ __forceinline__ void request(Env&, int row0) {
         __syncwarp();
         if (lane == 0) {
             fence_proxy_async();                        // the slot's last generic-proxy accesses precede the async write
-            const int q = row0 / R - q0;
-            uint64_t* b = bar + (q % NBAR);
+            const int q = (int)((unsigned)row0 / (unsigned)R) - q0;
+            uint64_t* b = bar + ((unsigned)q % (unsigned)NBAR);
             mbar_expect_tx(b, (uint32_t)(R * LANES * sizeof(T) * (OP == LOP_PLAIN ? 1 : 3)));
             tma_load_3d(win + ((row0 & (W - 1)) << 5), &a->tmA, x0, row0, z, b);
             if (OP != LOP_PLAIN) {
@@ -207,10 +404,10 @@ template <typename T, int W, int RT, int OP> struct FeedStrided {
             }
         }
     }
-    __device__ __forceinline__ bool landed(DevEnv<T, W>&, int row0, bool block) {
-        const int q = row0 / R - q0;
-        uint64_t* b = bar + (q % NBAR);
-        const uint32_t parity = (uint32_t)((q / NBAR) & 1);
+    template <class Env> __device__ __forceinline__ bool landed(Env&, int row0, bool block) {
+        const unsigned q = (unsigned)row0 / (unsigned)R - (unsigned)q0;
+        uint64_t* b = bar + (q % (unsigned)NBAR);
+        const uint32_t parity = (uint32_t)((q / (unsigned)NBAR) & 1u);
         // the decision must be warp-uniform (it steers the task's control flow), and every lane needs the acquire of its own
         // successful wait before it reads the tile: all lanes poll, the vote decides
         bool ok = __all_sync(0xffffffffu, mbar_test(b, parity));
@@ -265,7 +462,7 @@ template <typename T, int W, int OP> struct DrainStrided {
             X[g] = OP == LOP_DR_B ? PassOp<T, OP>::out(xs[u], B[g], C[g]) : xs[u];
         }
     }
-    __device__ __forceinline__ void flush(DevEnv<T, W>&, const Window<T, W>&, int, bool) {}
+    template <class Env> __device__ __forceinline__ void flush(Env&, const Window<T, W>&, int, bool) {}
     __device__ __forceinline__ int hold(int, int) const { return 0x3fffffff; }
 };
 
@@ -292,20 +489,20 @@ template <typename T, int W> struct FeedContig {
     static constexpr int NBAR = W / R;
     static constexpr int EPC = 16 / (int)sizeof(T);          // elements per 16-byte chunk
     const LaneArgs<T>* a; T* win; uint64_t* bar; int f0, q0, lane;
-    __device__ __forceinline__ void request(DevEnv<T, W>&, int row0) {
+    template <class Env> __device__ __forceinline__ void request(Env&, int row0) {
         __syncwarp();
         if (lane == 0) {
             fence_proxy_async();
-            const int q = row0 / R - q0;
-            uint64_t* b = bar + (q % NBAR);
+            const unsigned q = (unsigned)row0 / (unsigned)R - (unsigned)q0;
+            uint64_t* b = bar + (q % (unsigned)NBAR);
             mbar_expect_tx(b, 4096u);
             tma_load_3d(win + ((row0 & (W - 1)) << 5), &a->tmA, row0, f0, 0, b);
         }
     }
-    __device__ __forceinline__ bool landed(DevEnv<T, W>&, int row0, bool block) {
-        const int q = row0 / R - q0;
-        uint64_t* b = bar + (q % NBAR);
-        const uint32_t parity = (uint32_t)((q / NBAR) & 1);
+    template <class Env> __device__ __forceinline__ bool landed(Env&, int row0, bool block) {
+        const unsigned q = (unsigned)row0 / (unsigned)R - (unsigned)q0;
+        uint64_t* b = bar + (q % (unsigned)NBAR);
+        const uint32_t parity = (uint32_t)((q / (unsigned)NBAR) & 1u);
         bool ok = __all_sync(0xffffffffu, mbar_test(b, parity));
         if (!ok && !block) return false;
         while (!ok) ok = __all_sync(0xffffffffu, mbar_try(b, parity));
@@ -341,7 +538,7 @@ template <typename T, int W> struct DrainContig {
         }
     }
     __device__ __forceinline__ void prefetch(int, int, bool) {}
-    __device__ __forceinline__ void flush(DevEnv<T, W>&, const Window<T, W>&, int, bool final) {
+    template <class Env> __device__ __forceinline__ void flush(Env&, const Window<T, W>&, int, bool final) {
         if (final) { if (lane == 0) bulk_wait_all(); __syncwarp(); }            // results are in global memory before the records go out
     }
     __device__ __forceinline__ int hold(int, int) const { return 0x3fffffff; }
@@ -377,8 +574,8 @@ __device__ __noinline__ int repair_fiber(const LaneArgs<T>* a, long long fiber, 
                           X[g] = OP == LOP_DR_B ? PassOp<T, OP>::out(v, B[g], C[g]) : v; });
 }
 
-template <typename T, int W, int RT, int TITER, int OP, int NW, int LAY>
-__global__ void __launch_bounds__(NW * 32) k_lane(const __grid_constant__ LaneArgs<T> a) {
+template <typename T, int W, int RT, int TITER, int OP, int NW, int LAY, bool SPEC>
+__global__ void __launch_bounds__(NW * 32, (12 + NW - 1) / NW) k_lane(const __grid_constant__ LaneArgs<T> a) {
     using SM = LaneSmem<T, W, RT, OP, LAY>;
     extern __shared__ __align__(1024) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -414,7 +611,7 @@ __global__ void __launch_bounds__(NW * 32) k_lane(const __grid_constant__ LaneAr
     const long long nfp = (long long)a.slabs * a.gps * LANES;
     const long long fiber = group * LANES + lane;
 
-    DevEnv<T, W> env; env.lane = lane; env.L.init(g, a.lam, valid);
+    DevEnv<T, W, SPEC> env; env.lane = lane; env.L.init(g, a.lam, valid);
     env.dw.wbase = s32(win); env.dw.lane8 = lane * (uint32_t)sizeof(T); env.dw.flg = s32(flg) + lane * (uint32_t)Window<T, W>::FP; env.dw.rcp = s32(rcp);
     Window<T, W> w{win, flg};
     if (LAY == LAY_CONTIG) {
@@ -498,10 +695,10 @@ long long lane_scratch_bytes(long long nf, int len) {
 }
 
 // launch one instantiation; with `slots` only report how many warp tasks the device can hold at once
-template <typename T, int W, int RT, int TITER, int OP, int NW, int LAY>
+template <typename T, int W, int RT, int TITER, int OP, int NW, int LAY, bool SPEC>
 static cudaError_t launch_v(LaneArgs<T>& a, cudaStream_t st, int* slots) {
     using SM = LaneSmem<T, W, RT, OP, LAY>;
-    auto kern = k_lane<T, W, RT, TITER, OP, NW, LAY>;
+    auto kern = k_lane<T, W, RT, TITER, OP, NW, LAY, SPEC>;
     const size_t smem = SM::rcp_bytes + (size_t)NW * SM::per_warp;
     static int s_slots = 0;                      // per instantiation: resident warps on the current device
     if (!s_slots) {
@@ -524,13 +721,13 @@ static cudaError_t launch_v(LaneArgs<T>& a, cudaStream_t st, int* slots) {
 template <typename T, int OP, int LAY>
 static cudaError_t launch_variant(int variant, LaneArgs<T>& a, cudaStream_t st, int* slots) {
     switch (variant) {
-        case 1: return launch_v<T, 64, 8, 16, OP, 4, LAY>(a, st, slots);
-        case 2: return launch_v<T, 32, 8, 8, OP, 1, LAY>(a, st, slots);
-        case 3: return launch_v<T, 64, 8, 24, OP, 1, LAY>(a, st, slots);
-        case 4: return launch_v<T, 64, 8, 8, OP, 1, LAY>(a, st, slots);
-        case 5: return launch_v<T, 128, 8, 16, OP, 1, LAY>(a, st, slots);
-        case 6: return launch_v<T, 128, 8, 32, OP, 1, LAY>(a, st, slots);
-        default: return launch_v<T, 64, 8, 16, OP, 1, LAY>(a, st, slots);
+        case 1: return launch_v<T, 64, 8, 16, OP, 4, LAY, false>(a, st, slots);
+        case 2: return launch_v<T, 64, 8, 16, OP, 1, LAY, true>(a, st, slots);
+        case 3: return launch_v<T, 64, 8, 24, OP, 1, LAY, true>(a, st, slots);
+        case 4: return launch_v<T, 64, 8, 16, OP, 4, LAY, true>(a, st, slots);
+        case 5: return launch_v<T, 128, 8, 16, OP, 1, LAY, false>(a, st, slots);
+        case 6: return launch_v<T, 128, 8, 32, OP, 1, LAY, true>(a, st, slots);
+        default: return launch_v<T, 64, 8, 16, OP, 1, LAY, false>(a, st, slots);
     }
 }
 template <typename T>

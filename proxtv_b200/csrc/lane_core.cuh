@@ -30,6 +30,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <math.h>
 
 #ifndef PTV_HD
 #define PTV_HD __host__ __device__ __forceinline__
@@ -108,6 +109,12 @@ template <typename T, int W> struct Window {
     uint8_t* flg;      // [32][FP]
     PTV_HD T ld(int row, int lane) const { return win[((row & (W - 1)) << 5) + lane]; }
     PTV_HD void st(int row, int lane, T v) const { win[((row & (W - 1)) << 5) + lane] = v; }
+    // 8 consecutive rows starting at an aligned row (row0 % 8 == 0): never wraps inside the group -> one base, fixed offsets
+    PTV_HD void ld8(int row0, int lane, T* t) const {
+        const T* p = win + ((row0 & (W - 1)) << 5) + lane;
+#pragma unroll
+        for (int u = 0; u < 8; u++) t[u] = p[u * LANES];
+    }
     PTV_HD void set_flag(int row, int lane) const { flg[lane * FP + (row & (W - 1))] = 1; }
     // the 8 flags of the aligned row group that starts at row0 (row0 % 8 == 0), and clearing them
     PTV_HD unsigned long long flags8(int row0, int lane) const {
@@ -160,7 +167,7 @@ template <typename T> struct Lane {
             const int k = i_ - last_;
             const T r = rcp[k];
             Z_ += y;
-            const T cl = Z_ * r, ch = (Z_ + lam2) * r;
+            const T cl = Z_ * r, ch = fma(lam2, r, cl);          // (Z + 2 lam) r
             const bool first = (k == 1);
             const bool can = !first & (last_ < g.ce);
             const bool cbk = can & (lo_ > ch);
@@ -255,8 +262,7 @@ PTV_HD void warp_task(Env& env, Feed& feed, Drain& drain, const Window<T, W>& w,
                         const int cnt = upto - r < 8 ? upto - r : 8;
                         const unsigned long long fl = w.flags8(r, lane);
                         T t[8];
-#pragma unroll
-                        for (int u = 0; u < 8; u++) t[u] = w.ld(r + u, lane);       // unconditional: straight-line, loads overlap
+                        w.ld8(r, lane, t);                                          // unconditional: straight-line, loads overlap
 #pragma unroll
                         for (int u = 0; u < 8; u++) {
                             L.xcur = ((fl >> (8 * u)) & 0xffull) ? t[u] : L.xcur;
