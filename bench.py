@@ -46,7 +46,7 @@ def ncu_traffic(cls=-1):
             if p[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
                 scale = 1e6 if p[1] == "Mbyte" else 1e9 if p[1] == "Gbyte" else 1e3 if p[1] == "Kbyte" else 1.0
                 vals = [float(x) for x in p[2:]]
-                v = (sum(vals) / len(vals) if cls < 0 else vals[cls]) * scale
+                v = (sum(vals) / len(vals) if cls < 0 else vals[1 - cls]) * scale      # r2 file: launch0 = row pass (class 1), launch1 = column pass (class 0)
                 if p[0] == "dram__bytes_read.sum": r = v
                 else: w = v
         return r + w if r is not None and w is not None else None

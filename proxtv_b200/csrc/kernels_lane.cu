@@ -99,6 +99,16 @@ template <> struct SmemIO<float> {
 __device__ __forceinline__ void opaque(double& v) { asm volatile("" : "+d"(v)); }
 __device__ __forceinline__ void opaque(float& v) { asm volatile("" : "+f"(v)); }
 __device__ __forceinline__ void sts_u8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t lds_u8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void sts_u8_pred(uint32_t a, int v, bool p) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q st.shared.u8 [%0], %1;\n\t}" ::"r"(a), "r"(v), "r"((uint32_t)p) : "memory");
+}
+__device__ __forceinline__ void sts_val_pred(uint32_t a, double v, bool p) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q st.shared.f64 [%0], %1;\n\t}" ::"r"(a), "d"(v), "r"((uint32_t)p) : "memory");
+}
+__device__ __forceinline__ void sts_val_pred(uint32_t a, float v, bool p) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q st.shared.f32 [%0], %1;\n\t}" ::"r"(a), "f"(v), "r"((uint32_t)p) : "memory");
+}
 // value + flag byte, both under one predicate (kept as predicated stores: the compiler would otherwise branch around them)
 __device__ __forceinline__ void sts_pred(uint32_t va, double v, uint32_t fa, bool p) {
     asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %3, 0;\n\t@q st.shared.f64 [%0], %1;\n\t@q st.shared.u8 [%2], 1;\n\t}"
@@ -112,12 +122,13 @@ __device__ __forceinline__ void sts_pred(uint32_t va, float v, uint32_t fa, bool
 template <typename T, int W> struct DevWin {
     static constexpr int ROWB = LANES * (int)sizeof(T);          // bytes per window row
     static constexpr uint32_t MASK = (uint32_t)(W * ROWB - 1) & ~(uint32_t)(ROWB - 1);
-    static constexpr int SH = (ROWB == 256) ? 5 : 5;             // (k * ROWB) >> SH == k * sizeof(T): 256 >> 5 = 8, 128 >> 5 = 4
+    static constexpr int SH = (ROWB == 256) ? 5 : 4;             // (k * ROWB) >> SH == k * 8: byte offset into the float64 reciprocal table
     static constexpr int FSH = (ROWB == 256) ? 8 : 7;            // scaled position -> row (positions are exact multiples: arithmetic shift)
     uint32_t wbase;    // shared address of the warp's window (a kernel constant when the CTA is a single warp: folds into the access)
     uint32_t lane8;    // byte offset of this lane's column inside a window row
     uint32_t flg;      // shared address of this lane's flag bytes
     uint32_t rcp;      // shared address of the reciprocal table
+    __device__ __forceinline__ uint32_t flag_at(int pos) const { return flg + (((uint32_t)pos >> FSH) & (uint32_t)(W - 1)); }
     __device__ __forceinline__ uint32_t at(int pos) const {
         uint32_t o;                                    // (pos & MASK) | lane8 in one LOP3 (the two fields never overlap)
         asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(o) : "r"((uint32_t)pos), "r"(MASK), "r"(lane8));
@@ -126,22 +137,21 @@ template <typename T, int W> struct DevWin {
 };
 
 template <bool PH1, typename T, int W>
-__device__ __forceinline__ void run_dev(Lane<T>& L, const DevWin<T, W> dw, const TaskGeom& g, T lam2, int niter) {
+__device__ __forceinline__ void run_dev(Lane<T>& L, const DevWin<T, W> dw, const TaskGeom& g, acc_t lam2, int niter) {
     using DW = DevWin<T, W>;
     constexpr int ROWB = DW::ROWB;
-    T Z = L.Z, lo = L.lo, hi = L.hi;
-    int ia = L.i << DW::FSH, la = L.last << DW::FSH, bloa = L.blo << DW::FSH, bhia = L.bhi << DW::FSH;
-    int kind = L.kind, lprev = L.lprev << DW::FSH, kprev = L.kprev, in_ = L.in_rec;
+    acc_t Z = L.Z, lo = L.lo, hi = L.hi;
+    int ia = L.i << DW::FSH, la = L.last << DW::FSH, bloa = L.blo << DW::FSH, bhia = L.bhi << DW::FSH, in_ = L.in_rec;
     const int cea = g.ce << DW::FSH, csa = g.cs << DW::FSH;
-    T nlam2 = -lam2;
+    acc_t nlam2 = -lam2;
     opaque(nlam2);                                     // keep -2 lam in a register (else it is re-negated every iteration)
 #pragma unroll 1
     for (int it = 0; it < niter; it++) {
-        const T y = SmemIO<T>::ld(dw.at(ia));
+        const acc_t y = (acc_t)SmemIO<T>::ld(dw.at(ia));
         const int ka = ia - la;
-        const T r = SmemIO<T>::ld(dw.rcp + ((uint32_t)ka >> DW::SH));
+        const acc_t r = SmemIO<double>::ld(dw.rcp + ((uint32_t)ka >> DW::SH));
         Z += y;
-        const T cl = Z * r, ch = fma(lam2, r, cl);                  // (Z + 2 lam) r, one operation shorter
+        const acc_t cl = Z * r, ch = fma(lam2, r, cl);              // (Z + 2 lam) r, one operation shorter
         const bool first = (ka == ROWB);
         const bool can = !first & (la < cea);
         const bool craw = lo > ch, fraw = hi < cl;          // both compares issue back to back (neither waits for the other)
@@ -149,225 +159,31 @@ __device__ __forceinline__ void run_dev(Lane<T>& L, const DevWin<T, W> dw, const
         const bool fbk = can & !craw & fraw;
         const bool brk = cbk | fbk;
         const int ea = cbk ? bloa : bhia;
-        const T v = cbk ? lo : hi;
         const int fa = la + ROWB;
-        // emit: the finished segment's value goes to its first (owned) row, plus the flag byte -- two predicated stores
+        // the finished segment's value goes to its first (owned) row; the new segment gets its start mark (kind + 1)
         bool em = brk; int fea = fa;
         if (PH1) {
             em = brk & (ea >= csa);
             fea = fa > csa ? fa : csa;
-            in_ = (em & (in_ == REC_NONE)) ? rec_pack(fa >> DW::FSH, kind) : in_;
+            const uint32_t kf = lds_u8(dw.flag_at(fa));
+            in_ = (em & (in_ == REC_NONE)) ? rec_pack(fa >> DW::FSH, (int)kf - 1) : in_;
+            sts_u8_pred(dw.flag_at(fea), LK_BEGIN + 1, em & (fea != fa));      // clipped: the sweep needs a start mark at cs
         }
         const uint32_t va = dw.at(fea);
-        const uint32_t fla = dw.flg + (((uint32_t)fea >> DW::FSH) & (uint32_t)(W - 1));
-        sts_pred(va, v, fla, em);
+        sts_val_pred(va, (T)lo, em & cbk);
+        sts_val_pred(va, (T)hi, em & fbk);
+        const uint32_t nfl = dw.flag_at(ea + ROWB);
+        sts_u8_pred(nfl, LK_CEIL + 1, cbk);
+        sts_u8_pred(nfl, LK_FLOOR + 1, fbk);
         const bool tlo = first | (cl >= lo), thi = first | (ch <= hi);
         lo = tlo ? cl : lo; bloa = tlo ? ia : bloa;
         hi = thi ? ch : hi; bhia = thi ? ia : bhia;
-        lprev = brk ? la : lprev; kprev = brk ? kind : kprev;
-        kind = cbk ? (int)LK_CEIL : (fbk ? (int)LK_FLOOR : kind);
-        Z = cbk ? T(0) : (fbk ? nlam2 : Z);
+        Z = cbk ? 0.0 : (fbk ? nlam2 : Z);
         ia = (brk ? ea : ia) + ROWB;
         la = brk ? ea : la;
     }
     L.Z = Z; L.lo = lo; L.hi = hi; L.i = ia >> DW::FSH; L.last = la >> DW::FSH; L.blo = bloa >> DW::FSH; L.bhi = bhia >> DW::FSH;
-    L.kind = kind; L.lprev = lprev >> DW::FSH; L.kprev = kprev; L.in_rec = in_;
-}
-
-// The steady-state loop (all lanes past their first owned segment) written in PTX.  On this architecture a scheduler issues one
-// instruction per cycle, but the integer/logic pipe (SEL, FSEL, LOP3, ISETP ...) and the FMA pipe (IMAD, FFMA ...) each accept a
-// warp instruction only every second cycle (B300_MICROARCH.md "fma vs alu split": rt_SMSP = 2).  The C++ form of the step
-// compiles to ~36 integer/logic-pipe instructions out of 53 -- 72 of the ~100 cycles a step takes.  Here every state update of
-// the form `x = p ? a : x` is a PREDICATED MOVE, which the assembler is free to issue on the FMA pipe (IMAD.MOV), so the two
-// pipes share the work and the step approaches the issue limit.  Same arithmetic, same decisions as run_dev<false>.
-template <typename T> struct StepAsm;
-template <> struct StepAsm<double> {
-    static __device__ __forceinline__ void step(double& Z, double& lo, double& hi, int& ia, int& la, int& bloa, int& bhia, int& kind,
-                                                int& lprev, int& kprev, double lam2, double nlam2, int cea, uint32_t mask, uint32_t lw,
-                                                uint32_t rcp, uint32_t flg, uint32_t wm1) {
-        asm volatile(
-            "{\n\t"
-            ".reg .pred first, can, cbk, fbk, brk, tlo, thi;\n\t"
-            ".reg .u32 ad, ka, ra, fa, va, fl;\n\t"
-            ".reg .f64 y, r, cl, ch;\n\t"
-            "lop3.b32 ad, %3, %14, 0, 0xC0;\n\t"            // ad = ia & mask
-            "add.u32 ad, ad, %15;\n\t"                       //    + lane/window base
-            "ld.shared.f64 y, [ad];\n\t"
-            "sub.s32 ka, %3, %4;\n\t"                        // ka = ia - la
-            "shr.u32 ra, ka, 5;\n\t"
-            "add.u32 ra, ra, %16;\n\t"
-            "ld.shared.f64 r, [ra];\n\t"
-            "add.s32 fa, %4, 256;\n\t"                       // first row of the open segment
-            "add.f64 %0, %0, y;\n\t"                         // Z += y
-            "mul.f64 cl, %0, r;\n\t"
-            "fma.rn.f64 ch, %11, r, cl;\n\t"
-            "setp.eq.s32 first, ka, 256;\n\t"
-            "setp.lt.and.s32 can, %4, %13, !first;\n\t"      // breaks allowed: not the first step, segment covering ce not finished
-            "setp.gt.and.f64 cbk, %1, ch, can;\n\t"          // ceiling violation: lo > ch
-            "setp.lt.and.f64 fbk, %2, cl, can;\n\t"          // floor violation:   hi < cl
-            "and.pred fbk, fbk, !cbk;\n\t"
-            "or.pred brk, cbk, fbk;\n\t"
-            "lop3.b32 va, fa, %14, 0, 0xC0;\n\t"
-            "add.u32 va, va, %15;\n\t"
-            "@cbk st.shared.f64 [va], %1;\n\t"               // the finished segment's value at its first row
-            "@fbk st.shared.f64 [va], %2;\n\t"
-            "shr.u32 fl, fa, 8;\n\t"
-            "and.b32 fl, fl, %18;\n\t"
-            "add.u32 fl, fl, %17;\n\t"
-            "@brk st.shared.u8 [fl], 1;\n\t"
-            "setp.ge.or.f64 tlo, cl, %1, first;\n\t"         // touches (evaluated against the old lines)
-            "setp.le.or.f64 thi, ch, %2, first;\n\t"
-            "@brk mov.b32 %8, %4;\n\t"                       // lprev = la ; kprev = kind
-            "@brk mov.b32 %9, %7;\n\t"
-            "@cbk mov.b32 %4, %5;\n\t"                       // la = last touch of the broken line
-            "@fbk mov.b32 %4, %6;\n\t"
-            "@cbk mov.b32 %7, 0;\n\t"                        // kind of the new segment
-            "@fbk mov.b32 %7, 1;\n\t"
-            "@tlo mov.f64 %1, cl;\n\t"
-            "@tlo mov.b32 %5, %3;\n\t"
-            "@thi mov.f64 %2, ch;\n\t"
-            "@thi mov.b32 %6, %3;\n\t"
-            "@brk mov.b32 %3, %4;\n\t"                       // restart right after the break point ...
-            "add.s32 %3, %3, 256;\n\t"                       // ... or advance
-            "@cbk mov.f64 %0, 0d0000000000000000;\n\t"
-            "@fbk mov.f64 %0, %12;\n\t"
-            "}"
-            : "+d"(Z), "+d"(lo), "+d"(hi), "+r"(ia), "+r"(la), "+r"(bloa), "+r"(bhia), "+r"(kind), "+r"(lprev), "+r"(kprev)
-            : "r"(0), "d"(lam2), "d"(nlam2), "r"(cea), "r"(mask), "r"(lw), "r"(rcp), "r"(flg), "r"(wm1)
-            : "memory");
-    }
-};
-template <> struct StepAsm<float> {
-    static __device__ __forceinline__ void step(float& Z, float& lo, float& hi, int& ia, int& la, int& bloa, int& bhia, int& kind,
-                                                int& lprev, int& kprev, float lam2, float nlam2, int cea, uint32_t mask, uint32_t lw,
-                                                uint32_t rcp, uint32_t flg, uint32_t wm1) {
-        asm volatile(
-            "{\n\t"
-            ".reg .pred first, can, cbk, fbk, brk, tlo, thi;\n\t"
-            ".reg .u32 ad, ka, ra, fa, va, fl;\n\t"
-            ".reg .f32 y, r, cl, ch;\n\t"
-            "lop3.b32 ad, %3, %14, 0, 0xC0;\n\t"
-            "add.u32 ad, ad, %15;\n\t"
-            "ld.shared.f32 y, [ad];\n\t"
-            "sub.s32 ka, %3, %4;\n\t"
-            "shr.u32 ra, ka, 5;\n\t"
-            "add.u32 ra, ra, %16;\n\t"
-            "ld.shared.f32 r, [ra];\n\t"
-            "add.s32 fa, %4, 128;\n\t"
-            "add.f32 %0, %0, y;\n\t"
-            "mul.f32 cl, %0, r;\n\t"
-            "fma.rn.f32 ch, %11, r, cl;\n\t"
-            "setp.eq.s32 first, ka, 128;\n\t"
-            "setp.lt.and.s32 can, %4, %13, !first;\n\t"
-            "setp.gt.and.f32 cbk, %1, ch, can;\n\t"
-            "setp.lt.and.f32 fbk, %2, cl, can;\n\t"
-            "and.pred fbk, fbk, !cbk;\n\t"
-            "or.pred brk, cbk, fbk;\n\t"
-            "lop3.b32 va, fa, %14, 0, 0xC0;\n\t"
-            "add.u32 va, va, %15;\n\t"
-            "@cbk st.shared.f32 [va], %1;\n\t"
-            "@fbk st.shared.f32 [va], %2;\n\t"
-            "shr.u32 fl, fa, 7;\n\t"
-            "and.b32 fl, fl, %18;\n\t"
-            "add.u32 fl, fl, %17;\n\t"
-            "@brk st.shared.u8 [fl], 1;\n\t"
-            "setp.ge.or.f32 tlo, cl, %1, first;\n\t"
-            "setp.le.or.f32 thi, ch, %2, first;\n\t"
-            "@brk mov.b32 %8, %4;\n\t"
-            "@brk mov.b32 %9, %7;\n\t"
-            "@cbk mov.b32 %4, %5;\n\t"
-            "@fbk mov.b32 %4, %6;\n\t"
-            "@cbk mov.b32 %7, 0;\n\t"
-            "@fbk mov.b32 %7, 1;\n\t"
-            "@tlo mov.f32 %1, cl;\n\t"
-            "@tlo mov.b32 %5, %3;\n\t"
-            "@thi mov.f32 %2, ch;\n\t"
-            "@thi mov.b32 %6, %3;\n\t"
-            "@brk mov.b32 %3, %4;\n\t"
-            "add.s32 %3, %3, 128;\n\t"
-            "@cbk mov.f32 %0, 0f00000000;\n\t"
-            "@fbk mov.f32 %0, %12;\n\t"
-            "}"
-            : "+f"(Z), "+f"(lo), "+f"(hi), "+r"(ia), "+r"(la), "+r"(bloa), "+r"(bhia), "+r"(kind), "+r"(lprev), "+r"(kprev)
-            : "r"(0), "f"(lam2), "f"(nlam2), "r"(cea), "r"(mask), "r"(lw), "r"(rcp), "r"(flg), "r"(wm1)
-            : "memory");
-    }
-};
-
-template <typename T, int W>
-__device__ __forceinline__ void run_dev_asm(Lane<T>& L, const DevWin<T, W> dw, const TaskGeom& g, T lam2, int niter) {
-    using DW = DevWin<T, W>;
-    T Z = L.Z, lo = L.lo, hi = L.hi;
-    int ia = L.i << DW::FSH, la = L.last << DW::FSH, bloa = L.blo << DW::FSH, bhia = L.bhi << DW::FSH;
-    int kind = L.kind, lprev = L.lprev << DW::FSH, kprev = L.kprev;
-    const int cea = g.ce << DW::FSH;
-    const T nlam2 = -lam2;
-    const uint32_t lw = dw.lane8 + dw.wbase;
-#pragma unroll 1
-    for (int it = 0; it < niter; it++)
-        StepAsm<T>::step(Z, lo, hi, ia, la, bloa, bhia, kind, lprev, kprev, lam2, nlam2, cea, DW::MASK, lw, dw.rcp, dw.flg, (uint32_t)(W - 1));
-    L.Z = Z; L.lo = lo; L.hi = hi; L.i = ia >> DW::FSH; L.last = la >> DW::FSH; L.blo = bloa >> DW::FSH; L.bhi = bhia >> DW::FSH;
-    L.kind = kind; L.lprev = lprev >> DW::FSH; L.kprev = kprev;
-}
-
-// The same loop with the sample and the reciprocal of the NEXT step fetched one step ahead.  The next position is one of three
-// -- the row after the current one (no break), the row after the last floor touch (ceiling break) or after the last ceiling touch
-// (floor break) -- and all three are known at the top of a step, so their loads are issued there and the step ends by selecting
-// among the three values: the shared-memory latency leaves the loop-carried dependency chain (address -> load -> add -> multiply ->
-// compare -> select -> address), which is what bounds a warp's issue rate at two or three resident warps per scheduler.
-template <bool PH1, typename T, int W>
-__device__ __forceinline__ void run_dev_spec(Lane<T>& L, const DevWin<T, W> dw, const TaskGeom& g, T lam2, int niter) {
-    using DW = DevWin<T, W>;
-    constexpr int ROWB = DW::ROWB;
-    T Z = L.Z, lo = L.lo, hi = L.hi;
-    int ia = L.i << DW::FSH, la = L.last << DW::FSH, bloa = L.blo << DW::FSH, bhia = L.bhi << DW::FSH;
-    int kind = L.kind, lprev = L.lprev << DW::FSH, kprev = L.kprev, in_ = L.in_rec;
-    const int cea = g.ce << DW::FSH, csa = g.cs << DW::FSH;
-    T nlam2 = -lam2;
-    opaque(nlam2);
-    T y = SmemIO<T>::ld(dw.at(ia));
-    T r = SmemIO<T>::ld(dw.rcp + ((uint32_t)(ia - la) >> DW::SH));
-#pragma unroll 1
-    for (int it = 0; it < niter; it++) {
-        const int ka = ia - la;
-        // candidates for the next step (addresses depend on nothing computed in this step)
-        const T ynb = SmemIO<T>::ld(dw.at(ia + ROWB));
-        const T ylo = SmemIO<T>::ld(dw.at(bloa + ROWB));
-        const T yhi = SmemIO<T>::ld(dw.at(bhia + ROWB));
-        const T rnb = SmemIO<T>::ld(dw.rcp + ((uint32_t)ka >> DW::SH) + (uint32_t)sizeof(T));
-        Z += y;
-        const T cl = Z * r, ch = fma(lam2, r, cl);
-        const bool first = (ka == ROWB);
-        const bool can = !first & (la < cea);
-        const bool craw = lo > ch, fraw = hi < cl;
-        const bool cbk = can & craw;
-        const bool fbk = can & !craw & fraw;
-        const bool brk = cbk | fbk;
-        const int ea = cbk ? bloa : bhia;
-        const T v = cbk ? lo : hi;
-        const int fa = la + ROWB;
-        bool em = brk; int fea = fa;
-        if (PH1) {
-            em = brk & (ea >= csa);
-            fea = fa > csa ? fa : csa;
-            in_ = (em & (in_ == REC_NONE)) ? rec_pack(fa >> DW::FSH, kind) : in_;
-        }
-        const uint32_t va = dw.at(fea);
-        const uint32_t fla = dw.flg + (((uint32_t)fea >> DW::FSH) & (uint32_t)(W - 1));
-        sts_pred(va, v, fla, em);
-        const bool tlo = first | (cl >= lo), thi = first | (ch <= hi);
-        lo = tlo ? cl : lo; bloa = tlo ? ia : bloa;
-        hi = thi ? ch : hi; bhia = thi ? ia : bhia;
-        lprev = brk ? la : lprev; kprev = brk ? kind : kprev;
-        kind = cbk ? (int)LK_CEIL : (fbk ? (int)LK_FLOOR : kind);
-        Z = cbk ? T(0) : (fbk ? nlam2 : Z);
-        y = cbk ? ylo : (fbk ? yhi : ynb);
-        r = brk ? T(1) : rnb;
-        ia = (brk ? ea : ia) + ROWB;
-        la = brk ? ea : la;
-    }
-    L.Z = Z; L.lo = lo; L.hi = hi; L.i = ia >> DW::FSH; L.last = la >> DW::FSH; L.blo = bloa >> DW::FSH; L.bhi = bhia >> DW::FSH;
-    L.kind = kind; L.lprev = lprev >> DW::FSH; L.kprev = kprev; L.in_rec = in_;
+    L.in_rec = in_;
 }
 
 template <typename T, int W, bool SPEC> struct DevEnv {
@@ -377,9 +193,8 @@ template <typename T, int W, bool SPEC> struct DevEnv {
     template <class F> __device__ __forceinline__ int rmax(F f) { return __reduce_max_sync(0xffffffffu, f(L, lane)); }
     template <class F> __device__ __forceinline__ bool any(F f) { return __any_sync(0xffffffffu, f(L, lane)); }
     __device__ __forceinline__ void sync() { __syncwarp(); }
-    __device__ __forceinline__ void scan(Lane<T>& l, const Window<T, W>&, int, const TaskGeom& g, const T*, T lam2, bool ph1, int niter) {
-        if (SPEC) { if (ph1) run_dev<true, T, W>(l, dw, g, lam2, niter); else run_dev_asm<T, W>(l, dw, g, lam2, niter); }
-        else { if (ph1) run_dev<true, T, W>(l, dw, g, lam2, niter); else run_dev<false, T, W>(l, dw, g, lam2, niter); }
+    __device__ __forceinline__ void scan(Lane<T>& l, const Window<T, W>&, int, const TaskGeom& g, const acc_t*, acc_t lam2, bool ph1, int niter) {
+        if (ph1) run_dev<true, T, W>(l, dw, g, lam2, niter); else run_dev<false, T, W>(l, dw, g, lam2, niter);
     }
 };
 
@@ -419,6 +234,51 @@ template <typename T, int W, int RT, int OP> struct FeedStrided {
 #pragma unroll
             for (int r = 0; r < R; r++) wr[r * LANES + lane] = PassOp<T, OP>::in(wr[r * LANES + lane], sb[r * LANES + lane], sc[r * LANES + lane]);
         }
+        __syncwarp();
+        return true;
+    }
+};
+
+// Fused forms without shared-memory staging of the B / C operands: the A tile (Y) still arrives by TMA, B and C (x_cols, t) are
+// fetched by the lanes themselves -- a window row is one coalesced 256-byte line -- into registers when the tile is requested,
+// one epoch before it is taken over, so their latency is covered by the scan in between.  Saves 8 KB of shared memory per
+// warp (11 resident warps per SM instead of 8) for 32 registers; one tile outstanding at a time.
+template <typename T, int W, int RT, int OP> struct FeedStridedReg {
+    static constexpr int R = RT;
+    static constexpr int MAXQ = 1;
+    static constexpr int NBAR = W / RT;
+    const LaneArgs<T>* a; T* win; uint64_t* bar; int x0, z, q0, lane; long long gbase, stride; bool valid; int n;
+    T fb[RT], fc[RT];
+    template <class Env> __device__ __forceinline__ void request(Env&, int row0) {
+        __syncwarp();
+        if (lane == 0) {
+            fence_proxy_async();
+            const int q = (int)((unsigned)row0 / (unsigned)R) - q0;
+            uint64_t* b = bar + ((unsigned)q % (unsigned)NBAR);
+            mbar_expect_tx(b, (uint32_t)(R * LANES * sizeof(T)));
+            tma_load_3d(win + ((row0 & (W - 1)) << 5), &a->tmA, x0, row0, z, b);
+        }
+        if (valid) {
+            const long long g0 = gbase + (long long)row0 * stride;
+            const T* __restrict__ qb = a->B + g0; const T* __restrict__ qc = a->C + g0;
+#pragma unroll
+            for (int u = 0; u < R; u++) {
+                const bool in = row0 + u < n;
+                fb[u] = in ? __ldg(qb) : T(0); fc[u] = in ? __ldg(qc) : T(0);
+                qb += stride; qc += stride;
+            }
+        }
+    }
+    template <class Env> __device__ __forceinline__ bool landed(Env&, int row0, bool block) {
+        const unsigned q = (unsigned)row0 / (unsigned)R - (unsigned)q0;
+        uint64_t* b = bar + (q % (unsigned)NBAR);
+        const uint32_t parity = (uint32_t)((q / (unsigned)NBAR) & 1u);
+        bool ok = __all_sync(0xffffffffu, mbar_test(b, parity));
+        if (!ok && !block) return false;
+        while (!ok) ok = __all_sync(0xffffffffu, mbar_try(b, parity));
+        T* wr = win + ((row0 & (W - 1)) << 5);
+#pragma unroll
+        for (int r = 0; r < R; r++) wr[r * LANES + lane] = PassOp<T, OP>::in(wr[r * LANES + lane], fb[r], fc[r]);
         __syncwarp();
         return true;
     }
@@ -546,40 +406,50 @@ template <typename T, int W> struct DrainContig {
 
 // ---------------------------------------------------------------- the kernel
 enum LaneLayout { LAY_STRIDED = 0, LAY_CONTIG = 1 };
-template <typename T, int W, int RT, int OP, int LAY> struct LaneSmem {
+template <typename T, int W, int RT, int OP, int LAY, bool REGOP = false> struct LaneSmem {
     static constexpr int NST = 2;
     static constexpr size_t win_bytes = (size_t)W * LANES * sizeof(T);
-    static constexpr size_t stg_bytes = LAY == LAY_CONTIG ? 4096 : ((OP == LOP_PLAIN) ? 0 : (size_t)2 * NST * RT * LANES * sizeof(T));
+    static constexpr size_t stg_bytes = LAY == LAY_CONTIG ? 4096 : ((OP == LOP_PLAIN || REGOP) ? 0 : (size_t)2 * NST * RT * LANES * sizeof(T));
     static constexpr size_t flg_bytes = ((size_t)LANES * (W + 8) + 127) / 128 * 128;
     static constexpr size_t bar_bytes = 128;            // W / RT <= 16 barriers
     static constexpr size_t align = LAY == LAY_CONTIG ? 1024 : 128;       // swizzled boxes need 1 KB aligned tiles
     static constexpr size_t per_warp = (win_bytes + stg_bytes + flg_bytes + bar_bytes + align - 1) / align * align;
-    static constexpr size_t rcp_bytes = ((W + 2) * sizeof(T) + align - 1) / align * align;
+    static constexpr size_t rcp_bytes = ((W + 2) * sizeof(acc_t) + align - 1) / align * align;
 };
 
-// repair: exact sequential continuation in global memory (rare; kept out of line so it does not cost the scan registers)
-template <typename T, int OP>
-__device__ __noinline__ int repair_fiber(const LaneArgs<T>* a, long long fiber, long long gbase, long long stride, long long nfp) {
+// repair of ONE fiber: exact sequential continuation from the last verified renewal state (verify_repair_fiber).  Executed by all
+// 32 lanes of the warp redundantly and in lock step (same records, same decisions), so that the staging can be cooperative: before
+// each repair scan the lanes copy the next NB rows of the fiber -- with the pass's input arithmetic applied -- into the warp's
+// window memory, and the scan reads them from there (a dependent global load per step would cost ~1 us each); rows beyond the
+// staged range fall back to global memory.  Lane 0 writes the results.  Rare: a handful of fibers per solve.
+template <typename T, int OP, int NB>
+__device__ __noinline__ int repair_fiber(const LaneArgs<T>* a, long long fiber, long long gbase, long long stride, long long nfp, T* buf,
+                                         int lane) {
     const ChunkPlan pl = a->plan;
     const int* rec = a->rec;
-    const long long cstride = nfp;
     const T* A = a->A; const T* B = a->B; const T* C = a->C; T* X = a->X;
+    int buf_lo = 0, buf_n = 0;
+    auto in_at = [&](int r) { const long long g = gbase + (long long)r * stride;
+                              return OP == LOP_PLAIN ? A[g] : PassOp<T, OP>::in(A[g], B[g], C[g]); };
     return verify_repair_fiber<T>(pl, a->lam,
-        [&](int c) { return rec[(0 * (long long)pl.nchunks + c) * cstride + fiber]; },
-        [&](int c) { return rec[(1 * (long long)pl.nchunks + c) * cstride + fiber]; },
-        [&](int c) { return rec[(2 * (long long)pl.nchunks + c) * cstride + fiber]; },
-        [&](int r) { const long long g = gbase + (long long)r * stride;
-                     return OP == LOP_PLAIN ? A[g] : PassOp<T, OP>::in(A[g], B[g], C[g]); },
-        [&](int r, T v) { const long long g = gbase + (long long)r * stride;
-                          X[g] = OP == LOP_DR_B ? PassOp<T, OP>::out(v, B[g], C[g]) : v; });
+        [&](int c) { return rec[(0 * (long long)pl.nchunks + c) * nfp + fiber]; },
+        [&](int c) { return rec[(1 * (long long)pl.nchunks + c) * nfp + fiber]; },
+        [&](int c) { return rec[(2 * (long long)pl.nchunks + c) * nfp + fiber]; },
+        [&](int pos) { __syncwarp();
+                       buf_lo = pos; buf_n = pl.n - pos < NB ? pl.n - pos : NB;
+                       for (int j = lane; j < buf_n; j += 32) buf[j] = in_at(pos + j);
+                       __syncwarp(); },
+        [&](int r) { const int j = r - buf_lo; return (j >= 0 && j < buf_n) ? buf[j] : in_at(r); },
+        [&](int r, T v) { if (lane == 0) { const long long g = gbase + (long long)r * stride;
+                                           X[g] = OP == LOP_DR_B ? PassOp<T, OP>::out(v, B[g], C[g]) : v; } });
 }
 
 template <typename T, int W, int RT, int TITER, int OP, int NW, int LAY, bool SPEC>
 __global__ void __launch_bounds__(NW * 32, (12 + NW - 1) / NW) k_lane(const __grid_constant__ LaneArgs<T> a) {
-    using SM = LaneSmem<T, W, RT, OP, LAY>;
+    using SM = LaneSmem<T, W, RT, OP, LAY, SPEC>;
     extern __shared__ __align__(1024) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    T* rcp = reinterpret_cast<T*>(smem);
+    acc_t* rcp = reinterpret_cast<acc_t*>(smem);
     unsigned char* wb = smem + SM::rcp_bytes + (size_t)warp * SM::per_warp;
     T* win = reinterpret_cast<T*>(wb);
     T* stB = reinterpret_cast<T*>(wb + SM::win_bytes);
@@ -587,7 +457,7 @@ __global__ void __launch_bounds__(NW * 32, (12 + NW - 1) / NW) k_lane(const __gr
     uint8_t* flg = wb + SM::win_bytes + SM::stg_bytes;
     uint64_t* bar = reinterpret_cast<uint64_t*>(wb + SM::win_bytes + SM::stg_bytes + SM::flg_bytes);
 
-    for (int k = threadIdx.x; k < W + 2; k += NW * 32) rcp[k] = k ? T(1) / T(k) : T(0);
+    for (int k = threadIdx.x; k < W + 2; k += NW * 32) rcp[k] = k ? 1.0 / (acc_t)k : 0.0;
     const long long task = (long long)blockIdx.x * NW + warp;
     const bool has_task = task < a.ntasks;
     if (has_task) {
@@ -611,13 +481,19 @@ __global__ void __launch_bounds__(NW * 32, (12 + NW - 1) / NW) k_lane(const __gr
     const long long nfp = (long long)a.slabs * a.gps * LANES;
     const long long fiber = group * LANES + lane;
 
-    DevEnv<T, W, SPEC> env; env.lane = lane; env.L.init(g, a.lam, valid);
+    DevEnv<T, W, SPEC> env; env.lane = lane; 
     env.dw.wbase = s32(win); env.dw.lane8 = lane * (uint32_t)sizeof(T); env.dw.flg = s32(flg) + lane * (uint32_t)Window<T, W>::FP; env.dw.rcp = s32(rcp);
     Window<T, W> w{win, flg};
+    env.L.init(w, lane, g, a.lam, valid);
     if (LAY == LAY_CONTIG) {
         FeedContig<T, W> feed{&a, win, bar, x0, g.p0 / FeedContig<T, W>::R, lane};
         DrainContig<T, W> drain{&a, stB, x0, lane, g.ce};
         warp_task<T, W, TITER>(env, feed, drain, w, rcp, g, a.lam, TITER + TITER / 2 + FeedContig<T, W>::R, (TaskStats*)nullptr);
+    } else if (SPEC && OP != LOP_PLAIN) {
+        FeedStridedReg<T, W, RT, OP> feed; feed.a = &a; feed.win = win; feed.bar = bar; feed.x0 = x0; feed.z = z; feed.q0 = g.p0 / RT; feed.lane = lane;
+        feed.gbase = gbase; feed.stride = a.inc; feed.valid = valid; feed.n = pl.n;
+        DrainStrided<T, W, OP> drain; drain.B = a.B; drain.C = a.C; drain.X = a.X; drain.gbase = gbase; drain.stride = a.inc; drain.pf_row = -1;
+        warp_task<T, W, TITER>(env, feed, drain, w, rcp, g, a.lam, TITER + TITER / 2 + RT, (TaskStats*)nullptr);
     } else {
         FeedStrided<T, W, RT, OP> feed{&a, win, stB, stC, bar, x0, z, g.p0 / RT, lane};
         DrainStrided<T, W, OP> drain; drain.B = a.B; drain.C = a.C; drain.X = a.X; drain.gbase = gbase; drain.stride = a.inc; drain.pf_row = -1;
@@ -649,10 +525,15 @@ __global__ void __launch_bounds__(NW * 32, (12 + NW - 1) / NW) k_lane(const __gr
             bad |= (c > 0 && ri != ro) || rv != REC_NONE;
         }
     }
-    if (bad) {
-        const int n = repair_fiber<T, OP>(&a, fiber, gbase, gstride, nfp);
-        if (n) atomicAdd(a.stats, (unsigned long long)n);
+    // the fibers that need it are repaired one after the other, by the whole warp (see repair_fiber)
+    unsigned m = __ballot_sync(0xffffffffu, bad);
+    int nrep = 0;
+    while (m) {
+        const int src = __ffs(m) - 1; m &= m - 1;
+        const long long gb = __shfl_sync(0xffffffffu, gbase, src);
+        nrep += repair_fiber<T, OP, W * LANES>(&a, group * LANES + src, gb, gstride, nfp, win, lane);
     }
+    if (nrep && lane == 0) atomicAdd(a.stats, (unsigned long long)nrep);
 }
 
 // ---------------------------------------------------------------- host side
@@ -687,17 +568,22 @@ struct LaneTuning { int clen, halo, variant; };
 static LaneTuning g_tune = {0, 32, 0};
 void lane_set_tuning(int clen, int halo, int variant) { g_tune.clen = clen; g_tune.halo = halo; g_tune.variant = variant; }
 
-long long lane_scratch_bytes(long long nf, int len) {
-    // records for the finest chunking the launcher may choose (chunks of >= 64 rows) + group counters + stats
+// Scratch of the lane engine, one buffer per device (grow-only, zero-initialised when (re)allocated):
+//     [stats 64 B][group counters: cap_groups ints][chunk records]
+// The counters must be zero between launches (the last warp of a group resets its counter), so their region has a FIXED size per
+// allocation -- it must never overlap what an earlier launch with fewer groups used for records.
+struct LaneScratch { void* p = nullptr; size_t cap = 0; long long cap_groups = 0; };
+static LaneScratch g_scr[64];
+static long long lane_scratch_bytes(long long groups_cap, long long nf, int len) {
     const long long nfp = (nf + 31) / 32 * 32 + 32 * 64;
     const long long maxchunks = len / 64 + 2;
-    return 3 * maxchunks * nfp * 4 + (nfp / 32 + 128) * 4 + 64;
+    return 64 + groups_cap * 4 + 3 * maxchunks * nfp * 4 + 256;
 }
 
 // launch one instantiation; with `slots` only report how many warp tasks the device can hold at once
 template <typename T, int W, int RT, int TITER, int OP, int NW, int LAY, bool SPEC>
 static cudaError_t launch_v(LaneArgs<T>& a, cudaStream_t st, int* slots) {
-    using SM = LaneSmem<T, W, RT, OP, LAY>;
+    using SM = LaneSmem<T, W, RT, OP, LAY, SPEC>;
     auto kern = k_lane<T, W, RT, TITER, OP, NW, LAY, SPEC>;
     const size_t smem = SM::rcp_bytes + (size_t)NW * SM::per_warp;
     static int s_slots = 0;                      // per instantiation: resident warps on the current device
@@ -787,10 +673,13 @@ cudaError_t lane_prox(int op, const T* A, const T* B, const T* C, T* X, long lon
     a.plan.n = len; a.plan.halo = halo;
     if (clen >= len) { a.plan.clen = len; a.plan.nchunks = 1; } else { a.plan.clen = clen; a.plan.nchunks = (len + clen - 1) / clen; }
     if (a.plan.nchunks > len / 64 + 2) return cudaErrorInvalidConfiguration;
-    // scratch layout (fixed places, whatever the chunking): [stats 64 B][group counters, zero between launches][records]
-    a.stats = (unsigned long long*)scratch;
-    a.group_count = (int*)((char*)scratch + 64);
-    a.rec = a.group_count + ((groups + 63) / 64) * 64;
+    {
+        int d = 0; cudaGetDevice(&d);
+        if (d < 0 || d >= 64 || scratch != g_scr[d].p || groups > g_scr[d].cap_groups) return cudaErrorInvalidValue;      // not lane_scratch()'s buffer
+        a.stats = (unsigned long long*)scratch;
+        a.group_count = (int*)((char*)scratch + 64);
+        a.rec = a.group_count + g_scr[d].cap_groups;
+    }
     a.ntasks = groups * a.plan.nchunks;
     return launch_any<T>(lay, op, g_tune.variant, a, st, nullptr);
 }
@@ -804,17 +693,16 @@ bool lane_shape_ok(long long nf, int len, long long inc, size_t elem, const void
     return encode_fn() != nullptr;
 }
 
-// per-device scratch for the records (grow-only, zero-initialised: the group counters must start at 0 and reset themselves)
-struct LaneScratch { void* p = nullptr; size_t cap = 0; };
-static LaneScratch g_scr[64];
 void* lane_scratch(long long nf, int len) {
     int d = 0; if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return nullptr;
-    const size_t need = (size_t)lane_scratch_bytes(nf, len);
     LaneScratch& s = g_scr[d];
-    if (need > s.cap) {
+    const long long groups = nf + 64;                   // upper bound on the fiber groups of any slicing of nf fibers
+    const long long gcap = groups > s.cap_groups ? groups : s.cap_groups;
+    const size_t need = (size_t)lane_scratch_bytes(gcap, nf, len);
+    if (need > s.cap || groups > s.cap_groups) {
         if (s.p) { cudaDeviceSynchronize(); cudaFree(s.p); s.p = nullptr; s.cap = 0; }
-        if (cudaMalloc(&s.p, need) != cudaSuccess) { cudaGetLastError(); s.p = nullptr; return nullptr; }
-        cudaMemset(s.p, 0, need); s.cap = need;
+        if (cudaMalloc(&s.p, need) != cudaSuccess) { cudaGetLastError(); s.p = nullptr; s.cap_groups = 0; return nullptr; }
+        cudaMemset(s.p, 0, need); s.cap = need; s.cap_groups = gcap;
     }
     return s.p;
 }

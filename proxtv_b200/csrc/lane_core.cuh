@@ -45,11 +45,10 @@ PTV_HD int rec_pack(int pos, int kind) { return pos * 4 + kind; }
 PTV_HD int rec_pos(int r) { return r >> 2; }
 PTV_HD int rec_kind(int r) { return r & 3; }
 
-template <typename T> struct LaneEps { };
-template <> struct LaneEps<double> { static PTV_HD double v() { return 1e-10; } };    // src/general.h:64
-template <> struct LaneEps<float>  { static PTV_HD float  v() { return 1e-10f; } };
-
-template <typename T> PTV_HD T z_of_kind(int kind, T lam) { return kind == LK_CEIL ? T(0) : (kind == LK_FLOOR ? T(-2) * lam : -lam); }
+// All scan arithmetic is carried in float64 whatever the storage type: a float32 array is read, accumulated and compared in
+// double and only the results are rounded to float32 (the reference itself upcasts float32 input, prox_tv/__init__.py:118-121).
+typedef double acc_t;
+PTV_HD acc_t z_of_kind(int kind, acc_t lam) { return kind == LK_CEIL ? 0.0 : (kind == LK_FLOOR ? -2.0 * lam : -lam); }
 
 // ------------------------------------------------------------------------------------------------------------------
 // Exact sequential scan in slope form from a renewal state, generic over how samples are read and results written.
@@ -58,42 +57,42 @@ template <typename T> PTV_HD T z_of_kind(int kind, T lam) { return kind == LK_CE
 //   seg(f, e, v, kind) called for every finished segment [f, e] with value v whose start has `kind`; returns true to stop
 // Starts at position `pos` with a segment of kind `kind` beginning there; runs to the end of the fiber (n) unless stopped.
 template <typename T, class Ld, class Seg>
-PTV_HD void slope_seq(int n, T lam, int pos, int kind, Ld ld, Seg seg) {
-    const T lam2 = T(2) * lam;
+PTV_HD void slope_seq(int n, T lam_, int pos, int kind, Ld ld, Seg seg) {
+    const acc_t lam = (acc_t)lam_, lam2 = 2.0 * lam, eps = 1e-10;      // src/general.h:64
     int last = pos - 1, i = pos, blo = pos, bhi = pos, kcur = kind;
-    T Z = z_of_kind<T>(kind, lam), lo = T(0), hi = T(0);
+    acc_t Z = z_of_kind(kind, lam), lo = 0.0, hi = 0.0;
     while (i < n) {
-        Z += ld(i);
+        Z += (acc_t)ld(i);
         const int k = i - last;
-        const T r = T(1) / T(k);
+        const acc_t r = 1.0 / (acc_t)k;
         if (i < n - 1) {
-            const T cl = Z * r, ch = (Z + lam2) * r;
+            const acc_t cl = Z * r, ch = fma(lam2, r, cl);
             if (k == 1) { lo = cl; hi = ch; blo = bhi = i; i++; continue; }
             if (lo > ch) {                                   // ceiling violation (hybridtautstring.cpp:93-111)
-                if (seg(last + 1, blo, lo, kcur)) return;
-                last = blo; i = blo + 1; Z = T(0); kcur = LK_CEIL; continue;
+                if (seg(last + 1, blo, (T)lo, kcur)) return;
+                last = blo; i = blo + 1; Z = 0.0; kcur = LK_CEIL; continue;
             }
             if (hi < cl) {                                   // floor violation (:119-137)
-                if (seg(last + 1, bhi, hi, kcur)) return;
+                if (seg(last + 1, bhi, (T)hi, kcur)) return;
                 last = bhi; i = bhi + 1; Z = -lam2; kcur = LK_FLOOR; continue;
             }
             if (cl >= lo) { lo = cl; blo = i; }              // (:153-160)
             if (ch <= hi) { hi = ch; bhi = i; }              // (:143-150)
             i++;
         } else {                                             // last sample: the tube closes on its centre (:169-224)
-            const T c = Z + lam;
-            if (k == 1) { seg(last + 1, i, c, kcur); return; }
-            const T hl = lo * T(k) - c, hh = hi * T(k) - c;
-            if (hl > LaneEps<T>::v()) {
-                if (seg(last + 1, blo, lo, kcur)) return;
-                last = blo; i = blo + 1; Z = T(0); kcur = LK_CEIL; continue;
+            const acc_t c = Z + lam;
+            if (k == 1) { seg(last + 1, i, (T)c, kcur); return; }
+            const acc_t hl = lo * (acc_t)k - c, hh = hi * (acc_t)k - c;
+            if (hl > eps) {
+                if (seg(last + 1, blo, (T)lo, kcur)) return;
+                last = blo; i = blo + 1; Z = 0.0; kcur = LK_CEIL; continue;
             }
-            if (hh < -LaneEps<T>::v()) {
-                if (seg(last + 1, bhi, hi, kcur)) return;
+            if (hh < -eps) {
+                if (seg(last + 1, bhi, (T)hi, kcur)) return;
                 last = bhi; i = bhi + 1; Z = -lam2; kcur = LK_FLOOR; continue;
             }
-            if (hl <= T(0)) lo = c * r;
-            seg(last + 1, i, lo, kcur);
+            if (hl <= 0.0) lo = c * r;
+            seg(last + 1, i, (T)lo, kcur);
             return;
         }
     }
@@ -102,7 +101,8 @@ PTV_HD void slope_seq(int n, T lam, int pos, int kind, Ld ld, Seg seg) {
 // ------------------------------------------------------------------------------------------------------------------
 // Shared-memory window of one warp: W rows (power of two) of 32 samples [row][lane], and one flag byte per slot kept per
 // lane ([lane][row], lane pitch W + 8 bytes: a lane's 8 consecutive flags are one aligned 8-byte word and the 32 lanes' words
-// of the same row group fall into 32 different banks).
+// of the same row group fall into different banks).  A flag byte is 0, or kind + 1 of the segment that STARTS at that row
+// (written when the break that creates the segment is taken); the segment's value is stored at the same row when it is finished.
 template <typename T, int W> struct Window {
     static constexpr int FP = W + 8;       // flag pitch per lane (bytes): 8-byte aligned rows, 18-word lane stride spreads the banks
     T* win;            // [W][32]
@@ -115,7 +115,8 @@ template <typename T, int W> struct Window {
 #pragma unroll
         for (int u = 0; u < 8; u++) t[u] = p[u * LANES];
     }
-    PTV_HD void set_flag(int row, int lane) const { flg[lane * FP + (row & (W - 1))] = 1; }
+    PTV_HD void set_flag(int row, int lane, int f) const { flg[lane * FP + (row & (W - 1))] = (uint8_t)f; }
+    PTV_HD int flag(int row, int lane) const { return flg[lane * FP + (row & (W - 1))]; }
     // the 8 flags of the aligned row group that starts at row0 (row0 % 8 == 0), and clearing them
     PTV_HD unsigned long long flags8(int row0, int lane) const {
         return *reinterpret_cast<const unsigned long long*>(flg + lane * FP + (row0 & (W - 1)));
@@ -132,12 +133,10 @@ struct TaskGeom {
     int p0;         // cold-start row (0: the true start of the fiber)
 };
 
-// Scan state of one lane.
+// Scan state of one lane.  The kind of every segment start lives in the window's flag bytes, so the loop carries positions only.
 template <typename T> struct Lane {
-    T Z, lo, hi;
+    acc_t Z, lo, hi;
     int i, last, blo, bhi;
-    int kind;             // kind of the current (open) segment's start
-    int lprev, kprev;     // `last` and `kind` before the most recent break: start and kind of the most recently finished segment
     int in_rec, out_rec;  // (start, kind) of the first emitted segment / of the finished segment that covers row ce
     bool done;            // finished (or retired); nothing more to scan
     bool valid;           // the lane has a fiber
@@ -145,62 +144,73 @@ template <typename T> struct Lane {
     int ovf_rec;
     T xcur;               // value carried by the sweep
 
-    PTV_HD void init(const TaskGeom& g, T lam, bool is_valid) {
-        i = g.p0; last = g.p0 - 1; blo = bhi = g.p0; kind = LK_BEGIN; lprev = last; kprev = LK_BEGIN;
-        Z = -lam; lo = hi = T(0);
+    template <int W>
+    PTV_HD void init(const Window<T, W>& w, int lane, const TaskGeom& g, T lam, bool is_valid) {
+        i = g.p0; last = g.p0 - 1; blo = bhi = g.p0;
+        Z = -(acc_t)lam; lo = hi = 0.0;
         in_rec = out_rec = ovf_rec = REC_NONE;
         valid = is_valid; done = !is_valid; retired = false; xcur = T(0);
+        w.set_flag(g.p0, lane, LK_BEGIN + 1);           // the (cold) start of the scan is a segment start of kind BEGIN
     }
 
     // `niter` scan steps, no bounds checks: the caller guarantees i + niter <= frontier (and <= n - 1: the last sample is never
     // processed here).  Straight-line and branch-free by design -- every lane of a warp executes the same instructions whether it
-    // advances, touches or breaks (a break is a handful of selects plus one predicated store), so the lanes of a warp never diverge.
+    // advances, touches or breaks (a break is a handful of selects plus predicated stores), so the lanes of a warp never diverge.
     // Once the segment that covers row ce is finished (last >= ce) breaks are disabled and the lane only coasts; the epoch loop
     // retires it.  PH1: the lane may still be in front of its first owned segment (clip to cs, record the entry state).
     template <bool PH1, int W>
-    PTV_HD void run(const Window<T, W>& w, int lane, const TaskGeom& g, const T* __restrict__ rcp, T lam2, int niter) {
-        T Z_ = Z, lo_ = lo, hi_ = hi;
-        int i_ = i, last_ = last, blo_ = blo, bhi_ = bhi, kind_ = kind, lprev_ = lprev, kprev_ = kprev, in_ = in_rec;
-        const T nlam2 = -lam2;
+    PTV_HD void run(const Window<T, W>& w, int lane, const TaskGeom& g, const acc_t* __restrict__ rcp, acc_t lam2, int niter) {
+        acc_t Z_ = Z, lo_ = lo, hi_ = hi;
+        int i_ = i, last_ = last, blo_ = blo, bhi_ = bhi, in_ = in_rec;
+        const acc_t nlam2 = -lam2;
         for (int it = 0; it < niter; it++) {
-            const T y = w.ld(i_, lane);
+            const acc_t y = (acc_t)w.ld(i_, lane);
             const int k = i_ - last_;
-            const T r = rcp[k];
+            const acc_t r = rcp[k];
             Z_ += y;
-            const T cl = Z_ * r, ch = fma(lam2, r, cl);          // (Z + 2 lam) r
+            const acc_t cl = Z_ * r, ch = fma(lam2, r, cl);      // (Z + 2 lam) r
             const bool first = (k == 1);
             const bool can = !first & (last_ < g.ce);
             const bool cbk = can & (lo_ > ch);
             const bool fbk = can & !cbk & (hi_ < cl);
             const bool brk = cbk | fbk;
             const int e = cbk ? blo_ : bhi_;
-            const T v = cbk ? lo_ : hi_;
+            const T v = (T)(cbk ? lo_ : hi_);
             const int f = last_ + 1;
             if (PH1) {
                 if (brk & (e >= g.cs)) {
-                    if (in_ == REC_NONE) in_ = rec_pack(f, kind_);
+                    if (in_ == REC_NONE) in_ = rec_pack(f, w.flag(f, lane) - 1);
                     const int fe = f > g.cs ? f : g.cs;
-                    w.st(fe, lane, v); w.set_flag(fe, lane);
+                    w.st(fe, lane, v);
+                    if (fe != f) w.set_flag(fe, lane, LK_BEGIN + 1);      // clipped: the sweep needs a start mark at cs
                 }
             } else {
-                if (brk) { w.st(f, lane, v); w.set_flag(f, lane); }
+                if (brk) w.st(f, lane, v);
             }
+            if (brk) w.set_flag(e + 1, lane, cbk ? LK_CEIL + 1 : LK_FLOOR + 1);      // the new segment: start mark + kind
             const bool tlo = first | (cl >= lo_), thi = first | (ch <= hi_);
             lo_ = tlo ? cl : lo_; blo_ = tlo ? i_ : blo_;
             hi_ = thi ? ch : hi_; bhi_ = thi ? i_ : bhi_;
-            lprev_ = brk ? last_ : lprev_; kprev_ = brk ? kind_ : kprev_;
-            kind_ = cbk ? (int)LK_CEIL : (fbk ? (int)LK_FLOOR : kind_);
-            Z_ = cbk ? T(0) : (fbk ? nlam2 : Z_);
+            Z_ = cbk ? 0.0 : (fbk ? nlam2 : Z_);
             i_ = brk ? e + 1 : i_ + 1;
             last_ = brk ? e : last_;
         }
-        Z = Z_; lo = lo_; hi = hi_; i = i_; last = last_; blo = blo_; bhi = bhi_; kind = kind_; lprev = lprev_; kprev = kprev_; in_rec = in_;
+        Z = Z_; lo = lo_; hi = hi_; i = i_; last = last_; blo = blo_; bhi = bhi_; in_rec = in_;
     }
 
-    // after run(): has the segment that covers row ce been finished?
-    PTV_HD void settle(const TaskGeom& g) {
-        if (!done && last >= g.ce) { done = true; out_rec = rec_pack(lprev + 1, kprev); }
+    // after run(): has the segment that covers row ce been finished?  Its start is the last start mark at or before ce.
+    template <int W>
+    PTV_HD void settle(const Window<T, W>& w, int lane, const TaskGeom& g) {
+        if (done || last < g.ce) return;
+        done = true;
+        int r = g.ce;
+        while (w.flag(r, lane) == 0) r--;                 // terminates: the segment's start lies inside the window
+        const bool clipped = (r == g.cs) && in_rec != REC_NONE && rec_pos(in_rec) < g.cs;     // one segment spans the whole chunk
+        out_rec = clipped ? in_rec : rec_pack(r, w.flag(r, lane) - 1);
     }
+
+    // renewal state of the open segment (for retirement)
+    template <int W> PTV_HD int open_rec(const Window<T, W>& w, int lane) const { return rec_pack(last + 1, w.flag(last + 1, lane) - 1); }
 
     // the fiber's last sample is inside the window and this lane waits in front of it: finish sequentially (closing rule)
     template <int W>
@@ -208,13 +218,13 @@ template <typename T> struct Lane {
         if (done) return;
         Lane<T>* self = this;
         // continue from the renewal state of the open segment: exact, and short (the open segment lies inside the window)
-        slope_seq<T>(g.n, lam, last + 1, kind,
+        slope_seq<T>(g.n, lam, last + 1, w.flag(last + 1, lane) - 1,
                      [&](int r) { return w.ld(r, lane); },
                      [&](int f, int e, T v, int k) {
                          if (e >= g.cs) {
                              if (self->in_rec == REC_NONE) self->in_rec = rec_pack(f, k);
                              const int fe = f > g.cs ? f : g.cs;
-                             w.st(fe, lane, v); w.set_flag(fe, lane);
+                             w.st(fe, lane, v); w.set_flag(fe, lane, k + 1);
                              if (e >= g.ce) { self->done = true; self->out_rec = rec_pack(f, k); }
                          }
                          return self->done; });
@@ -232,11 +242,11 @@ template <typename T> struct Lane {
 struct TaskStats { int epochs, retired, tail, iters; };
 
 template <typename T, int W, int TITER, class Env, class Feed, class Drain>
-PTV_HD void warp_task(Env& env, Feed& feed, Drain& drain, const Window<T, W>& w, const T* __restrict__ rcp, const TaskGeom g, T lam,
+PTV_HD void warp_task(Env& env, Feed& feed, Drain& drain, const Window<T, W>& w, const acc_t* __restrict__ rcp, const TaskGeom g, T lam,
                       int ahead, TaskStats* stats) {
     constexpr int R = Feed::R;
     constexpr int DMIN = 8;           // lanes closer than this to the frontier sit an epoch out rather than shorten it for everybody
-    const T lam2 = T(2) * lam;
+    const acc_t lam2 = 2.0 * (acc_t)lam;
     int row_lo = g.p0;                // first row still held by the window
     int row_req = g.p0;               // rows below have been requested
     int row_hi = g.p0;                // rows below are in the window, ready for the scan
@@ -280,6 +290,13 @@ PTV_HD void warp_task(Env& env, Feed& feed, Drain& drain, const Window<T, W>& w,
             if (nlo > fill_pos && fill_pos < g.ce) nlo = fill_pos;      // rows not swept yet (partial group) stay
             const int hold = drain.hold(fill_pos, g.ce);
             if (nlo > hold) nlo = hold;
+            if (row_lo < g.cs) {
+                // halo rows are never swept: their start marks are wiped when they leave the window (whole groups of 8),
+                // before their slots are reused by owned rows
+                nlo = nlo < g.cs ? (nlo & ~7) : nlo;
+                const int c1 = nlo < g.cs ? nlo : g.cs;
+                if (c1 > row_lo) { const int c0 = row_lo; env.each([&](Lane<T>&, int lane) { for (int r = c0; r < c1; r += 8) w.clear8(r, lane); }); }
+            }
             if (nlo > row_lo) row_lo = nlo;
         }
         if (all_done) break;
@@ -312,8 +329,8 @@ PTV_HD void warp_task(Env& env, Feed& feed, Drain& drain, const Window<T, W>& w,
                 // stuck: nothing pending, nothing more fits -> retire the lanes that pin the window
                 const bool can_feed = (row_req < g.n) && (row_req + R <= row_lo + W) && (row_req - row_hi < Feed::MAXQ * R);
                 if (!can_feed) {
-                    env.each([&](Lane<T>& L, int) {
-                        if (!L.done && L.last + 1 == low) { L.done = true; L.retired = true; L.ovf_rec = rec_pack(L.last + 1, L.kind); }
+                    env.each([&](Lane<T>& L, int lane_) {
+                        if (!L.done && L.last + 1 == low) { L.done = true; L.retired = true; L.ovf_rec = L.template open_rec<W>(w, lane_); }
                     });
                     if (stats) stats->retired++;
                 }
@@ -327,7 +344,7 @@ PTV_HD void warp_task(Env& env, Feed& feed, Drain& drain, const Window<T, W>& w,
             env.each([&](Lane<T>& L, int lane) {
                 if (!L.done && lim_ - L.i >= niter_) {
                     env.scan(L, w, lane, g, rcp, lam2, ph1_, niter_);      // Lane::run, or the kernel's equivalent device form
-                    L.settle(g);
+                    L.template settle<W>(w, lane, g);
                 }
             });
             env.sync();
@@ -357,8 +374,9 @@ struct ChunkPlan {
 // in the identical renewal state from that start on).  Otherwise -- or when a lane retired inside the chunk -- the exact
 // sequential scan continues from the last verified renewal state, writing results directly, until one of its finished
 // segments coincides with the first segment of a later chunk (merge) or the fiber ends.  Returns the number of repair scans.
-template <typename T, class RecIn, class RecOut, class RecOvf, class Ld, class St>
-PTV_HD int verify_repair_fiber(const ChunkPlan& pl, T lam, RecIn rin, RecOut rout, RecOvf rovf, Ld ld, St st) {
+// prep(pos): called before every repair scan with its start row (the kernel stages the fiber's rows from there into shared memory).
+template <typename T, class RecIn, class RecOut, class RecOvf, class Prep, class Ld, class St>
+PTV_HD int verify_repair_fiber(const ChunkPlan& pl, T lam, RecIn rin, RecOut rout, RecOvf rovf, Prep prep, Ld ld, St st) {
     int repairs = 0, c = 0;
     bool entry_ok = true;                 // chunk c is known to be exact on entry (chunk 0; or established by a merge)
     while (c < pl.nchunks) {
@@ -369,6 +387,7 @@ PTV_HD int verify_repair_fiber(const ChunkPlan& pl, T lam, RecIn rin, RecOut rou
         if (cur == REC_NONE) { c++; entry_ok = false; continue; }
         repairs++;
         int resume = pl.nchunks;
+        prep(rec_pos(cur));
         slope_seq<T>(pl.n, lam, rec_pos(cur), rec_kind(cur), ld,
                      [&](int f, int e, T v, int kind) {
                          for (int r = f; r <= e; r++) st(r, v);

@@ -38,6 +38,21 @@ template <typename T>
 cudaError_t prox_fibers_ex(const T* A, const T* B, const T* C, InOp op, T* X, int out_op, FiberGeom g, T lam, const T* lamv,
                            Engine eng, T* scratch, cudaStream_t st, long long scratch_elems) {
     if (g.nf <= 0 || g.len <= 0) return cudaSuccess;
+    // plain unweighted prox over many fibers: the lane-per-fiber streaming engine (kernels_lane.cu), when the shape suits TMA tiling
+    // and there are enough fibers to fill the machine without cutting them (a single long fiber stays with the chunked kernels,
+    // which are also the bit-faithful ones behind the 1D entry points)
+    if ((eng == ENGINE_AUTO || eng == ENGINE_LANE) && op == IN_A && out_op == OUT_X && !lamv && lam > T(0) && g.len >= 64 && g.nf >= 1024) {
+        const void* ptrs[2] = {A, X};
+        if (ptvl::lane_shape_ok(g.nf, g.len, g.inc, sizeof(T), ptrs, 2)) {
+            void* lscr = ptvl::lane_scratch(g.nf, g.len);
+            if (lscr) {
+                KernelSpan span(g.inc == 1 ? KC_PROX_CONTIG : KC_PROX_STRIDED, 1, st);
+                cudaError_t e = ptvl::lane_prox<T>(ptvl::LANE_PLAIN, A, nullptr, nullptr, X, g.nf, g.len, g.inc, lam, lscr, st);
+                if (e != cudaErrorInvalidConfiguration) return e;
+                cudaGetLastError(); span.cancel();
+            }
+        }
+    }
     if (eng != ENGINE_SEQ && g.len >= 2 * 32) {
         if (g.inc == 1) {
             KernelSpan span(KC_PROX_CONTIG, 1, st);

@@ -184,10 +184,10 @@ int dr2_tspace_body(size_t M, size_t N, int batch, const T* Y, T w1, T w2, T* ou
                     bool plain_transposes);
 
 struct DrGraphKey {
-    size_t tsize, M, N; const void* Y; void* out; void* ws; double w1, w2; int maxit;
+    size_t tsize, M, N; const void* Y; void* out; void* ws; double w1, w2; int maxit; const void* aux;      // aux: the lane engine's scratch
     bool operator==(const DrGraphKey& o) const {
         return tsize == o.tsize && M == o.M && N == o.N && Y == o.Y && out == o.out && ws == o.ws && w1 == o.w1 && w2 == o.w2 &&
-               maxit == o.maxit;
+               maxit == o.maxit && aux == o.aux;
     }
 };
 struct DrGraph { cudaGraphExec_t exec = nullptr; DrGraphKey key{}; long long launches[KC_COUNT] = {0, 0, 0}; };
@@ -243,7 +243,7 @@ int dr2_device(size_t M, size_t N, int batch, int row_major, const T* Y, T w1, T
                           : dr2_piped_body<T>(M, N, Y, w1, w2, out, maxit, t, s, x, scr, scratch, gc, n, eng == ENGINE_AUTO && sizeof(T) == 8, bs);
         };
         DrGraphKey key{sizeof(T) + (tspace ? 100u : 0u) + (tpose ? 200u : 0u) + (eng == ENGINE_AUTO ? 400u : 0u) + (lane ? 800u : 0u) + 1000u * (size_t)batch, M, N, (const void*)Y, (void*)out, ws, (double)w1,
-                       (double)w2, maxit};
+                       (double)w2, maxit, lane ? lscr : nullptr};
         int rc = -1;
         if (!profile_is_enabled()) {
             DrGraph& G = g_dr_graph;

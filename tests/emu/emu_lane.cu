@@ -17,7 +17,7 @@ template <typename T> struct HostEnv {
     template <class F> int rmax(F f) { int m = f(L[0], 0); for (int l = 1; l < LANES; l++) { int v = f(L[l], l); if (v > m) m = v; } return m; }
     template <class F> bool any(F f) { for (int l = 0; l < LANES; l++) if (f(L[l], l)) return true; return false; }
     void sync() {}
-    template <int W> void scan(Lane<T>& L, const Window<T, W>& w, int lane, const TaskGeom& g, const T* rcp, T lam2, bool ph1, int niter) {
+    template <int W> void scan(Lane<T>& L, const Window<T, W>& w, int lane, const TaskGeom& g, const acc_t* rcp, acc_t lam2, bool ph1, int niter) {
         if (ph1) L.template run<true, W>(w, lane, g, rcp, lam2, niter); else L.template run<false, W>(w, lane, g, rcp, lam2, niter);
     }
 };
@@ -89,10 +89,10 @@ static int run_all(int opkind, const T* A, const T* B, const T* C, T* X, long lo
     Op<T> op{opkind, A, B, C, X};
     ChunkPlan pl; pl.n = len; pl.halo = halo;
     if (clen <= 0 || clen >= len) { pl.clen = len; pl.nchunks = 1; } else { pl.clen = clen; pl.nchunks = (len + clen - 1) / clen; }
-    std::vector<T> win((size_t)W * LANES), rcp(W + 2);
+    std::vector<T> win((size_t)W * LANES); std::vector<acc_t> rcp(W + 2);
     std::vector<unsigned long long> flg8((Window<T, W>::flag_bytes() + 7) / 8 + 1);
     uint8_t* flgp = reinterpret_cast<uint8_t*>(flg8.data());
-    for (int k = 1; k < W + 2; k++) rcp[k] = T(1) / T(k);
+    for (int k = 1; k < W + 2; k++) rcp[k] = 1.0 / (acc_t)k;
     const long long slabs = inc > 1 ? nf / inc : 1, per_slab = inc > 1 ? inc : nf;
     const long long gps = (per_slab + LANES - 1) / LANES;
     std::vector<int> rin((size_t)pl.nchunks * LANES), rout((size_t)pl.nchunks * LANES), rovf((size_t)pl.nchunks * LANES);
@@ -110,7 +110,7 @@ static int run_all(int opkind, const T* A, const T* B, const T* C, T* X, long lo
                 Window<T, W> w{win.data(), flgp};
                 memset(flgp, 0, Window<T, W>::flag_bytes());
                 HostEnv<T> env;
-                for (int l = 0; l < LANES; l++) env.L[l].init(g, lam, fb.valid[l]);
+                for (int l = 0; l < LANES; l++) env.L[l].init(w, l, g, lam, fb.valid[l]);
                 long long fed = 0;
                 HostFeed<T, W, RT> feed{&w, &op, &fb, len, &fed};
                 TaskStats ts{0, 0, 0, 0};
@@ -133,7 +133,7 @@ static int run_all(int opkind, const T* A, const T* B, const T* C, T* X, long lo
                 const long long base = fb.base[l], st = fb.stride;
                 es->repairs += verify_repair_fiber<T>(pl, lam,
                     [&](int c) { return rin[(size_t)c * LANES + l]; }, [&](int c) { return rout[(size_t)c * LANES + l]; },
-                    [&](int c) { return rovf[(size_t)c * LANES + l]; },
+                    [&](int c) { return rovf[(size_t)c * LANES + l]; }, [](int) {},
                     [&](int r) { return op.in(base + (long long)r * st); }, [&](int r, T v) { op.out(base + (long long)r * st, v); });
             }
         }
