@@ -168,6 +168,114 @@ def run_reference(args, rank, world):
         "gpu_launches": 0}))
 
 
+def run_other_workload(args, rank, world, local):
+    """--workload cfg3 | cfg4 | cfg5: the other BASELINE.json configurations, same JSON contract (value = whole-job throughput,
+    device-resident; roofline = the workload's algorithmic bytes, SURVEY.md 8d, over the measured step time)."""
+    import torch
+    import torch.distributed as dist
+    import proxtv_b200 as ptv
+    from oracle import oracle as O
+
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = ptv.require_device()
+    peak, peak_src = peaks()
+    wl = args.workload
+    vp = C.c_void_p
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    extra = {}
+    if wl == "cfg3":                    # tv1w_1d on 65536 signals x 4096, per-element weights, f64 (new batched API)
+        B, L = args.batch or 65536, 4096
+        g = torch.Generator(device="cuda"); g.manual_seed(rank)
+        X = (torch.randn((B, L // 64), device="cuda", dtype=torch.float64, generator=g) * 2).repeat_interleave(64, dim=1) \
+            + torch.randn((B, L), device="cuda", dtype=torch.float64, generator=g) * 0.5
+        Wt = torch.rand((B, L - 1), device="cuda", dtype=torch.float64, generator=g) * 0.9 + 0.1
+        out = torch.empty_like(X)
+        st = vp(torch.cuda.current_stream().cuda_stream)
+        step = lambda: lib.proxtv_prox_fibers_dev_f64(vp(X.data_ptr()), vp(out.data_ptr()), B, L, 1, 0.0, vp(Wt.data_ptr()), st)  # noqa: E731
+        units, unit, metric = B * L, "Msamples/s", "tv1w_1d Msamples/s"
+        alg_bytes = B * (L * 16 + (L - 1) * 8)
+        workload = "tv1w_1d batch %d x %d f64, per-element weights U(0.1,1)" % (B, L); dtype = "f64"
+        h2d, d2h = B * (2 * L - 1) * 8, B * L * 8
+    elif wl == "cfg4":                  # tvgen 3D anisotropic TV (PD_TV), 512 x 512 x 256 f32
+        shp = (512, 512, 256)
+        V = O.gen_cfg4(shp, seed=rank)
+        Vd = torch.from_numpy(np.ascontiguousarray(V.astype(np.float32).transpose(2, 1, 0))).cuda(); outd = torch.empty_like(Vd)
+        ns = np.array(shp, dtype=np.int32); dims = np.array([1.0, 2.0, 3.0]); inf = np.zeros(3)
+
+        def step():
+            lam = np.array([0.2, 0.2, 0.2])
+            lib.proxtv_PD_TV_dev_f32(vp(Vd.data_ptr()), vp(lam.ctypes.data), vp(dims.ctypes.data), vp(outd.data_ptr()), vp(inf.ctypes.data),
+                                     vp(ns.ctypes.data), 3, 3, 0, None)
+        units, unit, metric = int(np.prod(shp)), "Mvoxels/s", "tvgen PD_TV Mvoxels/s"
+        k = 3
+        alg_bytes = None                 # needs the iteration count: filled in after the run
+        workload = "tvgen PD_TV %dx%dx%d f32, ws=(.2,.2,.2), ds=(1,2,3)" % shp; dtype = "f32 storage, f64 scan arithmetic"
+        h2d = d2h = units * 4
+    else:                               # cfg5: tv1_2d on a batch of 2048 x 2048 f32 images, 128 per GPU, NCCL scatter / gather of images
+        from proxtv_b200.distributed import tv1_2d_batched_sharded
+        per_gpu = args.batch or 128; H = 2048; B = per_gpu * world
+        x = None
+        if rank == 0:
+            g = torch.Generator(device="cuda"); g.manual_seed(0)
+            x = torch.empty((B, H, H), device="cuda", dtype=torch.float32)
+            for b0 in range(0, B, 32):
+                nb = min(32, B - b0)
+                lv = torch.randn((nb, H // 64, H // 64), device="cuda", generator=g).repeat_interleave(64, dim=1).repeat_interleave(64, dim=2)
+                x[b0:b0 + nb] = lv + torch.randn((nb, H, H), device="cuda", generator=g) * 0.3
+        tm = {}
+        step = (lambda: tv1_2d_batched_sharded(x, LAM, pieces=args.pieces, timings=tm)) if world > 1 else (lambda: ptv.tv1_2d_batched(x, LAM))  # noqa: E731
+        units, unit, metric = B * H * H, "Mpixels/s", "tv1_2d batched Mpixels/s"
+        alg_bytes = units * B_PER_PIXEL_SOLVE(4)
+        workload = "tv1_2d DR2_TV batch %d x %dx%d f32 (%d images per GPU), lambda=%.1f; %s" % (
+            B, H, H, per_gpu, LAM, ("NCCL scatter + gather of image slabs from/to rank 0, %d pipelined pieces" % args.pieces) if world > 1 else "single GPU, no collective")
+        dtype = "f32 storage, f64 scan arithmetic"
+        h2d = d2h = 0
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    clocks = ClockSampler(local); clocks.start()
+    lib.proxtv_profile_reset()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    stt = torch.cuda.current_stream()
+    barrier(); e0.record(stt)
+    for _ in range(args.steps):
+        step()
+    e1.record(stt); barrier()
+    ms = e0.elapsed_time(e1)
+    kms = (C.c_double * 3)(); kl = (C.c_longlong * 3)(); ks = (C.c_longlong * 3)()
+    lib.proxtv_profile_read(kms, kl, ks)
+    clk = clocks.stop()
+    tmax = torch.tensor([ms], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms_step = float(tmax.item()) / args.steps
+    total_units = units if wl == "cfg5" else units * world
+    if wl == "cfg4":
+        iters = int(inf[0]); extra["iterations"] = iters; extra["stop"] = float(inf[1])
+        alg_bytes = units * 4 * ((k + 1) + iters * (5 * k + 2))
+    if rank == 0:
+        ach = alg_bytes * (1 if wl == "cfg5" else world) / (ms_step * 1e-3) / 1e9 / world
+        line = {"metric": metric, "value": total_units / (ms_step * 1e-3) / 1e6, "unit": unit, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": dtype, "data": "synthetic", "config": dict({"workload": workload}, **extra),
+                "roofline": {"bound": "hbm", "kernel": "whole step (all kernels of the workload)", "achieved": ach, "peak": peak, "unit": "GB/s per GPU",
+                             "frac": ach / peak, "algorithmic_bytes_per_step_per_gpu": alg_bytes / (world if wl == "cfg5" else 1), "peak_source": peak_src, "traffic": None},
+                "gpu_launches": int(sum(kl[i] for i in range(3))), "clocks": clk,
+                "e2e": {"value": None, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "note": "device-resident workload (inputs generated on the GPU); the headline e2e number is config 2's"}}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -177,11 +285,17 @@ def main():
     ap.add_argument("--size", type=int, default=4096)
     ap.add_argument("--engine", default="auto")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4", "cfg5"])
+    ap.add_argument("--batch", type=int, default=0, help="cfg3: signals; cfg5: images per GPU (0 = BASELINE.json's)")
+    ap.add_argument("--pieces", type=int, default=4, help="cfg5: pipelined transfer pieces per GPU slab")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+        return
+    if args.workload != "cfg2":
+        run_other_workload(args, rank, world, local)
         return
 
     import torch

@@ -10,7 +10,7 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, batch, tmp):
+def _worker(rank, world, port, batch, tmp, pieces=1):
     sys.path.insert(0, ROOT)
     import torch
     import torch.distributed as dist
@@ -26,7 +26,7 @@ def _worker(rank, world, port, batch, tmp):
     imgs = None
     if rank == 0:
         imgs = np.stack([np.ascontiguousarray(O.gen_cfg2(24, 20, seed=s, block=4)) for s in range(batch)])
-    out = tv1_2d_batched_sharded(imgs, 0.2, max_iters=5, src=0, solver=solver)
+    out = tv1_2d_batched_sharded(imgs, 0.2, max_iters=5, src=0, solver=solver, pieces=pieces)
     if rank == 0:
         want = np.stack([P.dr2_tv(im, 0.2, maxit=5)[0] for im in imgs])
         ok = out.shape == want.shape and np.array_equal(out.numpy(), want)
@@ -45,6 +45,14 @@ def test_batch_sharding_over_gloo(batch, tmp_path):
     port = 29500 + (os.getpid() + batch) % 2000
     mp.spawn(_worker, args=(2, port, batch, str(tmp_path)), nprocs=2, join=True)
     assert open(os.path.join(str(tmp_path), "ok_%d" % batch)).read() == "1"
+
+
+def test_batch_sharding_pipelined_over_gloo(tmp_path):
+    """pieces > 1: the transfers of neighbouring pieces overlap the solves; same result, uneven pieces included."""
+    import torch.multiprocessing as mp
+    port = 31500 + os.getpid() % 2000
+    mp.spawn(_worker, args=(2, port, 7, str(tmp_path), 3), nprocs=2, join=True)
+    assert open(os.path.join(str(tmp_path), "ok_7")).read() == "1"
 
 
 def test_slab_bounds():
