@@ -17,7 +17,7 @@ using namespace ptv;
 namespace {
 
 thread_local std::string g_err;
-std::mutex g_mu;
+std::recursive_mutex g_mu;
 int g_engine = ENGINE_AUTO;
 
 struct Arena {
@@ -37,9 +37,27 @@ struct Arena {
 // (torch tensors on cuda:0 and cuda:1) never hands one device's memory to kernels running on another
 constexpr int MAX_DEV = 64;
 Arena g_ws_d[MAX_DEV], g_io_d[MAX_DEV];
-int cur_dev() { int d = 0; if (cudaGetDevice(&d) != cudaSuccess) { cudaGetLastError(); d = 0; } return (d < 0 || d >= MAX_DEV) ? 0 : d; }
+// slot of the current device; devices beyond MAX_DEV share the last slot's workspace tables only after have_device() refused them
+int cur_dev() { int d = 0; if (cudaGetDevice(&d) != cudaSuccess) { cudaGetLastError(); d = 0; } return (d < 0 || d >= MAX_DEV) ? MAX_DEV - 1 : d; }
 #define g_ws (g_ws_d[cur_dev()])
 #define g_io (g_io_d[cur_dev()])
+
+// The workspaces, pipeline streams and captured graphs are one set per device, shared by every call: calls are serialised on the
+// host by g_mu, and ON THE DEVICE by a per-device event -- a call's stream first waits for the previous call's work (which may
+// have been enqueued on another stream), and records the event when its own work is enqueued.  Held for the whole call.
+struct WsGuard {
+    std::lock_guard<std::recursive_mutex> lk;
+    cudaStream_t st; int dev;
+    static cudaEvent_t& ev(int d) { static cudaEvent_t e[MAX_DEV] = {}; return e[d]; }
+    explicit WsGuard(cudaStream_t s) : lk(g_mu), st(s), dev(-1) {
+        int d = 0;
+        if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= MAX_DEV) { cudaGetLastError(); return; }
+        dev = d;
+        if (!ev(d)) { if (cudaEventCreateWithFlags(&ev(d), cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); ev(d) = nullptr; dev = -1; return; } }
+        else cudaStreamWaitEvent(st, ev(d), 0);
+    }
+    ~WsGuard() { if (dev >= 0 && ev(dev)) cudaEventRecord(ev(dev), st); }
+};
 
 bool fail(const char* fn, const char* msg, double* info) {
     g_err = std::string(fn) + ": " + msg;
@@ -57,6 +75,9 @@ bool have_device(const char* fn, double* info) {
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess || n <= 0) { cudaGetLastError();
         return fail(fn, "no usable CUDA device (libproxtv_b200 has no CPU fallback)", info); }
+    int d = -1;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= MAX_DEV - 1) { cudaGetLastError();
+        return fail(fn, "current CUDA device index out of the supported range (0..62)", info); }
     return true;
 }
 inline size_t al(size_t b) { return (b + 255) & ~(size_t)255; }
@@ -66,7 +87,7 @@ template <typename T>
 int host_prox_fibers(const char* fn, const T* in, T* out, long long nf, int len, long long inc, T lam, const T* lamv) {
     if (nf <= 0 || len <= 0) return 1;
     if (!have_device(fn, nullptr)) return 0;
-    std::lock_guard<std::mutex> lk(g_mu);
+    WsGuard guard(0);
     const size_t n = (size_t)nf * len, nw = lamv ? (size_t)nf * (len - 1) : 0;
     char* d = (char*)g_io.get(2 * al(n * sizeof(T)) + al(nw * sizeof(T) + 8));
     // scratch: staging of strided fibers (2n), or the overlapping tiles of contiguous fibers longer than shared memory
@@ -88,7 +109,7 @@ int host_prox_fibers(const char* fn, const T* in, T* out, long long nf, int len,
 template <typename T>
 int host_dr2(const char* fn, size_t M, size_t N, int batch, const T* Y, T W1, T W2, T* out, int maxit, double* info) {
     if (!have_device(fn, info)) return 0;
-    std::lock_guard<std::mutex> lk(g_mu);
+    WsGuard guard(0);
     const size_t n = M * N * (size_t)batch;
     if (n == 0) { if (info) { info[INFO_ITERS] = maxit <= 0 ? MAX_ITERS_DR : maxit; info[INFO_RC] = RC_OK; } return 0; }
     char* d = (char*)g_io.get(2 * al(n * sizeof(T)));
@@ -97,8 +118,10 @@ int host_dr2(const char* fn, size_t M, size_t N, int batch, const T* Y, T W1, T 
     T* dY = (T*)d; T* dout = (T*)(d + al(n * sizeof(T)));
     cudaStream_t st = 0;
     if (!cuda_ok(fn, cudaMemcpyAsync(dY, Y, n * sizeof(T), cudaMemcpyHostToDevice, st), info)) return 0;
-    dr2_device<T>(M, N, batch, 0, dY, W1, W2, dout, maxit, info, ws, (Engine)g_engine, st);
-    if (info && info[INFO_RC] == RC_ERROR) { fail(fn, "device solver failed", info); return 0; }
+    double linfo[3] = {0, 0, RC_OK};                   // a NULL info must not hide a failed solve (nothing is copied back then)
+    double* pinfo = info ? info : linfo;
+    dr2_device<T>(M, N, batch, 0, dY, W1, W2, dout, maxit, pinfo, ws, (Engine)g_engine, st);
+    if (pinfo[INFO_RC] == RC_ERROR) { fail(fn, "device solver failed", info); return 0; }
     if (!cuda_ok(fn, cudaMemcpyAsync(out, dout, n * sizeof(T), cudaMemcpyDeviceToHost, st), info)) return 0;
     if (!cuda_ok(fn, cudaStreamSynchronize(st), info)) return 0;
     return 0;
@@ -109,7 +132,7 @@ template <typename T>
 int run_drw(const char* fn, bool host_io, size_t M, size_t N, const T* Y, const T* W1, const T* W2, T* out, int maxit, double* info,
             cudaStream_t st) {
     if (!have_device(fn, info)) return 0;
-    std::lock_guard<std::mutex> lk(g_mu);
+    WsGuard guard(st);
     const size_t n = M * N, n1 = M ? (M - 1) * N : 0, n2 = N ? M * (N - 1) : 0;
     if (n == 0) { if (info) { info[INFO_ITERS] = maxit <= 0 ? MAX_ITERS_DR : maxit; info[INFO_RC] = RC_OK; } return 0; }
     void* ws = g_ws.get(ws_bytes_dr2<T>(M, N, 1));
@@ -121,8 +144,10 @@ int run_drw(const char* fn, bool host_io, size_t M, size_t N, const T* Y, const 
     if (!cuda_ok(fn, cudaMemcpyAsync(dY, Y, n * sizeof(T), cudaMemcpyHostToDevice, st), info)) return 0;
     if (n1 && !cuda_ok(fn, cudaMemcpyAsync(d1, W1, n1 * sizeof(T), cudaMemcpyHostToDevice, st), info)) return 0;
     if (n2 && !cuda_ok(fn, cudaMemcpyAsync(d2, W2, n2 * sizeof(T), cudaMemcpyHostToDevice, st), info)) return 0;
-    drw_device<T>(M, N, dY, d1, d2, dout, maxit, info, ws, (Engine)g_engine, st);
-    if (info && info[INFO_RC] == RC_ERROR) { fail(fn, "device solver failed", info); return 0; }
+    double linfo[3] = {0, 0, RC_OK};
+    double* pinfo = info ? info : linfo;
+    drw_device<T>(M, N, dY, d1, d2, dout, maxit, pinfo, ws, (Engine)g_engine, st);
+    if (pinfo[INFO_RC] == RC_ERROR) { fail(fn, "device solver failed", info); return 0; }
     if (!cuda_ok(fn, cudaMemcpyAsync(out, dout, n * sizeof(T), cudaMemcpyDeviceToHost, st), info)) return 0;
     if (!cuda_ok(fn, cudaStreamSynchronize(st), info)) return 0;
     return 0;
@@ -137,7 +162,7 @@ int run_pd(const char* fn, int mode, bool host_io, const T* y, double* lambdas, 
         fail(fn, "only p = 1 (TV-L1) penalty terms are implemented on the GPU path", info); return 0; }
     if (nds <= 0 || !ns) { fail(fn, "invalid dimensions", info); return 0; }
     long long n = 1; for (int i = 0; i < nds; i++) n *= ns[i];
-    std::lock_guard<std::mutex> lk(g_mu);
+    WsGuard guard(st);
     if (mode == 1) for (int i = 0; i < npen; i++) lambdas[i] *= npen;                   // TVNDopt.cpp:100-101 (in place)
     void* ws = g_ws.get(ws_bytes_pd<T>(n, npen > 2 ? npen : 2));
     if (!ws) { fail(fn, "out of memory", info); return 0; }
@@ -160,7 +185,7 @@ int run_pd(const char* fn, int mode, bool host_io, const T* y, double* lambdas, 
 
 template <typename T> static T* dev_scratch(long long nf, int len, long long inc) {
     if (nf <= 0 || len <= 0 || (inc == 1 && len <= 16384)) return nullptr;
-    std::lock_guard<std::mutex> lk(g_mu);
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
     if (inc == 1) return (T*)g_ws.get(al((size_t)lf_scratch_elems(nf, len) * sizeof(T)) + 256);
     return (T*)g_ws.get(al((size_t)strided_scratch_elems(nf, len) * sizeof(T)));
 }
@@ -168,7 +193,7 @@ template <typename T> static T* dev_scratch(long long nf, int len, long long inc
 template <typename T>
 static int dev_dr2(const char* fn, size_t M, size_t N, int batch, int row_major, const T* Y, T W1, T W2, T* out, int maxit, double* info, void* stream) {
     if (!have_device(fn, info)) return 0;
-    std::lock_guard<std::mutex> lk(g_mu);
+    WsGuard guard((cudaStream_t)stream);
     void* ws = g_ws.get(ws_bytes_dr2<T>(M, N, batch));
     if (!ws) { fail(fn, "out of memory", info); return 0; }
     return dr2_device<T>(M, N, batch, row_major, Y, W1, W2, out, maxit, info, ws, (Engine)g_engine, (cudaStream_t)stream);
@@ -187,11 +212,12 @@ void proxtv_host_free(void* p) { if (p) cudaFreeHost(p); }
 void proxtv_profile_enable(int on) { profile_enable(on); }
 void proxtv_profile_reset(void) { profile_reset(); }
 void proxtv_profile_read(double* ms, long long* launches, long long* spans) { profile_read(ms, launches, spans); }
-void proxtv_release_workspace(void) { std::lock_guard<std::mutex> lk(g_mu); for (int d = 0; d < MAX_DEV; d++) { g_ws_d[d].release(); g_io_d[d].release(); } }
+void proxtv_release_workspace(void) { std::lock_guard<std::recursive_mutex> lk(g_mu); for (int d = 0; d < MAX_DEV; d++) { g_ws_d[d].release(); g_io_d[d].release(); } }
 
 // ---- experimental: the lane-per-fiber streaming engine (kernels_lane.cu), device pointers ----
 int proxtv_lane_prox_dev_f64(int op, const double* A, const double* B, const double* C, double* X, long long nf, int len, long long inc,
                              double lam, void* stream) {
+    WsGuard guard((cudaStream_t)stream);
     void* scr = ptvl::lane_scratch(nf, len);
     if (!scr) return 0;
     cudaError_t e = ptvl::lane_prox<double>(op, A, B, C, X, nf, len, inc, lam, scr, (cudaStream_t)stream);
@@ -200,6 +226,7 @@ int proxtv_lane_prox_dev_f64(int op, const double* A, const double* B, const dou
 }
 int proxtv_lane_prox_dev_f32(int op, const float* A, const float* B, const float* C, float* X, long long nf, int len, long long inc,
                              float lam, void* stream) {
+    WsGuard guard((cudaStream_t)stream);
     void* scr = ptvl::lane_scratch(nf, len);
     if (!scr) return 0;
     cudaError_t e = ptvl::lane_prox<float>(op, A, B, C, X, nf, len, inc, lam, scr, (cudaStream_t)stream);
@@ -286,11 +313,13 @@ int PD_TV(double* y, double* lambdas, double* norms, double* dims, double* x, do
 // ---- Part 2: extensions ----
 int proxtv_prox_fibers_dev_f64(const double* in, double* out, long long nf, int len, long long inc, double lam, const double* lamv, void* stream) {
     if (!have_device("proxtv_prox_fibers_dev_f64", nullptr)) return 0;
+    WsGuard guard((cudaStream_t)stream);
     return cuda_ok("proxtv_prox_fibers_dev_f64", prox_fibers<double>(in, nullptr, IN_A, out, 0, FiberGeom{nf, len, inc}, lam, lamv, (Engine)g_engine, dev_scratch<double>(nf, len, inc), (cudaStream_t)stream,
                                                                  (inc == 1 && len > 16384) ? lf_scratch_elems(nf, len) : (inc != 1 ? strided_scratch_elems(nf, len) : 0)), nullptr);
 }
 int proxtv_prox_fibers_dev_f32(const float* in, float* out, long long nf, int len, long long inc, float lam, const float* lamv, void* stream) {
     if (!have_device("proxtv_prox_fibers_dev_f32", nullptr)) return 0;
+    WsGuard guard((cudaStream_t)stream);
     return cuda_ok("proxtv_prox_fibers_dev_f32", prox_fibers<float>(in, nullptr, IN_A, out, 0, FiberGeom{nf, len, inc}, lam, lamv, (Engine)g_engine, dev_scratch<float>(nf, len, inc), (cudaStream_t)stream,
                                                                  (inc == 1 && len > 16384) ? lf_scratch_elems(nf, len) : (inc != 1 ? strided_scratch_elems(nf, len) : 0)), nullptr);
 }

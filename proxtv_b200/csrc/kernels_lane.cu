@@ -150,8 +150,9 @@ __device__ __forceinline__ void run_dev(Lane<T>& L, const DevWin<T, W> dw, const
         const acc_t y = (acc_t)SmemIO<T>::ld(dw.at(ia));
         const int ka = ia - la;
         const acc_t r = SmemIO<double>::ld(dw.rcp + ((uint32_t)ka >> DW::SH));
+        // both slopes straight from the old sum (ch does not wait for cl: the float64 dependency chain is add -> multiply -> compare)
+        const acc_t cl = (Z + y) * r, ch = (Z + (y + lam2)) * r;
         Z += y;
-        const acc_t cl = Z * r, ch = fma(lam2, r, cl);              // (Z + 2 lam) r, one operation shorter
         const bool first = (ka == ROWB);
         const bool can = !first & (la < cea);
         const bool craw = lo > ch, fraw = hi < cl;          // both compares issue back to back (neither waits for the other)
@@ -565,7 +566,7 @@ static bool make_map(CUtensorMap* m, const T* base, long long d0, long long d1, 
 }
 
 struct LaneTuning { int clen, halo, variant; };
-static LaneTuning g_tune = {0, 32, 0};
+static LaneTuning g_tune = {0, 32, 0};        // chunk length (0 = one wave), halo rows, variant
 void lane_set_tuning(int clen, int halo, int variant) { g_tune.clen = clen; g_tune.halo = halo; g_tune.variant = variant; }
 
 // Scratch of the lane engine, one buffer per device (grow-only, zero-initialised when (re)allocated):
@@ -669,7 +670,9 @@ cudaError_t lane_prox(int op, const T* A, const T* B, const T* C, T* X, long lon
         clen = (int)((len + c - 1) / c);
         if (clen < 64) clen = 64;
     }
-    clen = (clen + 31) / 32 * 32; halo = (halo + 31) / 32 * 32;
+    // boundaries on TMA box rows: 16 (float64) / 32 (float32) for the CONTIG layout, 8 for STRIDED; chunks on 32
+    const int hal = lay == LAY_CONTIG ? 128 / (int)sizeof(T) : 8;
+    clen = (clen + 31) / 32 * 32; halo = (halo + hal - 1) / hal * hal;
     a.plan.n = len; a.plan.halo = halo;
     if (clen >= len) { a.plan.clen = len; a.plan.nchunks = 1; } else { a.plan.clen = clen; a.plan.nchunks = (len + clen - 1) / clen; }
     if (a.plan.nchunks > len / 64 + 2) return cudaErrorInvalidConfiguration;

@@ -62,11 +62,13 @@ PTV_HD void slope_seq(int n, T lam_, int pos, int kind, Ld ld, Seg seg) {
     int last = pos - 1, i = pos, blo = pos, bhi = pos, kcur = kind;
     acc_t Z = z_of_kind(kind, lam), lo = 0.0, hi = 0.0;
     while (i < n) {
-        Z += (acc_t)ld(i);
+        const acc_t y = (acc_t)ld(i);
         const int k = i - last;
         const acc_t r = 1.0 / (acc_t)k;
+        // same expressions, same association as the lanes' loop (Lane::run): identical decisions and values bit for bit
+        const acc_t cl = (Z + y) * r, ch = (Z + (y + lam2)) * r;
+        Z += y;
         if (i < n - 1) {
-            const acc_t cl = Z * r, ch = fma(lam2, r, cl);
             if (k == 1) { lo = cl; hi = ch; blo = bhi = i; i++; continue; }
             if (lo > ch) {                                   // ceiling violation (hybridtautstring.cpp:93-111)
                 if (seg(last + 1, blo, (T)lo, kcur)) return;
@@ -167,8 +169,8 @@ template <typename T> struct Lane {
             const acc_t y = (acc_t)w.ld(i_, lane);
             const int k = i_ - last_;
             const acc_t r = rcp[k];
+            const acc_t cl = (Z_ + y) * r, ch = (Z_ + (y + lam2)) * r;      // slopes to the tube floor / ceiling at sample i
             Z_ += y;
-            const acc_t cl = Z_ * r, ch = fma(lam2, r, cl);      // (Z + 2 lam) r
             const bool first = (k == 1);
             const bool can = !first & (last_ < g.ce);
             const bool cbk = can & (lo_ > ch);

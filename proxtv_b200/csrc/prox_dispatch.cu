@@ -61,7 +61,8 @@ cudaError_t prox_fibers_ex(const T* A, const T* B, const T* C, InOp op, T* X, in
             cudaGetLastError();
             // too long for shared memory: overlapping tiles, verified stitching (long_fiber.cu); the scratch convention for
             // this case is lf_scratch_elems() elements, which the 1D host entry points provide
-            if (!lamv && out_op < OUT_DR_ROWS && scratch && scratch_elems >= lf_scratch_elems(g.nf, g.len)) {
+            // (plain results only: the agreement test of the stitching compares prox values, which the fused output forms would hide)
+            if (!lamv && out_op == OUT_X && scratch && scratch_elems >= lf_scratch_elems(g.nf, g.len)) {
                 e = prox_long_fibers<T>(A, B, op, X, out_op, g, lam, scratch, lf_scratch_elems(g.nf, g.len), st);
                 if (e == cudaSuccess) return e;
                 if (e != cudaErrorInvalidConfiguration && e != cudaErrorNotReady) return e;

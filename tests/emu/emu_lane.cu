@@ -2,7 +2,8 @@
 // scan steps, window management, sweep, chunk records, verification and repair) on the CPU, one warp task at a time, the 32
 // lanes of a warp in a plain loop (lanes only interact through the warp collectives, which the host Env computes over the
 // loop).  Feed and Drain are the host stand-ins of the kernel's TMA feeder / row drain: same window contents, same calls.
-// Not part of the product; built by tests/test_lane_emulation.py with nvcc (host code only).
+// Not part of the product; built by tests/test_lane_emulation.py with g++ (host code only; the CUDA headers only supply the
+// __host__ __device__ macros).
 #include "../../proxtv_b200/csrc/lane_core.cuh"
 #include <vector>
 #include <string.h>

@@ -30,6 +30,7 @@ def stream():
 
 
 def old_prox(x, nf, ln, inc, lam):
+    ptv.set_engine("chunked")                       # the bit-faithful chunked engine (engine 'auto' would dispatch to the lane engine)
     out = torch.empty_like(x)
     fn = lib.proxtv_prox_fibers_dev_f64 if x.dtype == torch.float64 else lib.proxtv_prox_fibers_dev_f32
     assert fn(vp(x.data_ptr()), vp(out.data_ptr()), nf, ln, inc, lam, None, stream()) == 1
