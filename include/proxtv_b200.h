@@ -81,6 +81,12 @@ int PD2_TV(double *y, double *lambdas, double *norms, double *dims, double *x, d
 /* replaces src/TVNDopt.cpp:48 (src/TVopt.h:137).  Like the reference it multiplies lambdas[] by npen IN PLACE (:100-101). */
 int PD_TV(double *y, double *lambdas, double *norms, double *dims, double *x, double *info, int *ns, int nds, int npen,
           int ncores, int maxIters);
+/* replaces src/TVNDopt.cpp:280 (src/TVopt.h:138; reached from MATLAB only in the reference, matlab/solveTVND_PDR.cpp:89): parallel
+ * Douglas-Rachford over npen one-dimensional TV-L1 terms.  Runs exactly maxIters iterations (<= 0: 35; the reference's loop has no
+ * stop test); multiplies lambdas[] by npen IN PLACE (:339-340); info = {iters, mean|x - x_last| of the last iteration, RC_ITERS when
+ * iters >= 35 else RC_OK}; returns 1 ok / 0 error.  norms must be 1 (the reference's p = 2 / general-p terms are out of scope). */
+int PDR_TV(double *y, double *lambdas, double *norms, double *dims, double *x, double *info, int *ns, int nds, int npen,
+           int ncores, int maxIters);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Part 2 -- extensions.  *_dev functions take DEVICE pointers and a cudaStream_t passed as void* (NULL = default
@@ -93,10 +99,13 @@ int proxtv_device_count(void);                 /* usable CUDA devices (0 => ever
 const char *proxtv_last_error(void);           /* last error text of the calling thread ("" if none) */
 const char *proxtv_version(void);
 
-/* kernel family / Douglas-Rachford schedule (results are bit-identical across 0, 2, 4, 5, 6; for measurements and tests):
- * 0 auto, 1 sequential lane-per-fiber, 2 chunked speculative with the plain serial schedule, 3 chunked with direct strided
- * staging, 4 pipelined gather/scatter schedule (what auto picks for one large image), 5 transposeless schedule (scan kernels
- * write both layouts), 6 plain transposes around a fused row kernel.  Returns the previous value. */
+/* kernel family / Douglas-Rachford schedule (for measurements and tests).  0 auto: the lane-per-fiber streaming engine in slope
+ * form (7) wherever the shape suits TMA tiling (16-byte aligned bases, row pitch a multiple of 16 bytes, positive weights, enough
+ * fibers), else the chunked family; 1 sequential lane-per-fiber; 2 chunked speculative scan with the plain serial schedule;
+ * 3 chunked with direct strided staging; 4 pipelined gather/scatter schedule; 5 transposeless schedule (scan kernels write both
+ * layouts); 6 plain transposes around a fused row kernel; 7 the lane engine (kernels_lane.cu).  Engines 2, 4, 5, 6 are bit-identical
+ * to each other (the reference's own arithmetic); the lane engine agrees with them to ~1e-13 (same decisions, slope-form arithmetic).
+ * The 1D entry points of Part 1 always use the bit-faithful chunked kernels.  Returns the previous value. */
 int proxtv_set_engine(int engine);
 
 /* Batched 1D prox over the fibers of a column-major array: nf fibers of len samples, fiber j starting at
@@ -141,6 +150,10 @@ int proxtv_PD_TV_dev_f64(const double *y, double *lambdas, double *dims, double 
                          int maxIters, void *stream);
 int proxtv_PD_TV_dev_f32(const float *y, double *lambdas, double *dims, float *x, double *info, int *ns, int nds, int npen,
                          int maxIters, void *stream);
+int proxtv_PDR_TV_dev_f64(const double *y, double *lambdas, double *dims, double *x, double *info, int *ns, int nds, int npen,
+                          int maxIters, void *stream);
+int proxtv_PDR_TV_dev_f32(const float *y, double *lambdas, double *dims, float *x, double *info, int *ns, int nds, int npen,
+                          int maxIters, void *stream);
 int proxtv_PD_TV_f32(const float *y, double *lambdas, double *dims, float *x, double *info, int *ns, int nds, int npen,
                      int maxIters);                                          /* host pointers, float32 */
 
@@ -156,6 +169,17 @@ void *proxtv_host_alloc(size_t bytes);
 void proxtv_host_free(void *p);
 /* release the cached device workspace */
 void proxtv_release_workspace(void);
+
+/* Lane engine, for measurements: one batched prox pass with the fused arithmetic `op` (0 plain: X = prox(A); 1 Douglas-Rachford
+ * second half: X = (C - B) + prox(A - (2 (C - B) - C)); 2 final projection: X = prox(A - (C - B))); fibers (nf, len, inc) as above
+ * (inc == 1 only with op 0).  Returns 0 when the shape does not suit the engine.  tuning: chunk length (0 = one wave of warp tasks),
+ * halo rows, kernel variant; stats: number of fibers that went through the sequential repair path since the last reset. */
+int proxtv_lane_prox_dev_f64(int op, const double *A, const double *B, const double *C, double *X, long long nf, int len,
+                             long long inc, double lam, void *stream);
+int proxtv_lane_prox_dev_f32(int op, const float *A, const float *B, const float *C, float *X, long long nf, int len,
+                             long long inc, float lam, void *stream);
+void proxtv_lane_tuning(int clen, int halo, int variant);
+unsigned long long proxtv_lane_stats(int reset);
 
 #ifdef __cplusplus
 }

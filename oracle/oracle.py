@@ -52,6 +52,7 @@ class Port:
         L.orc_dr2l1w_tv.argtypes = [C.c_size_t, C.c_size_t, _dp, _dp, _dp, _dp, C.c_int, _dp]
         L.orc_pd2_tv.argtypes = [_dp, _dp, _dp, _dp, _dp, _ip, C.c_int, C.c_int, C.c_int]
         L.orc_pd_tv.argtypes = [_dp, _dp, _dp, _dp, _dp, _ip, C.c_int, C.c_int, C.c_int]
+        L.orc_pdr_tv.argtypes = [_dp, _dp, _dp, _dp, _dp, _ip, C.c_int, C.c_int, C.c_int]
         L.orc_jump_set.argtypes = [_dp, C.c_long, C.c_long, _ip]
         L.orc_jump_set.restype = C.c_long
 
@@ -106,6 +107,9 @@ class Port:
     def pd_tv(self, Y, ws, ds, maxit=0, n_threads=1):
         return self._pd(self.lib.orc_pd_tv, Y, ws, ds, maxit)[:2]
 
+    def pdr_tv(self, Y, ws, ds, maxit=0, n_threads=1):
+        return self._pd(self.lib.orc_pdr_tv, Y, ws, ds, maxit)[:2]
+
     def jump_set(self, x):
         x = _f64(x).ravel(); idx = np.empty(max(x.size, 1), dtype=np.int32)
         c = self.lib.orc_jump_set(_p(x), x.size, 1, idx.ctypes.data_as(_ip))
@@ -133,7 +137,7 @@ class Ref:
         L.DR2_TV.argtypes = [C.c_size_t, C.c_size_t, _dp, C.c_double, C.c_double, C.c_double, C.c_double, _dp,
                              C.c_int, C.c_int, _dp]
         L.DR2L1W_TV.argtypes = [C.c_size_t, C.c_size_t, _dp, _dp, _dp, _dp, C.c_int, C.c_int, _dp]
-        for f in (L.PD2_TV, L.PD_TV):
+        for f in (L.PD2_TV, L.PD_TV, L.PDR_TV):
             f.argtypes = [_dp, _dp, _dp, _dp, _dp, _dp, _ip, C.c_int, C.c_int, C.c_int, C.c_int]
 
     def tv1_hybrid(self, y, lam, exp=None):
@@ -187,6 +191,9 @@ class Ref:
 
     def pd_tv(self, Y, ws, ds, maxit=0, n_threads=1):
         return self._pd(self.lib.PD_TV, Y, ws, ds, maxit, n_threads)
+
+    def pdr_tv(self, Y, ws, ds, maxit=0, n_threads=1):
+        return self._pd(self.lib.PDR_TV, Y, ws, ds, maxit, n_threads)
 
 
 def have_ref():

@@ -17,7 +17,7 @@ import numpy as np
 from . import _lib
 from ._lib import ProxTVError, load, require_device  # noqa: F401
 
-__all__ = ["tv1_1d", "tv1w_1d", "tv1_2d", "tv1w_2d", "tvgen", "tv1_1d_batched", "tv1w_1d_batched", "tv1_2d_batched",
+__all__ = ["tv1_1d", "tv1w_1d", "tv1_2d", "tv1w_2d", "tvgen", "tvgen_pdr", "tv1_1d_batched", "tv1w_1d_batched", "tv1_2d_batched",
            "set_engine", "ProxTVError"]
 
 _N_INFO = 3                      # prox_tv/__init__.py:67
@@ -337,3 +337,34 @@ def tvgen(x, ws, ds, ps, n_threads=1, max_iters=0):
 
 
 tvgen.last_info = None
+
+
+def tvgen_pdr(x, ws, ds, ps, n_threads=1, max_iters=0):
+    r"""The same generalized TV prox as ``tvgen`` solved with the reference's Parallel Douglas-Rachford splitting, ``PDR_TV``
+    (src/TVNDopt.cpp:280-500; reached from MATLAB only in the reference, matlab/solveTVND_PDR.cpp:89 -- SURVEY.md 8f N4).
+
+    Runs exactly ``max_iters`` iterations (0: 35; the reference's loop has no stop test) and, like PD_TV, scales a float64
+    ndarray ``ws`` by ``len(ws)`` IN PLACE.  float64 only from numpy (use the C ABI's ``proxtv_PDR_TV_dev_f32`` for float32
+    device arrays); p = 1 norms only.  ``tvgen_pdr.last_info`` = [iterations, mean|x - x_last|, RC].
+    """
+    assert len(ws) == len(ds)
+    assert len(ws) == len(ps)
+    assert n_threads >= 1
+    assert max_iters >= 0
+    info = np.zeros(_N_INFO)
+    x = np.asfortranarray(x, dtype="float64")
+    ws = force_float_matrix(ws)
+    ps = force_float_matrix(ps)
+    if np.any(ps != 1):
+        raise NotImplementedError("proxtv_b200 implements TV-L1 (p = 1) penalty terms only")
+    y = np.zeros(np.shape(x), order="F", dtype=x.dtype)
+    lib = require_device()
+    dsa = np.array(ds, dtype=np.float64)
+    ns = np.array(x.shape, dtype=np.int32)
+    ok = lib.PDR_TV(_ptr(x), _ptr(ws), _ptr(ps), _ptr(dsa), _ptr(y), _ptr(info), _ptr(ns), x.ndim, len(ws), int(n_threads), int(max_iters))
+    _check(ok and info[2] != 3, "tvgen_pdr")
+    tvgen_pdr.last_info = info
+    return y
+
+
+tvgen_pdr.last_info = None

@@ -153,7 +153,7 @@ int run_drw(const char* fn, bool host_io, size_t M, size_t N, const T* Y, const 
     return 0;
 }
 
-// mode 0: PD2_TV, 1: PD_TV.  y/x host (host_io) or device pointers.
+// mode 0: PD2_TV, 1: PD_TV, 2: PDR_TV.  y/x host (host_io) or device pointers.
 template <typename T>
 int run_pd(const char* fn, int mode, bool host_io, const T* y, double* lambdas, double* norms, double* dims, T* x, double* info,
            int* ns, int nds, int npen, int maxIters, cudaStream_t st) {
@@ -163,7 +163,7 @@ int run_pd(const char* fn, int mode, bool host_io, const T* y, double* lambdas, 
     if (nds <= 0 || !ns) { fail(fn, "invalid dimensions", info); return 0; }
     long long n = 1; for (int i = 0; i < nds; i++) n *= ns[i];
     WsGuard guard(st);
-    if (mode == 1) for (int i = 0; i < npen; i++) lambdas[i] *= npen;                   // TVNDopt.cpp:100-101 (in place)
+    if (mode >= 1) for (int i = 0; i < npen; i++) lambdas[i] *= npen;                   // TVNDopt.cpp:100-101, :339-340 (in place)
     void* ws = g_ws.get(ws_bytes_pd<T>(n, npen > 2 ? npen : 2));
     if (!ws) { fail(fn, "out of memory", info); return 0; }
     const T* dy = y; T* dx = x;
@@ -174,7 +174,8 @@ int run_pd(const char* fn, int mode, bool host_io, const T* y, double* lambdas, 
         if (!cuda_ok(fn, cudaMemcpyAsync((void*)dy, y, (size_t)n * sizeof(T), cudaMemcpyHostToDevice, st), info)) return 0;
     }
     int rc = mode == 0 ? pd2_device<T>(dy, lambdas, dims, dx, info, ns, nds, npen, maxIters, ws, (Engine)g_engine, st)
-                       : pd_device<T>(dy, lambdas, dims, dx, info, ns, nds, npen, maxIters, ws, (Engine)g_engine, st);
+           : mode == 1 ? pd_device<T>(dy, lambdas, dims, dx, info, ns, nds, npen, maxIters, ws, (Engine)g_engine, st)
+                       : pdr_device<T>(dy, lambdas, dims, dx, info, ns, nds, npen, maxIters, ws, (Engine)g_engine, st);
     if (!rc) return 0;
     if (host_io && n > 0) {
         if (!cuda_ok(fn, cudaMemcpyAsync(x, dx, (size_t)n * sizeof(T), cudaMemcpyDeviceToHost, st), info)) return 0;
@@ -309,6 +310,10 @@ int PD_TV(double* y, double* lambdas, double* norms, double* dims, double* x, do
           int maxIters) {
     return run_pd<double>("PD_TV", 1, true, y, lambdas, norms, dims, x, info, ns, nds, npen, maxIters, 0);
 }
+int PDR_TV(double* y, double* lambdas, double* norms, double* dims, double* x, double* info, int* ns, int nds, int npen, int,
+           int maxIters) {
+    return run_pd<double>("PDR_TV", 2, true, y, lambdas, norms, dims, x, info, ns, nds, npen, maxIters, 0);
+}
 
 // ---- Part 2: extensions ----
 int proxtv_prox_fibers_dev_f64(const double* in, double* out, long long nf, int len, long long inc, double lam, const double* lamv, void* stream) {
@@ -352,6 +357,10 @@ int proxtv_PD_TV_dev_f64(const double* y, double* lambdas, double* dims, double*
     return run_pd<double>("proxtv_PD_TV_dev_f64", 1, false, y, lambdas, nullptr, dims, x, info, ns, nds, npen, maxIters, (cudaStream_t)stream); }
 int proxtv_PD_TV_dev_f32(const float* y, double* lambdas, double* dims, float* x, double* info, int* ns, int nds, int npen, int maxIters, void* stream) {
     return run_pd<float>("proxtv_PD_TV_dev_f32", 1, false, y, lambdas, nullptr, dims, x, info, ns, nds, npen, maxIters, (cudaStream_t)stream); }
+int proxtv_PDR_TV_dev_f64(const double* y, double* lambdas, double* dims, double* x, double* info, int* ns, int nds, int npen, int maxIters, void* stream) {
+    return run_pd<double>("proxtv_PDR_TV_dev_f64", 2, false, y, lambdas, nullptr, dims, x, info, ns, nds, npen, maxIters, (cudaStream_t)stream); }
+int proxtv_PDR_TV_dev_f32(const float* y, double* lambdas, double* dims, float* x, double* info, int* ns, int nds, int npen, int maxIters, void* stream) {
+    return run_pd<float>("proxtv_PDR_TV_dev_f32", 2, false, y, lambdas, nullptr, dims, x, info, ns, nds, npen, maxIters, (cudaStream_t)stream); }
 int proxtv_PD_TV_f32(const float* y, double* lambdas, double* dims, float* x, double* info, int* ns, int nds, int npen, int maxIters) {
     return run_pd<float>("proxtv_PD_TV_f32", 1, true, y, lambdas, nullptr, dims, x, info, ns, nds, npen, maxIters, 0); }
 

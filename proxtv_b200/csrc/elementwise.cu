@@ -239,6 +239,95 @@ template <typename T> cudaError_t ew_pd_combine(T* const* dp, T* const* dz, T* c
     return cudaGetLastError();
 }
 
+// ---- parallel Douglas-Rachford combine (src/TVNDopt.cpp:456-475): q = sum_i p_i/k ; x = sum_i z_i/k (both accumulated term by
+//      term) ; z_i += 2 q - x - p_i ; stop = mean|x - x_old| ----
+template <typename T> __global__ void k_pdr_combine(T* const* __restrict__ p, T* const* __restrict__ z, int k, T* __restrict__ x,
+                                                   long long n, double* __restrict__ partial) {
+    double acc = 0;
+    const T kk = (T)k;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        T xo = x[e], xn = T(0), q = T(0);
+        for (int i = 0; i < k; i++) { q += p[i][e] / kk; xn += z[i][e] / kk; }
+        for (int i = 0; i < k; i++) z[i][e] += T(2) * q - xn - p[i][e];
+        x[e] = xn;
+        acc += fabs((double)xn - (double)xo);
+    }
+    acc = block_sum(acc);
+    if (threadIdx.x == 0) partial[blockIdx.x] = acc;
+}
+template <typename T, int K>
+__global__ void __launch_bounds__(256) k_pdr_combine_vec(PdPtrs<T, K> a, T* __restrict__ x, long long n, double* __restrict__ partial) {
+    constexpr int V = 16 / (int)sizeof(T);
+    struct alignas(16) Vec { T v[V]; };
+    double acc = 0;
+    const T kk = (T)K;
+    const long long nv = n / V;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < nv; e += (long long)gridDim.x * blockDim.x) {
+        Vec xo = reinterpret_cast<const Vec*>(x)[e], pv[K], zv[K], xn;
+#pragma unroll
+        for (int i = 0; i < K; i++) { pv[i] = reinterpret_cast<const Vec*>(a.p[i])[e]; zv[i] = reinterpret_cast<const Vec*>(a.z[i])[e]; }
+#pragma unroll
+        for (int c = 0; c < V; c++) {
+            T q = T(0), s = T(0);
+#pragma unroll
+            for (int i = 0; i < K; i++) { q += pv[i].v[c] / kk; s += zv[i].v[c] / kk; }
+#pragma unroll
+            for (int i = 0; i < K; i++) zv[i].v[c] += T(2) * q - s - pv[i].v[c];
+            xn.v[c] = s;
+            acc += fabs((double)s - (double)xo.v[c]);
+        }
+#pragma unroll
+        for (int i = 0; i < K; i++) reinterpret_cast<Vec*>(a.z[i])[e] = zv[i];
+        reinterpret_cast<Vec*>(x)[e] = xn;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)                       // the < V trailing elements
+        for (long long e = nv * V; e < n; e++) {
+            T xo = x[e], s = T(0), q = T(0);
+            for (int i = 0; i < K; i++) { q += a.p[i][e] / kk; s += a.z[i][e] / kk; }
+            for (int i = 0; i < K; i++) a.z[i][e] += T(2) * q - s - a.p[i][e];
+            x[e] = s; acc += fabs((double)s - (double)xo);
+        }
+    acc = block_sum(acc);
+    if (threadIdx.x == 0) partial[blockIdx.x] = acc;
+}
+template <typename T, int K>
+static void launch_pdr_vec(T* const* hp, T* const* hz, T* x, long long n, double* scratch, int nblk, cudaStream_t st) {
+    PdPtrs<T, K> a;
+    for (int i = 0; i < K; i++) { a.p[i] = hp[i]; a.z[i] = hz[i]; }
+    k_pdr_combine_vec<T, K><<<nblk, 256, 0, st>>>(a, x, n, scratch);
+}
+template <typename T> cudaError_t ew_pdr_combine(T* const* dp, T* const* dz, T* const* hp, T* const* hz, int k, T* x, long long n,
+                                                 double* scratch, double* result, cudaStream_t st) {
+    KernelSpan span(KC_ELEMENTWISE, 2, st);
+    bool aligned = (((uintptr_t)x) & 15) == 0;
+    for (int i = 0; i < k && aligned; i++) aligned = ((((uintptr_t)hp[i]) | ((uintptr_t)hz[i])) & 15) == 0;
+    int nblk;
+    if (aligned && k >= 1 && k <= 4) {
+        nblk = (int)grid_for(n, 256, 16 / (int)sizeof(T) * 2); if (nblk > REDUCE_BLOCKS) nblk = REDUCE_BLOCKS;
+        switch (k) {
+            case 1: launch_pdr_vec<T, 1>(hp, hz, x, n, scratch, nblk, st); break;
+            case 2: launch_pdr_vec<T, 2>(hp, hz, x, n, scratch, nblk, st); break;
+            case 3: launch_pdr_vec<T, 3>(hp, hz, x, n, scratch, nblk, st); break;
+            default: launch_pdr_vec<T, 4>(hp, hz, x, n, scratch, nblk, st); break;
+        }
+    } else {
+        nblk = (int)grid_for(n, 256, 4); if (nblk > REDUCE_BLOCKS) nblk = REDUCE_BLOCKS;
+        k_pdr_combine<T><<<nblk, 256, 0, st>>>(dp, dz, k, x, n, scratch);
+    }
+    k_final_mean<<<1, 256, 0, st>>>(scratch, nblk, n, result);
+    return cudaGetLastError();
+}
+// x = y / k (src/TVNDopt.cpp:367)
+template <typename T> __global__ void k_div_scalar(const T* __restrict__ y, T* __restrict__ x, long long n, T kk) {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) x[e] = y[e] / kk;
+}
+template <typename T> cudaError_t ew_div_scalar(const T* y, T* x, long long n, T k, cudaStream_t st) {
+    KernelSpan span(KC_ELEMENTWISE, 1, st);
+    int nblk = (int)grid_for(n, 256, 8); if (nblk > REDUCE_BLOCKS) nblk = REDUCE_BLOCKS;
+    k_div_scalar<T><<<nblk, 256, 0, st>>>(y, x, n, k);
+    return cudaGetLastError();
+}
+
 #define INST(T) \
     template cudaError_t ew_image_means_x2<T>(const T*, long long, int, T*, double*, cudaStream_t); \
     template cudaError_t ew_dr_reflect_cols<T>(const T*, const T*, T*, long long, cudaStream_t); \
@@ -248,7 +337,9 @@ template <typename T> cudaError_t ew_pd_combine(T* const* dp, T* const* dz, T* c
     template cudaError_t ew_dual_update<T>(T*, const T*, const T*, long long, cudaStream_t); \
     template cudaError_t ew_dr_reflect_bcast<T>(const T*, const T*, T*, long long, long long, int, long long, cudaStream_t); \
     template cudaError_t ew_mean_abs_diff<T>(const T*, const T*, long long, double*, double*, cudaStream_t); \
-    template cudaError_t ew_pd_combine<T>(T* const*, T* const*, T* const*, T* const*, int, T*, long long, double*, double*, cudaStream_t);
+    template cudaError_t ew_pd_combine<T>(T* const*, T* const*, T* const*, T* const*, int, T*, long long, double*, double*, cudaStream_t); \
+    template cudaError_t ew_pdr_combine<T>(T* const*, T* const*, T* const*, T* const*, int, T*, long long, double*, double*, cudaStream_t); \
+    template cudaError_t ew_div_scalar<T>(const T*, T*, long long, T, cudaStream_t);
 INST(double)
 INST(float)
 

@@ -79,6 +79,9 @@ template <typename T> cudaError_t ew_mean_abs_diff(const T* a, const T* b, long 
                                                    cudaStream_t st);                  // *result = mean|a-b| (device)
 template <typename T> cudaError_t ew_pd_combine(T* const* dp, T* const* dz, T* const* hp, T* const* hz, int k, T* x, long long n,
                                                 double* scratch, double* result, cudaStream_t st);
+template <typename T> cudaError_t ew_pdr_combine(T* const* dp, T* const* dz, T* const* hp, T* const* hz, int k, T* x, long long n,
+                                                 double* scratch, double* result, cudaStream_t st);
+template <typename T> cudaError_t ew_div_scalar(const T* y, T* x, long long n, T k, cudaStream_t st);             // x = y / k
 constexpr int REDUCE_BLOCKS = 1184;    // 148 SMs x 8; partial sums are combined in a fixed order (deterministic)
 
 // ---- device-resident solvers (solver.cu).  All arrays are device pointers; `ws` must hold ws_bytes_*() bytes. ----
@@ -93,6 +96,9 @@ template <typename T> int pd2_device(const T* y, const double* lambdas, const do
                                      int nds, int npen, int maxIters, void* ws, Engine eng, cudaStream_t st);
 template <typename T> int pd_device(const T* y, const double* lambdas_scaled, const double* dims, T* x, double* info,
                                     const int* ns, int nds, int npen, int maxIters, void* ws, Engine eng, cudaStream_t st);
+// PDR_TV (src/TVNDopt.cpp:280-500): parallel Douglas-Rachford, fixed iteration count; same workspace as pd_device
+template <typename T> int pdr_device(const T* y, const double* lambdas_scaled, const double* dims, T* x, double* info,
+                                     const int* ns, int nds, int npen, int maxIters, void* ws, Engine eng, cudaStream_t st);
 
 }  // namespace ptv
 

@@ -461,13 +461,59 @@ int pd_device(const T* y, const double* lam, const double* dims, T* x, double* i
     return 1;
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// PDR_TV (src/TVNDopt.cpp:280-500): parallel Douglas-Rachford over k one-dimensional TV terms.  x = y / k, z_i = y; a FIXED
+// number of iterations (the reference's loop has no stop test, :394) of  p_i = prox_{d_i}(z_i, k lam_i)  (1D solver: the
+// reference calls TV1D_denoise, :439 -- the same minimiser as every other exact 1D solver here) ; q = mean p_i ; x = mean z_i ;
+// z_i += 2 q - x - p_i ; stop = mean|x - x_last|.  The result x is the average of the z_i BEFORE the last update, like the
+// reference's.  info = {iters, stop, RC_ITERS if iters >= 35 else RC_OK}; the stop value is read back once, after the loop.
+template <typename T>
+int pdr_device(const T* y, const double* lam, const double* dims, T* x, double* info, const int* ns, int nds, int npen,
+               int maxIters, void* ws, Engine eng, cudaStream_t st) {
+    long long n = 1; for (int i = 0; i < nds; i++) n *= ns[i];
+    if (maxIters <= 0) maxIters = MAX_ITERS_DR;                                                       // :320
+    if (npen > 64) { printf("PDR_TV: more than 64 penalty terms are not supported\n"); if (info) info[INFO_RC] = RC_ERROR; return 0; }
+    FiberGeom g[64];
+    for (int i = 0; i < npen; i++)
+        if (!geom_of(ns, nds, dims[i], n, &g[i])) { printf("PDR_TV: invalid penalty dimensions\n");
+                                                     if (info) info[INFO_RC] = RC_ERROR; return 0; }
+    double stop = 0; int iters = 0;
+    if (n > 0 && npen > 0) {
+        char* w = (char*)ws; const size_t ab = align256((size_t)n * sizeof(T));
+        T* hp[64]; T* hz[64];
+        for (int i = 0; i < npen; i++) { hp[i] = (T*)w; w += ab; hz[i] = (T*)w; w += ab; }
+        T* scr = (T*)w; w += 3 * ab;
+        double* scratch = (double*)w; double* dres = scratch + REDUCE_BLOCKS; w += SCRATCH_BYTES;
+        T** dp = (T**)w; T** dz = dp + 64;
+        PTV_TRY(cudaMemcpyAsync(dp, hp, sizeof(T*) * npen, cudaMemcpyHostToDevice, st));
+        PTV_TRY(cudaMemcpyAsync(dz, hz, sizeof(T*) * npen, cudaMemcpyHostToDevice, st));
+        PTV_TRY(cudaStreamSynchronize(st));    // hp/hz are stack arrays
+        PTV_TRY(ew_div_scalar<T>(y, x, n, (T)npen, st));                                              // :365-370
+        for (int i = 0; i < npen; i++) PTV_TRY(cudaMemcpyAsync(hz[i], y, (size_t)n * sizeof(T), cudaMemcpyDeviceToDevice, st));
+        while (iters < maxIters) {                                                                    // :394
+            for (int i = 0; i < npen; i++)
+                PTV_TRY(prox_fibers<T>(hz[i], nullptr, IN_A, hp[i], 0, g[i], (T)lam[i], nullptr, eng, scr, st, 3 * n));  // :409-449
+            PTV_TRY(ew_pdr_combine<T>(dp, dz, hp, hz, npen, x, n, scratch, dres, st));                        // :456-475
+            iters++;
+        }
+        if (iters > 0 && !read_stop(dres, &stop, st)) { PTV_TRY(cudaGetLastError()); PTV_TRY(cudaErrorUnknown); }
+    } else if (n > 0) {
+        PTV_TRY(cudaMemsetAsync(x, 0, (size_t)n * sizeof(T), st));
+        iters = maxIters;
+    }
+    if (info) { info[INFO_ITERS] = iters; info[INFO_GAP] = stop;
+                info[INFO_RC] = iters >= MAX_ITERS_DR ? RC_ITERS : RC_OK; }                           // :481-492
+    return 1;
+}
+
 #define INST(T) \
     template size_t ws_bytes_dr2<T>(size_t, size_t, int); \
     template int dr2_device<T>(size_t, size_t, int, int, const T*, T, T, T*, int, double*, void*, Engine, cudaStream_t); \
     template int drw_device<T>(size_t, size_t, const T*, const T*, const T*, T*, int, double*, void*, Engine, cudaStream_t); \
     template size_t ws_bytes_pd<T>(long long, int); \
     template int pd2_device<T>(const T*, const double*, const double*, T*, double*, const int*, int, int, int, void*, Engine, cudaStream_t); \
-    template int pd_device<T>(const T*, const double*, const double*, T*, double*, const int*, int, int, int, void*, Engine, cudaStream_t);
+    template int pd_device<T>(const T*, const double*, const double*, T*, double*, const int*, int, int, int, void*, Engine, cudaStream_t); \
+    template int pdr_device<T>(const T*, const double*, const double*, T*, double*, const int*, int, int, int, void*, Engine, cudaStream_t);
 INST(double)
 INST(float)
 

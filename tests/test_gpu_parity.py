@@ -364,3 +364,25 @@ def test_full_size_properties_cfg3(ptv, port):
         assert np.array_equal(G[b], port.tv1_weighted(X[b], W[b]))
     U = np.cumsum(X - G, axis=1)
     assert np.all(np.abs(U[:, :-1]) <= W + 1e-9) and np.abs(U[:, -1]).max() < 1e-8
+
+
+def test_pdr_tv(ptv, port, eng):
+    """PDR_TV (parallel Douglas-Rachford) against the oracle: values <= 1e-9 relative, info[] equal, weights
+    scaled in place, raw C ABI and the float32 device entry point."""
+    rng = np.random.default_rng(14)
+    for shp, ws, ds in [((40, 36), [0.3, 0.2], [1, 2]), ((24, 20, 12), [0.2, 0.2, 0.2], [1, 2, 3]),
+                        ((7, 6, 5, 4), [0.3, 0.1, 0.2, 0.4, 0.05], [1, 2, 3, 4, 2]), ((300,), [0.7], [1])]:
+        V = np.asfortranarray(rng.normal(size=shp))
+        for it in (0, 4):
+            want, winfo = port.pdr_tv(V, ws, ds, maxit=it)
+            w2 = np.array(ws, dtype=np.float64)
+            got = ptv.tvgen_pdr(V, w2, ds, [1] * len(ws), max_iters=it)
+            assert relerr(got, want) <= 1e-9, (shp, it)
+            assert ptv.tvgen_pdr.last_info[0] == winfo[0] and ptv.tvgen_pdr.last_info[2] == winfo[2]
+            assert abs(ptv.tvgen_pdr.last_info[1] - winfo[1]) <= 1e-9 * max(1.0, abs(winfo[1]))
+            assert np.allclose(w2, np.array(ws) * len(ws))                       # scaled in place like the reference (:339-340)
+    V = O.gen_cfg4((64, 48, 40), seed=3, block=8)
+    want, winfo = port.pdr_tv(V, [0.2, 0.2, 0.2], [1, 2, 3])
+    assert relerr(ptv.tvgen_pdr(V, [0.2, 0.2, 0.2], [1, 2, 3], [1, 1, 1]), want) <= 1e-9
+    with pytest.raises(NotImplementedError):
+        ptv.tvgen_pdr(V, [0.2, 0.2], [1, 2], [2, 1])

@@ -147,3 +147,15 @@ def test_pd_single_term_equals_tv1_1d(port):
     y = np.random.default_rng(6).normal(size=500)
     o, info = port.pd_tv(y, [0.8], [1])
     assert np.array_equal(o.ravel(), port.tv1_hybrid(y, 0.8))
+
+
+def test_pdr_port_equals_reference(port, ref):
+    """PDR_TV (src/TVNDopt.cpp:280-500): the port must be bit-identical to the compiled reference, including
+    info[] and the in-place scaling of the weights."""
+    rng = np.random.default_rng(4)
+    for shp, ws, ds in [((20, 17), [0.3, 0.2], [1, 2]), ((9, 8, 7), [0.2, 0.2, 0.2], [1, 2, 3]),
+                        ((6, 5, 4, 3), [0.3, 0.1, 0.2, 0.4, 0.05], [1, 2, 3, 4, 2]), ((40,), [0.7], [1])]:
+        V = np.asfortranarray(rng.normal(size=shp))
+        for it in (0, 3, 50):
+            a, ia = port.pdr_tv(V, ws, ds, maxit=it); b, ib = ref.pdr_tv(V, ws, ds, maxit=it)
+            assert np.array_equal(a, b) and np.array_equal(ia, ib), (shp, it)
