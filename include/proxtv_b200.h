@@ -180,6 +180,9 @@ int proxtv_lane_prox_dev_f32(int op, const float *A, const float *B, const float
                              long long inc, float lam, void *stream);
 void proxtv_lane_tuning(int clen, int halo, int variant);
 unsigned long long proxtv_lane_stats(int reset);
+/* tools: device buffer of 4 x cap_tasks uint64 that receives, per warp task of the next launches, {start ns, scan end ns, end ns, SM id}
+ * (globaltimer); NULL switches the log off. */
+void proxtv_lane_tasklog(unsigned long long *dev, long long cap_tasks);
 
 #ifdef __cplusplus
 }

@@ -235,6 +235,7 @@ int proxtv_lane_prox_dev_f32(int op, const float* A, const float* B, const float
     return 1;
 }
 void proxtv_lane_tuning(int clen, int halo, int variant) { ptvl::lane_set_tuning(clen, halo, variant); }
+void proxtv_lane_tasklog(unsigned long long* dev, long long cap_tasks) { ptvl::lane_set_tasklog(dev, cap_tasks); }
 unsigned long long proxtv_lane_stats(int reset) { return ptvl::lane_read_stats(reset); }
 
 // ---- Part 1: drop-in symbols ----

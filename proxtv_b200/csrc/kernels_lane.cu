@@ -66,6 +66,7 @@ template <typename T> struct LaneArgs {
     int* rec;                       // [3][nchunks][slabs*gps*32] chunk records (in, out, overflow)
     int* group_count;               // [slabs*gps] finished-task counters (self-resetting)
     unsigned long long* stats;      // [0] repair scans, [1] retired lanes
+    unsigned long long* tlog;       // optional (tools): per task {start ns, scan end ns, end ns, SM id}
     long long ntasks;
 };
 
@@ -445,6 +446,9 @@ __device__ __noinline__ int repair_fiber(const LaneArgs<T>* a, long long fiber, 
                                            X[g] = OP == LOP_DR_B ? PassOp<T, OP>::out(v, B[g], C[g]) : v; } });
 }
 
+__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ unsigned smid() { unsigned r; asm volatile("mov.u32 %0, %%smid;" : "=r"(r)); return r; }
+
 template <typename T, int W, int RT, int TITER, int OP, int NW, int LAY, bool SPEC>
 __global__ void __launch_bounds__(NW * 32, (12 + NW - 1) / NW) k_lane(const __grid_constant__ LaneArgs<T> a) {
     using SM = LaneSmem<T, W, RT, OP, LAY, SPEC>;
@@ -468,6 +472,8 @@ __global__ void __launch_bounds__(NW * 32, (12 + NW - 1) / NW) k_lane(const __gr
     }
     __syncthreads();                                    // the only CTA barrier: reciprocal table ready
     if (!has_task) return;
+    if (a.tlog && lane == 0) { a.tlog[task * 4 + 0] = gtimer(); a.tlog[task * 4 + 3] = smid(); }
+    struct TLogEnd { unsigned long long* p; __device__ ~TLogEnd() { if (p) *p = gtimer(); } } tlog_end{a.tlog && lane == 0 ? a.tlog + task * 4 + 2 : nullptr};
 
     const ChunkPlan pl = a.plan;
     const long long group = task / pl.nchunks;
@@ -501,6 +507,7 @@ __global__ void __launch_bounds__(NW * 32, (12 + NW - 1) / NW) k_lane(const __gr
         warp_task<T, W, TITER>(env, feed, drain, w, rcp, g, a.lam, TITER + TITER / 2 + RT, (TaskStats*)nullptr);
     }
 
+    if (a.tlog && lane == 0) a.tlog[task * 4 + 1] = gtimer();
     // ---- chunk records; the last warp of the fiber group to finish verifies (and repairs) its 32 fibers ----
     int* rec = a.rec;
     rec[(0 * (long long)pl.nchunks + chunk) * nfp + fiber] = env.L.in_rec;
@@ -567,6 +574,8 @@ static bool make_map(CUtensorMap* m, const T* base, long long d0, long long d1, 
 
 struct LaneTuning { int clen, halo, variant; };
 static LaneTuning g_tune = {0, 32, 0};        // chunk length (0 = one wave), halo rows, variant
+static unsigned long long* g_tlog = nullptr; static long long g_tlog_cap = 0;
+void lane_set_tasklog(unsigned long long* dev, long long cap_tasks) { g_tlog = dev; g_tlog_cap = cap_tasks; }
 void lane_set_tuning(int clen, int halo, int variant) { g_tune.clen = clen; g_tune.halo = halo; g_tune.variant = variant; }
 
 // Scratch of the lane engine, one buffer per device (grow-only, zero-initialised when (re)allocated):
@@ -684,6 +693,7 @@ cudaError_t lane_prox(int op, const T* A, const T* B, const T* C, T* X, long lon
         a.rec = a.group_count + g_scr[d].cap_groups;
     }
     a.ntasks = groups * a.plan.nchunks;
+    a.tlog = (g_tlog && a.ntasks <= g_tlog_cap) ? g_tlog : nullptr;
     return launch_any<T>(lay, op, g_tune.variant, a, st, nullptr);
 }
 

@@ -312,6 +312,9 @@ PTV_HD void warp_task(Env& env, Feed& feed, Drain& drain, const Window<T, W>& w,
             if (want > g.n) want = g.n;
             while (row_req < want && row_req + R <= row_lo + W && row_req - row_hi < Feed::MAXQ * R) { feed.request(env, row_req); row_req += R; }
             while (row_hi < row_req && feed.landed(env, row_hi, false)) row_hi += R;      // take over what has landed
+            // a feed with a short queue (MAXQ == 1) was blocked above by the tile it has just handed over: ask again
+            if (Feed::MAXQ < 2)
+                while (row_req < want && row_req + R <= row_lo + W && row_req - row_hi < Feed::MAXQ * R) { feed.request(env, row_req); row_req += R; }
         }
         // ---- how many steps can every participating lane take? ----
         const int lim = row_hi < g.n - 1 ? row_hi : g.n - 1;

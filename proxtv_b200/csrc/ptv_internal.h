@@ -112,5 +112,6 @@ cudaError_t lane_prox(int op, const T* A, const T* B, const T* C, T* X, long lon
 void* lane_scratch(long long nf, int len);          // per-device records / counters (allocates: call outside stream capture)
 bool lane_shape_ok(long long nf, int len, long long inc, size_t elem, const void* const* ptrs, int nptrs);
 void lane_set_tuning(int clen, int halo, int variant);
+void lane_set_tasklog(unsigned long long* dev, long long cap_tasks);
 unsigned long long lane_read_stats(int reset);
 }  // namespace ptvl
