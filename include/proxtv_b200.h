@@ -178,6 +178,9 @@ int proxtv_lane_prox_dev_f64(int op, const double *A, const double *B, const dou
                              long long inc, double lam, void *stream);
 int proxtv_lane_prox_dev_f32(int op, const float *A, const float *B, const float *C, float *X, long long nf, int len,
                              long long inc, float lam, void *stream);
+/* same with a second result array (the ops that write two results: 3 = first half of a Douglas-Rachford iteration, transposed) */
+int proxtv_lane_prox2_dev_f64(int op, const double *A, const double *B, const double *C, double *X, double *X2, long long nf, int len,
+                              long long inc, double lam, void *stream);
 void proxtv_lane_tuning(int clen, int halo, int variant);
 unsigned long long proxtv_lane_stats(int reset);
 /* tools: device buffer of 4 x cap_tasks uint64 that receives, per warp task of the next launches, {start ns, scan end ns, end ns, SM id}

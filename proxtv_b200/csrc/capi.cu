@@ -207,7 +207,7 @@ extern "C" {
 int proxtv_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; } return n; }
 const char* proxtv_last_error(void) { return g_err.c_str(); }
 const char* proxtv_version(void) { return "proxtv_b200 0.1 (sm_100a)"; }
-int proxtv_set_engine(int e) { int o = g_engine; if (e >= 0 && e <= 7) g_engine = e; return o; }
+int proxtv_set_engine(int e) { int o = g_engine; if (e >= 0 && e <= 8) g_engine = e; return o; }
 void* proxtv_host_alloc(size_t bytes) { void* p = nullptr; if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; } return p; }
 void proxtv_host_free(void* p) { if (p) cudaFreeHost(p); }
 void proxtv_profile_enable(int on) { profile_enable(on); }
@@ -223,6 +223,15 @@ int proxtv_lane_prox_dev_f64(int op, const double* A, const double* B, const dou
     if (!scr) return 0;
     cudaError_t e = ptvl::lane_prox<double>(op, A, B, C, X, nf, len, inc, lam, scr, (cudaStream_t)stream);
     if (e != cudaSuccess) { cudaGetLastError(); g_err = std::string("proxtv_lane_prox_dev_f64: ") + cudaGetErrorString(e); return 0; }
+    return 1;
+}
+int proxtv_lane_prox2_dev_f64(int op, const double* A, const double* B, const double* C, double* X, double* X2, long long nf, int len, long long inc,
+                              double lam, void* stream) {
+    WsGuard guard((cudaStream_t)stream);
+    void* scr = ptvl::lane_scratch(nf, len);
+    if (!scr) return 0;
+    cudaError_t e = ptvl::lane_prox<double>(op, A, B, C, X, nf, len, inc, lam, scr, (cudaStream_t)stream, X2);
+    if (e != cudaSuccess) { cudaGetLastError(); g_err = std::string("proxtv_lane_prox2_dev_f64: ") + cudaGetErrorString(e); return 0; }
     return 1;
 }
 int proxtv_lane_prox_dev_f32(int op, const float* A, const float* B, const float* C, float* X, long long nf, int len, long long inc,

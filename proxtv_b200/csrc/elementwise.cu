@@ -328,7 +328,23 @@ template <typename T> cudaError_t ew_div_scalar(const T* y, T* x, long long n, T
     return cudaGetLastError();
 }
 
+// first Douglas-Rachford half-iteration on the constant start image t (2 * mean): the column prox of a constant is that constant, so
+// d = t - x_cols and u = Y - (2 d - t) need no scan; written with the very expressions the lane drain uses (PassOp<LOP_DRA>)
+template <typename T> __global__ void k_dr_first(const T* __restrict__ Y, const T* __restrict__ t, T* __restrict__ U, T* __restrict__ D, long long n) {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        const T c = t[e], d = c - c;
+        D[e] = d; U[e] = Y[e] - (T(2) * d - c);
+    }
+}
+template <typename T> cudaError_t ew_dr_first(const T* Y, const T* t, T* U, T* D, long long n, cudaStream_t st) {
+    KernelSpan span(KC_ELEMENTWISE, 1, st);
+    int nblk = (int)grid_for(n, 256, 8); if (nblk > REDUCE_BLOCKS) nblk = REDUCE_BLOCKS;
+    k_dr_first<T><<<nblk, 256, 0, st>>>(Y, t, U, D, n);
+    return cudaGetLastError();
+}
+
 #define INST(T) \
+    template cudaError_t ew_dr_first<T>(const T*, const T*, T*, T*, long long, cudaStream_t); \
     template cudaError_t ew_image_means_x2<T>(const T*, long long, int, T*, double*, cudaStream_t); \
     template cudaError_t ew_dr_reflect_cols<T>(const T*, const T*, T*, long long, cudaStream_t); \
     template cudaError_t ew_dr_combine_rows<T>(const T*, const T*, const T*, T*, long long, cudaStream_t); \

@@ -52,18 +52,30 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 
 // ---------------------------------------------------------------- kernel arguments
-enum LaneOp { LOP_PLAIN = 0, LOP_DR_B = 1, LOP_DR_B_FINAL = 2 };
+// Fused pass arithmetic.  Two generations of the Douglas-Rachford forms:
+//   LOP_DR_B / LOP_DR_B_FINAL  "staged": the row pass combines three operand tiles when they land (in = Y - (2 (t - x1) - t)); costs
+//                              8 KB of staging per warp, i.e. a third of the resident warps
+//   LOP_DRA / _FINAL / LOP_DRB "transposed": every pass lands plain tiles, does its arithmetic in the DRAIN (operands read with
+//                              coalesced loads, one epoch ahead) and writes its results TRANSPOSED, so that both passes of an
+//                              iteration are strided passes -- one over the row-major copies, one over the column-major ones
+enum LaneOp { LOP_PLAIN = 0, LOP_DR_B = 1, LOP_DR_B_FINAL = 2, LOP_DRA = 3, LOP_DRA_FINAL = 4, LOP_DRB = 5 };
+template <int OP> struct OpTraits {
+    static constexpr bool staged = OP == LOP_DR_B || OP == LOP_DR_B_FINAL;           // B, C tiles combined at landing
+    static constexpr bool tout = OP >= LOP_DRA;                                     // results written transposed (fiber-major)
+    static constexpr bool two_out = OP == LOP_DRA;                                  // second result array X2
+    static constexpr int drain_reads = (OP == LOP_DR_B || OP == LOP_DRA || OP == LOP_DRA_FINAL) ? 2 : (OP == LOP_DRB ? 1 : 0);
+};
 
 template <typename T> struct LaneArgs {
     CUtensorMap tmA, tmB, tmC;      // loads (B, C only for the fused Douglas-Rachford forms)
     CUtensorMap tmX;                // store (CONTIG layout)
-    const T* A; const T* B; const T* C; T* X;
+    const T* A; const T* B; const T* C; T* X; T* X2;
     long long inc;                  // fiber stride (STRIDED: fibers per slab; CONTIG: 1)
     long long per_slab;             // fibers per slab (STRIDED: inc; CONTIG: nf)
     int slabs, gps;                 // groups of 32 fibers per slab
-    ChunkPlan plan;
+    TaskPlan plan;
     T lam;
-    int* rec;                       // [3][nchunks][slabs*gps*32] chunk records (in, out, overflow)
+    int* rec;                       // [3][plan.nmax][slabs*gps*32] chunk records (in, out, overflow)
     int* group_count;               // [slabs*gps] finished-task counters (self-resetting)
     unsigned long long* stats;      // [0] repair scans, [1] retired lanes
     unsigned long long* tlog;       // optional (tools): per task {start ns, scan end ns, end ns, SM id}
@@ -72,15 +84,21 @@ template <typename T> struct LaneArgs {
 
 // fused arithmetic of a pass: what a lane scans (in) and what it writes for prox value x (out)
 template <typename T, int OP> struct PassOp {
+    // what a lane scans, from the landed tiles (staged forms only; every other form scans A as it is)
     static __device__ __forceinline__ T in(T a, T b, T c) {
-        if (OP == LOP_PLAIN) return a;
+        if (!OpTraits<OP>::staged) return a;
         const T d = c - b;                                   // t - prox_cols(t)              (src/TV2Dopt.cpp:545-546)
         if (OP == LOP_DR_B) return a - (T(2) * d - c);       // Y - s, s = 2 (t - x) - t      (:411, :515)
         return a - d;                                        // final: s = t - x              (:427)
     }
-    static __device__ __forceinline__ T out(T x, T b, T c) {
-        if (OP == LOP_DR_B) return (c - b) + x;              // t' = 0.5 (t + s + 2 prox_rows(Y - s)) = (t - x_cols) + x_rows   (:419-422)
-        return x;
+    // what the drain writes for prox value x and the operands b, c read at the drained position: o1 -> X, o2 -> X2
+    static __device__ __forceinline__ void out(T x, T b, T c, T& o1, T& o2) {
+        o2 = T(0);
+        if (OP == LOP_DR_B) o1 = (c - b) + x;                // t' = 0.5 (t + s + 2 prox_rows(Y - s)) = (t - x_cols) + x_rows   (:419-422)
+        else if (OP == LOP_DRA) { const T d = c - x; o2 = d; o1 = b - (T(2) * d - c); }   // b = Y, c = t: d = t - x_cols, u = Y - (2 d - t)
+        else if (OP == LOP_DRA_FINAL) o1 = b - (c - x);      // u = Y - (t - x_cols)          (:427)
+        else if (OP == LOP_DRB) o1 = b + x;                  // b = d: t' = (t - x_cols) + x_rows
+        else o1 = x;
     }
 };
 
@@ -188,7 +206,7 @@ __device__ __forceinline__ void run_dev(Lane<T>& L, const DevWin<T, W> dw, const
     L.in_rec = in_;
 }
 
-template <typename T, int W, bool SPEC> struct DevEnv {
+template <typename T, int W> struct DevEnv {
     Lane<T> L; int lane; DevWin<T, W> dw;
     template <class F> __device__ __forceinline__ void each(F f) { f(L, lane); }
     template <class F> __device__ __forceinline__ int rmin(F f) { return __reduce_min_sync(0xffffffffu, f(L, lane)); }
@@ -204,7 +222,7 @@ template <typename T, int W, bool SPEC> struct DevEnv {
 template <typename T, int W, int RT, int OP> struct FeedStrided {
     static constexpr int R = RT;
     static constexpr int NST = 2;                       // staging tiles for the B / C operands of the fused forms
-    static constexpr int MAXQ = (OP == LOP_PLAIN) ? W / RT : NST;
+    static constexpr int MAXQ = OpTraits<OP>::staged ? NST : W / RT;
     static constexpr int NBAR = W / RT;
     const LaneArgs<T>* a; T* win; T* stB; T* stC; uint64_t* bar; int x0, z, q0, lane;
     template <class Env> __device__ __forceinline__ void request(Env&, int row0) {
@@ -213,9 +231,9 @@ template <typename T, int W, int RT, int OP> struct FeedStrided {
             fence_proxy_async();                        // the slot's last generic-proxy accesses precede the async write
             const int q = (int)((unsigned)row0 / (unsigned)R) - q0;
             uint64_t* b = bar + ((unsigned)q % (unsigned)NBAR);
-            mbar_expect_tx(b, (uint32_t)(R * LANES * sizeof(T) * (OP == LOP_PLAIN ? 1 : 3)));
+            mbar_expect_tx(b, (uint32_t)(R * LANES * sizeof(T) * (OpTraits<OP>::staged ? 3 : 1)));
             tma_load_3d(win + ((row0 & (W - 1)) << 5), &a->tmA, x0, row0, z, b);
-            if (OP != LOP_PLAIN) {
+            if (OpTraits<OP>::staged) {
                 tma_load_3d(stB + (q % NST) * R * LANES, &a->tmB, x0, row0, z, b);
                 tma_load_3d(stC + (q % NST) * R * LANES, &a->tmC, x0, row0, z, b);
             }
@@ -230,7 +248,7 @@ template <typename T, int W, int RT, int OP> struct FeedStrided {
         bool ok = __all_sync(0xffffffffu, mbar_test(b, parity));
         if (!ok && !block) return false;
         while (!ok) ok = __all_sync(0xffffffffu, mbar_try(b, parity));
-        if (OP != LOP_PLAIN) {
+        if (OpTraits<OP>::staged) {
             const T* sb = stB + (q % NST) * R * LANES; const T* sc = stC + (q % NST) * R * LANES;
             T* wr = win + ((row0 & (W - 1)) << 5);
 #pragma unroll
@@ -241,87 +259,88 @@ template <typename T, int W, int RT, int OP> struct FeedStrided {
     }
 };
 
-// Fused forms without shared-memory staging of the B / C operands: the A tile (Y) still arrives by TMA, B and C (x_cols, t) are
-// fetched by the lanes themselves -- a window row is one coalesced 256-byte line -- into registers when the tile is requested,
-// one epoch before it is taken over, so their latency is covered by the scan in between.  Saves 8 KB of shared memory per
-// warp (11 resident warps per SM instead of 8) for 32 registers; one tile outstanding at a time.
-template <typename T, int W, int RT, int OP> struct FeedStridedReg {
-    static constexpr int R = RT;
-    static constexpr int MAXQ = 1;
-    static constexpr int NBAR = W / RT;
-    const LaneArgs<T>* a; T* win; uint64_t* bar; int x0, z, q0, lane; long long gbase, stride; bool valid; int n;
-    T fb[RT], fc[RT];
-    template <class Env> __device__ __forceinline__ void request(Env&, int row0) {
-        __syncwarp();
-        if (lane == 0) {
-            fence_proxy_async();
-            const int q = (int)((unsigned)row0 / (unsigned)R) - q0;
-            uint64_t* b = bar + ((unsigned)q % (unsigned)NBAR);
-            mbar_expect_tx(b, (uint32_t)(R * LANES * sizeof(T)));
-            tma_load_3d(win + ((row0 & (W - 1)) << 5), &a->tmA, x0, row0, z, b);
-        }
-        if (valid) {
-            const long long g0 = gbase + (long long)row0 * stride;
-            const T* __restrict__ qb = a->B + g0; const T* __restrict__ qc = a->C + g0;
-#pragma unroll
-            for (int u = 0; u < R; u++) {
-                const bool in = row0 + u < n;
-                fb[u] = in ? __ldg(qb) : T(0); fc[u] = in ? __ldg(qc) : T(0);
-                qb += stride; qc += stride;
-            }
-        }
-    }
-    template <class Env> __device__ __forceinline__ bool landed(Env&, int row0, bool block) {
-        const unsigned q = (unsigned)row0 / (unsigned)R - (unsigned)q0;
-        uint64_t* b = bar + (q % (unsigned)NBAR);
-        const uint32_t parity = (uint32_t)((q / (unsigned)NBAR) & 1u);
-        bool ok = __all_sync(0xffffffffu, mbar_test(b, parity));
-        if (!ok && !block) return false;
-        while (!ok) ok = __all_sync(0xffffffffu, mbar_try(b, parity));
-        T* wr = win + ((row0 & (W - 1)) << 5);
-#pragma unroll
-        for (int r = 0; r < R; r++) wr[r * LANES + lane] = PassOp<T, OP>::in(wr[r * LANES + lane], fb[r], fc[r]);
-        __syncwarp();
-        return true;
-    }
+template <typename T> struct Vec16 { };
+template <> struct Vec16<double> {
+    static __device__ __forceinline__ void ld(uint32_t a, double* v) { asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v[0]), "=d"(v[1]) : "r"(a)); }
+    static __device__ __forceinline__ void st(uint32_t a, const double* v) { asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(v[0]), "d"(v[1]) : "memory"); }
+};
+template <> struct Vec16<float> {
+    static __device__ __forceinline__ void ld(uint32_t a, float* v) { asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(a)); }
+    static __device__ __forceinline__ void st(uint32_t a, const float* v) { asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory"); }
 };
 
+
+__device__ __forceinline__ void st_global_v16(double* p, const double* v) { asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v[0]), "d"(v[1]) : "memory"); }
+__device__ __forceinline__ void st_global_v16(float* p, const float* v) { asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory"); }
+
+// 8 results per lane (rows r0 .. r0+7 of 32 adjacent fibers) written TRANSPOSED -- dst[f * n + r], fiber-major -- without any extra
+// shared memory: the window rows just swept are dead, so their 32 x 8 block is rewritten fiber-major in place (16-byte chunks,
+// chunk c of fiber f at position c ^ s(f): conflict-free on both sides) and read back so that NCH adjacent lanes hold the 8
+// consecutive results of ONE fiber; a store instruction then covers 32 / NCH fibers x one full 64-byte (f64) / 32-byte (f32) run instead
+// of 32 scattered 16-byte pieces.  dst points at (fiber 0 of the group, row r0); fibers >= nvalid are not written.
+template <typename T, int W>
+__device__ __forceinline__ void store8_transposed(const Window<T, W>& w, int r0, int lane, const T* xs, T* dst, long long n, int nvalid) {
+    constexpr int EPC = 16 / (int)sizeof(T), NCH = 8 / EPC, FB = 8 * (int)sizeof(T), FPI = LANES / NCH, SG = 8 / NCH;
+    const uint32_t reg = s32(w.win) + (uint32_t)(((r0 & (W - 1)) << 5) * (int)sizeof(T));
+    __syncwarp();                                        // every lane has read its column of these rows
+#pragma unroll
+    for (int c = 0; c < NCH; c++) Vec16<T>::st(reg + (uint32_t)(lane * FB + ((c ^ ((lane / SG) & (NCH - 1))) << 4)), xs + c * EPC);
+    __syncwarp();
+    const int cc = lane % NCH;
+#pragma unroll
+    for (int k = 0; k < NCH; k++) {
+        const int f = lane / NCH + FPI * k;
+        T v[EPC];
+        Vec16<T>::ld(reg + (uint32_t)(f * FB + ((cc ^ ((f / SG) & (NCH - 1))) << 4)), v);
+        if (f < nvalid) st_global_v16(dst + (long long)f * n + cc * EPC, v);
+    }
+    __syncwarp();                                        // the block may be rewritten (second output, next tile)
+}
+
 template <typename T, int W, int OP> struct DrainStrided {
-    const T* __restrict__ B; const T* __restrict__ C; T* __restrict__ X; long long gbase, stride;     // gbase includes the lane
-    // operands of the fused Douglas-Rachford drain for the group of rows that will be swept next, fetched one epoch ahead
-    // (they were read by this warp's feeder a window ago: L2 hits, whose latency would otherwise be exposed once per epoch)
+    using TR = OpTraits<OP>;
+    const T* __restrict__ B; const T* __restrict__ C; T* __restrict__ X; T* __restrict__ X2;
+    long long gbase, stride;          // this lane's fiber: element of row 0, element stride between rows
+    int ce;                           // end of the chunk (rows beyond are not this task's)
+    long long tbase, n; int nvalid;   // transposed results: element (fiber 0 of the group, row 0) of the fiber-major array; fibers in the group
+    // operands of the fused drain arithmetic for the group of rows that will be swept next, fetched one epoch ahead (coalesced: a
+    // window row is one contiguous line of every operand array)
     T pb[8], pc[8]; int pf_row;
-    __device__ __forceinline__ void prefetch(int r0, int ce, bool valid) {
-        if (OP != LOP_DR_B || !valid || r0 + 8 > ce || r0 == pf_row) return;
+    __device__ __forceinline__ void fetch(int r0) {
         const long long g0 = gbase + (long long)r0 * stride;
         const T* __restrict__ qb = B + g0; const T* __restrict__ qc = C + g0;
 #pragma unroll
-        for (int u = 0; u < 8; u++) { pb[u] = __ldg(qb); pc[u] = __ldg(qc); qb += stride; qc += stride; }
-        pf_row = r0;
+        for (int u = 0; u < 8; u++) { pb[u] = __ldg(qb); qb += stride; if (TR::drain_reads > 1) { pc[u] = __ldg(qc); qc += stride; } }
     }
-    __device__ __forceinline__ void rows8(const Window<T, W>&, int r0, int cnt, int, const T* xs, bool valid) {
-        if (!valid) return;
+    __device__ __forceinline__ void prefetch(int r0, int ce, bool valid) {
+        if (TR::drain_reads == 0 || !valid || r0 + 8 > ce || r0 == pf_row) return;
+        fetch(r0); pf_row = r0;
+    }
+    __device__ __forceinline__ void rows8(const Window<T, W>& w, int r0, int cnt, int lane, const T* xs, bool valid) {
+        if (!valid && !(TR::tout && cnt == 8)) return;      // the transposed store is a warp-cooperative exchange: every lane takes part
         const long long g0 = gbase + (long long)r0 * stride;
-        T* __restrict__ px = X + g0;
-        if (cnt == 8) {                                  // whole group: one pointer, bumped by the row stride
-            if (OP == LOP_DR_B) {
-                if (r0 != pf_row) {
-                    const T* __restrict__ qb = B + g0; const T* __restrict__ qc = C + g0;
+        if (cnt == 8) {                                     // whole group
+            T o1[8], o2[8];
+            if (TR::drain_reads > 0 && valid && r0 != pf_row) fetch(r0);
 #pragma unroll
-                    for (int u = 0; u < 8; u++) { pb[u] = __ldg(qb); pc[u] = __ldg(qc); qb += stride; qc += stride; }
-                }
-#pragma unroll
-                for (int u = 0; u < 8; u++) { *px = PassOp<T, OP>::out(xs[u], pb[u], pc[u]); px += stride; }
-                pf_row = -1;
+            for (int u = 0; u < 8; u++) PassOp<T, OP>::out(xs[u], pb[u], pc[u], o1[u], o2[u]);
+            pf_row = -1;
+            if (TR::tout) {
+                store8_transposed<T, W>(w, r0, lane, o1, X + tbase + r0, n, nvalid);
+                if (TR::two_out) store8_transposed<T, W>(w, r0, lane, o2, X2 + tbase + r0, n, nvalid);
             } else {
+                T* __restrict__ px = X + g0;                // one pointer, bumped by the row stride
 #pragma unroll
-                for (int u = 0; u < 8; u++) { *px = xs[u]; px += stride; }
+                for (int u = 0; u < 8; u++) { *px = o1[u]; px += stride; }
             }
             return;
         }
-        for (int u = 0; u < cnt; u++) {                  // the last, partial group of a fiber
+        for (int u = 0; u < cnt; u++) {                      // the last, partial group of a fiber
             const long long g = g0 + u * stride;
-            X[g] = OP == LOP_DR_B ? PassOp<T, OP>::out(xs[u], B[g], C[g]) : xs[u];
+            T o1, o2;
+            PassOp<T, OP>::out(xs[u], TR::drain_reads > 0 ? B[g] : T(0), TR::drain_reads > 1 ? C[g] : T(0), o1, o2);
+            if (TR::tout) { const long long tg = tbase + (long long)lane * n + r0 + u; X[tg] = o1; if (TR::two_out) X2[tg] = o2; }
+            else X[g] = o1;
         }
     }
     template <class Env> __device__ __forceinline__ void flush(Env&, const Window<T, W>&, int, bool) {}
@@ -335,16 +354,6 @@ template <typename T, int W, int OP> struct DrainStrided {
 // 1 KB aligned) and transposed IN PLACE through registers: lane j reads its own fiber's 128 bytes (8 conflict-free 16-byte loads),
 // the warp synchronises, lane j writes its window column.  On the way out the sweep hands each lane 8 consecutive results of its
 // fiber; they go straight into a swizzled staging box (conflict-free 16-byte stores) that leaves with one TMA store per BR rows.
-template <typename T> struct Vec16 { };
-template <> struct Vec16<double> {
-    static __device__ __forceinline__ void ld(uint32_t a, double* v) { asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v[0]), "=d"(v[1]) : "r"(a)); }
-    static __device__ __forceinline__ void st(uint32_t a, const double* v) { asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(v[0]), "d"(v[1]) : "memory"); }
-};
-template <> struct Vec16<float> {
-    static __device__ __forceinline__ void ld(uint32_t a, float* v) { asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(a)); }
-    static __device__ __forceinline__ void st(uint32_t a, const float* v) { asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory"); }
-};
-
 template <typename T, int W> struct FeedContig {
     static constexpr int R = 128 / (int)sizeof(T);          // rows per box: 16 (f64) / 32 (f32)
     static constexpr int MAXQ = W / R;
@@ -408,15 +417,18 @@ template <typename T, int W> struct DrainContig {
 
 // ---------------------------------------------------------------- the kernel
 enum LaneLayout { LAY_STRIDED = 0, LAY_CONTIG = 1 };
-template <typename T, int W, int RT, int OP, int LAY, bool REGOP = false> struct LaneSmem {
+// Shared memory of a CTA of NW warps: [NW windows][NW staging areas][NW x (flags, barriers)][reciprocal table].  Windows first: the
+// swizzled boxes of the CONTIG layout need 1 KB alignment, which the 16 / 32 KB windows and 4 KB staging boxes keep by themselves.
+template <typename T, int W, int RT, int OP, int LAY, int NW> struct LaneSmem {
     static constexpr int NST = 2;
     static constexpr size_t win_bytes = (size_t)W * LANES * sizeof(T);
-    static constexpr size_t stg_bytes = LAY == LAY_CONTIG ? 4096 : ((OP == LOP_PLAIN || REGOP) ? 0 : (size_t)2 * NST * RT * LANES * sizeof(T));
+    static constexpr size_t stg_bytes = LAY == LAY_CONTIG ? 4096 : (OpTraits<OP>::staged ? (size_t)2 * NST * RT * LANES * sizeof(T) : 0);
     static constexpr size_t flg_bytes = ((size_t)LANES * (W + 8) + 127) / 128 * 128;
     static constexpr size_t bar_bytes = 128;            // W / RT <= 16 barriers
-    static constexpr size_t align = LAY == LAY_CONTIG ? 1024 : 128;       // swizzled boxes need 1 KB aligned tiles
-    static constexpr size_t per_warp = (win_bytes + stg_bytes + flg_bytes + bar_bytes + align - 1) / align * align;
-    static constexpr size_t rcp_bytes = ((W + 2) * sizeof(acc_t) + align - 1) / align * align;
+    static constexpr size_t off_stg = (size_t)NW * win_bytes;
+    static constexpr size_t off_flg = off_stg + (size_t)NW * stg_bytes;
+    static constexpr size_t off_rcp = off_flg + (size_t)NW * (flg_bytes + bar_bytes);
+    static constexpr size_t total = off_rcp + ((W + 2) * sizeof(acc_t) + 15) / 16 * 16;
 };
 
 // repair of ONE fiber: exact sequential continuation from the last verified renewal state (verify_repair_fiber).  Executed by all
@@ -425,42 +437,44 @@ template <typename T, int W, int RT, int OP, int LAY, bool REGOP = false> struct
 // window memory, and the scan reads them from there (a dependent global load per step would cost ~1 us each); rows beyond the
 // staged range fall back to global memory.  Lane 0 writes the results.  Rare: a handful of fibers per solve.
 template <typename T, int OP, int NB>
-__device__ __noinline__ int repair_fiber(const LaneArgs<T>* a, long long fiber, long long gbase, long long stride, long long nfp, T* buf,
-                                         int lane) {
-    const ChunkPlan pl = a->plan;
+__device__ __noinline__ int repair_fiber(const LaneArgs<T>* a, const ChunkPlan pl, long long fiber, long long gbase, long long stride, long long tfib,
+                                         long long nfp, T* buf, int lane) {
     const int* rec = a->rec;
-    const T* A = a->A; const T* B = a->B; const T* C = a->C; T* X = a->X;
+    const long long cstride = (long long)a->plan.nmax;
+    const T* A = a->A; const T* B = a->B; const T* C = a->C; T* X = a->X; T* X2 = a->X2;
     int buf_lo = 0, buf_n = 0;
     auto in_at = [&](int r) { const long long g = gbase + (long long)r * stride;
-                              return OP == LOP_PLAIN ? A[g] : PassOp<T, OP>::in(A[g], B[g], C[g]); };
+                              return OpTraits<OP>::staged ? PassOp<T, OP>::in(A[g], B[g], C[g]) : A[g]; };
     return verify_repair_fiber<T>(pl, a->lam,
-        [&](int c) { return rec[(0 * (long long)pl.nchunks + c) * nfp + fiber]; },
-        [&](int c) { return rec[(1 * (long long)pl.nchunks + c) * nfp + fiber]; },
-        [&](int c) { return rec[(2 * (long long)pl.nchunks + c) * nfp + fiber]; },
+        [&](int c) { return rec[(0 * cstride + c) * nfp + fiber]; },
+        [&](int c) { return rec[(1 * cstride + c) * nfp + fiber]; },
+        [&](int c) { return rec[(2 * cstride + c) * nfp + fiber]; },
         [&](int pos) { __syncwarp();
                        buf_lo = pos; buf_n = pl.n - pos < NB ? pl.n - pos : NB;
                        for (int j = lane; j < buf_n; j += 32) buf[j] = in_at(pos + j);
                        __syncwarp(); },
         [&](int r) { const int j = r - buf_lo; return (j >= 0 && j < buf_n) ? buf[j] : in_at(r); },
         [&](int r, T v) { if (lane == 0) { const long long g = gbase + (long long)r * stride;
-                                           X[g] = OP == LOP_DR_B ? PassOp<T, OP>::out(v, B[g], C[g]) : v; } });
+                                           T o1, o2;
+                                           PassOp<T, OP>::out(v, OpTraits<OP>::drain_reads > 0 ? B[g] : T(0), OpTraits<OP>::drain_reads > 1 ? C[g] : T(0), o1, o2);
+                                           if (OpTraits<OP>::tout) { X[tfib + r] = o1; if (OpTraits<OP>::two_out) X2[tfib + r] = o2; }
+                                           else X[g] = o1; } });
 }
 
 __device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 __device__ __forceinline__ unsigned smid() { unsigned r; asm volatile("mov.u32 %0, %%smid;" : "=r"(r)); return r; }
 
-template <typename T, int W, int RT, int TITER, int OP, int NW, int LAY, bool SPEC>
+template <typename T, int W, int RT, int TITER, int OP, int NW, int LAY>
 __global__ void __launch_bounds__(NW * 32, (12 + NW - 1) / NW) k_lane(const __grid_constant__ LaneArgs<T> a) {
-    using SM = LaneSmem<T, W, RT, OP, LAY, SPEC>;
+    using SM = LaneSmem<T, W, RT, OP, LAY, NW>;
     extern __shared__ __align__(1024) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    acc_t* rcp = reinterpret_cast<acc_t*>(smem);
-    unsigned char* wb = smem + SM::rcp_bytes + (size_t)warp * SM::per_warp;
-    T* win = reinterpret_cast<T*>(wb);
-    T* stB = reinterpret_cast<T*>(wb + SM::win_bytes);
+    acc_t* rcp = reinterpret_cast<acc_t*>(smem + SM::off_rcp);
+    T* win = reinterpret_cast<T*>(smem + (size_t)warp * SM::win_bytes);
+    T* stB = reinterpret_cast<T*>(smem + SM::off_stg + (size_t)warp * SM::stg_bytes);
     T* stC = stB + (LAY == LAY_CONTIG ? 0 : SM::NST * RT * LANES);
-    uint8_t* flg = wb + SM::win_bytes + SM::stg_bytes;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(wb + SM::win_bytes + SM::stg_bytes + SM::flg_bytes);
+    uint8_t* flg = smem + SM::off_flg + (size_t)warp * (SM::flg_bytes + SM::bar_bytes);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(flg + SM::flg_bytes);
 
     for (int k = threadIdx.x; k < W + 2; k += NW * 32) rcp[k] = k ? 1.0 / (acc_t)k : 0.0;
     const long long task = (long long)blockIdx.x * NW + warp;
@@ -475,9 +489,9 @@ __global__ void __launch_bounds__(NW * 32, (12 + NW - 1) / NW) k_lane(const __gr
     if (a.tlog && lane == 0) { a.tlog[task * 4 + 0] = gtimer(); a.tlog[task * 4 + 3] = smid(); }
     struct TLogEnd { unsigned long long* p; __device__ ~TLogEnd() { if (p) *p = gtimer(); } } tlog_end{a.tlog && lane == 0 ? a.tlog + task * 4 + 2 : nullptr};
 
-    const ChunkPlan pl = a.plan;
-    const long long group = task / pl.nchunks;
-    const int chunk = (int)(task - group * pl.nchunks);
+    long long group; int chunk, nc;
+    a.plan.locate(task, &group, &chunk, &nc);
+    const ChunkPlan pl = a.plan.plan(nc);
     const int z = (int)(group / a.gps);
     const int x0 = (int)(group - (long long)z * a.gps) * LANES;
     const TaskGeom g = pl.geom(chunk);
@@ -485,51 +499,49 @@ __global__ void __launch_bounds__(NW * 32, (12 + NW - 1) / NW) k_lane(const __gr
     // element (row 0) of this lane's fiber, and its element stride
     const long long gbase = LAY == LAY_CONTIG ? ((long long)x0 + lane) * pl.n : (long long)z * a.inc * pl.n + x0 + lane;
     const long long gstride = LAY == LAY_CONTIG ? 1 : a.inc;
+    const long long tgroup = ((long long)z * a.inc + x0) * pl.n;      // transposed results: (fiber 0 of the group, row 0)
     const long long nfp = (long long)a.slabs * a.gps * LANES;
     const long long fiber = group * LANES + lane;
 
-    DevEnv<T, W, SPEC> env; env.lane = lane; 
+    DevEnv<T, W> env; env.lane = lane;
     env.dw.wbase = s32(win); env.dw.lane8 = lane * (uint32_t)sizeof(T); env.dw.flg = s32(flg) + lane * (uint32_t)Window<T, W>::FP; env.dw.rcp = s32(rcp);
     Window<T, W> w{win, flg};
     env.L.init(w, lane, g, a.lam, valid);
-    if (LAY == LAY_CONTIG) {
+    if constexpr (LAY == LAY_CONTIG) {
         FeedContig<T, W> feed{&a, win, bar, x0, g.p0 / FeedContig<T, W>::R, lane};
         DrainContig<T, W> drain{&a, stB, x0, lane, g.ce};
         warp_task<T, W, TITER>(env, feed, drain, w, rcp, g, a.lam, TITER + TITER / 2 + FeedContig<T, W>::R, (TaskStats*)nullptr);
-    } else if (SPEC && OP != LOP_PLAIN) {
-        FeedStridedReg<T, W, RT, OP> feed; feed.a = &a; feed.win = win; feed.bar = bar; feed.x0 = x0; feed.z = z; feed.q0 = g.p0 / RT; feed.lane = lane;
-        feed.gbase = gbase; feed.stride = a.inc; feed.valid = valid; feed.n = pl.n;
-        DrainStrided<T, W, OP> drain; drain.B = a.B; drain.C = a.C; drain.X = a.X; drain.gbase = gbase; drain.stride = a.inc; drain.pf_row = -1;
-        warp_task<T, W, TITER>(env, feed, drain, w, rcp, g, a.lam, TITER + TITER / 2 + RT, (TaskStats*)nullptr);
     } else {
         FeedStrided<T, W, RT, OP> feed{&a, win, stB, stC, bar, x0, z, g.p0 / RT, lane};
-        DrainStrided<T, W, OP> drain; drain.B = a.B; drain.C = a.C; drain.X = a.X; drain.gbase = gbase; drain.stride = a.inc; drain.pf_row = -1;
+        DrainStrided<T, W, OP> drain; drain.B = a.B; drain.C = a.C; drain.X = a.X; drain.X2 = a.X2; drain.gbase = gbase; drain.stride = a.inc;
+        drain.pf_row = -1; drain.ce = g.ce; drain.tbase = tgroup; drain.n = pl.n; drain.nvalid = (int)(a.per_slab - x0 < LANES ? a.per_slab - x0 : LANES);
         warp_task<T, W, TITER>(env, feed, drain, w, rcp, g, a.lam, TITER + TITER / 2 + RT, (TaskStats*)nullptr);
     }
-
     if (a.tlog && lane == 0) a.tlog[task * 4 + 1] = gtimer();
+
     // ---- chunk records; the last warp of the fiber group to finish verifies (and repairs) its 32 fibers ----
     int* rec = a.rec;
-    rec[(0 * (long long)pl.nchunks + chunk) * nfp + fiber] = env.L.in_rec;
-    rec[(1 * (long long)pl.nchunks + chunk) * nfp + fiber] = env.L.out_rec;
-    rec[(2 * (long long)pl.nchunks + chunk) * nfp + fiber] = env.L.retired ? env.L.ovf_rec : REC_NONE;
+    const long long cstride = (long long)a.plan.nmax;
+    rec[(0 * cstride + chunk) * nfp + fiber] = env.L.in_rec;
+    rec[(1 * cstride + chunk) * nfp + fiber] = env.L.out_rec;
+    rec[(2 * cstride + chunk) * nfp + fiber] = env.L.retired ? env.L.ovf_rec : REC_NONE;
     const bool any_retired = __any_sync(0xffffffffu, env.L.retired);
-    if (pl.nchunks == 1 && !any_retired) return;
+    if (nc == 1 && !any_retired) return;
     __threadfence();
     __syncwarp();
     int old = 0;
     if (lane == 0) old = atomicAdd(a.group_count + group, 1);
     old = __shfl_sync(0xffffffffu, old, 0);
-    if (old != pl.nchunks - 1) return;
+    if (old != nc - 1) return;
     __threadfence();
     if (lane == 0) a.group_count[group] = 0;
     // quick test first: every entry record equals the predecessor's exit record and nobody retired
     bool bad = false;
     if (valid) {
-        for (int c = 0; c < pl.nchunks; c++) {
-            const int ri = __ldcg(rec + (0 * (long long)pl.nchunks + c) * nfp + fiber);
-            const int ro = c > 0 ? __ldcg(rec + (1 * (long long)pl.nchunks + c - 1) * nfp + fiber) : ri;
-            const int rv = __ldcg(rec + (2 * (long long)pl.nchunks + c) * nfp + fiber);
+        for (int c = 0; c < nc; c++) {
+            const int ri = __ldcg(rec + (0 * cstride + c) * nfp + fiber);
+            const int ro = c > 0 ? __ldcg(rec + (1 * cstride + c - 1) * nfp + fiber) : ri;
+            const int rv = __ldcg(rec + (2 * cstride + c) * nfp + fiber);
             bad |= (c > 0 && ri != ro) || rv != REC_NONE;
         }
     }
@@ -539,7 +551,7 @@ __global__ void __launch_bounds__(NW * 32, (12 + NW - 1) / NW) k_lane(const __gr
     while (m) {
         const int src = __ffs(m) - 1; m &= m - 1;
         const long long gb = __shfl_sync(0xffffffffu, gbase, src);
-        nrep += repair_fiber<T, OP, W * LANES>(&a, group * LANES + src, gb, gstride, nfp, win, lane);
+        nrep += repair_fiber<T, OP, W * LANES>(&a, pl, group * LANES + src, gb, gstride, tgroup + (long long)src * pl.n, nfp, win, lane);
     }
     if (nrep && lane == 0) atomicAdd(a.stats, (unsigned long long)nrep);
 }
@@ -591,11 +603,11 @@ static long long lane_scratch_bytes(long long groups_cap, long long nf, int len)
 }
 
 // launch one instantiation; with `slots` only report how many warp tasks the device can hold at once
-template <typename T, int W, int RT, int TITER, int OP, int NW, int LAY, bool SPEC>
+template <typename T, int W, int RT, int TITER, int OP, int NW, int LAY>
 static cudaError_t launch_v(LaneArgs<T>& a, cudaStream_t st, int* slots) {
-    using SM = LaneSmem<T, W, RT, OP, LAY, SPEC>;
-    auto kern = k_lane<T, W, RT, TITER, OP, NW, LAY, SPEC>;
-    const size_t smem = SM::rcp_bytes + (size_t)NW * SM::per_warp;
+    using SM = LaneSmem<T, W, RT, OP, LAY, NW>;
+    auto kern = k_lane<T, W, RT, TITER, OP, NW, LAY>;
+    const size_t smem = SM::total;
     static int s_slots = 0;                      // per instantiation: resident warps on the current device
     if (!s_slots) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -613,44 +625,50 @@ static cudaError_t launch_v(LaneArgs<T>& a, cudaStream_t st, int* slots) {
     return cudaGetLastError();
 }
 
-// tuning variants (window rows, steps per epoch, warps per CTA); 0 is the default
+// tuning variants (window rows, warps per CTA); 0 is the default: CTAs of 4 warps -- one per SM sub-partition -- three of which fit
+// an SM when the pass needs no staging (12 resident warps, 3 per sub-partition; single-warp CTAs only reach 11, unevenly spread)
 template <typename T, int OP, int LAY>
 static cudaError_t launch_variant(int variant, LaneArgs<T>& a, cudaStream_t st, int* slots) {
     switch (variant) {
-        case 1: return launch_v<T, 64, 8, 16, OP, 4, LAY, false>(a, st, slots);
-        case 2: return launch_v<T, 64, 8, 16, OP, 1, LAY, true>(a, st, slots);
-        case 3: return launch_v<T, 64, 8, 24, OP, 1, LAY, true>(a, st, slots);
-        case 4: return launch_v<T, 64, 8, 16, OP, 4, LAY, true>(a, st, slots);
-        case 5: return launch_v<T, 128, 8, 16, OP, 1, LAY, false>(a, st, slots);
-        case 6: return launch_v<T, 128, 8, 32, OP, 1, LAY, true>(a, st, slots);
-        default: return launch_v<T, 64, 8, 16, OP, 1, LAY, false>(a, st, slots);
+        case 1: return launch_v<T, 64, 8, 16, OP, 1, LAY>(a, st, slots);
+        case 5: return launch_v<T, 128, 8, 16, OP, 1, LAY>(a, st, slots);
+        default: return launch_v<T, 64, 8, 16, OP, 4, LAY>(a, st, slots);
     }
 }
 template <typename T>
 static cudaError_t launch_any(int lay, int op, int variant, LaneArgs<T>& a, cudaStream_t st, int* slots) {
     if (lay == LAY_CONTIG) return launch_variant<T, LOP_PLAIN, LAY_CONTIG>(variant, a, st, slots);
-    return op == LOP_PLAIN ? launch_variant<T, LOP_PLAIN, LAY_STRIDED>(variant, a, st, slots)
-         : op == LOP_DR_B  ? launch_variant<T, LOP_DR_B, LAY_STRIDED>(variant, a, st, slots)
-                           : launch_variant<T, LOP_DR_B_FINAL, LAY_STRIDED>(variant, a, st, slots);
+    switch (op) {
+        case LOP_DR_B: return launch_variant<T, LOP_DR_B, LAY_STRIDED>(variant, a, st, slots);
+        case LOP_DR_B_FINAL: return launch_variant<T, LOP_DR_B_FINAL, LAY_STRIDED>(variant, a, st, slots);
+        case LOP_DRA: return launch_variant<T, LOP_DRA, LAY_STRIDED>(variant, a, st, slots);
+        case LOP_DRA_FINAL: return launch_variant<T, LOP_DRA_FINAL, LAY_STRIDED>(variant, a, st, slots);
+        case LOP_DRB: return launch_variant<T, LOP_DRB, LAY_STRIDED>(variant, a, st, slots);
+        default: return launch_variant<T, LOP_PLAIN, LAY_STRIDED>(variant, a, st, slots);
+    }
 }
 
 // x = prox_{lam TV}(in) over the fibers (nf, len, inc) of an array (the reference's slicing rule, src/TVNDopt.cpp:184-188).
-//   inc > 1: STRIDED layout, any op (in / out arithmetic of PassOp);   inc == 1: CONTIG layout, plain op only.
+//   inc > 1: STRIDED layout, any op (PassOp);   inc == 1: CONTIG layout, plain op only.
+//   ops that write transposed (LANE_DRA, LANE_DRA_FINAL, LANE_DRB): X (and X2) are fiber-major arrays, element (fiber f, row r) at
+//   f * len + r -- for the fibers of a 2D image that is the transposed image.
 // scratch: lane_scratch() (records, group counters).  Returns cudaErrorInvalidConfiguration when the shape does not suit TMA
 // tiling (unaligned base, row pitch not a multiple of 16 bytes, tiny fibers) -- the caller then uses the chunked engine.
 template <typename T>
 cudaError_t lane_prox(int op, const T* A, const T* B, const T* C, T* X, long long nf, int len, long long inc, T lam, void* scratch,
-                      cudaStream_t st) {
-    if (nf <= 0 || len < 2 || !(lam > T(0))) return cudaErrorInvalidConfiguration;
+                      cudaStream_t st, T* X2) {
+    if (nf <= 0 || len < 2 || !(lam > T(0)) || op < 0 || op > LOP_DRB) return cudaErrorInvalidConfiguration;
     const int lay = inc == 1 ? LAY_CONTIG : LAY_STRIDED;
     if (lay == LAY_CONTIG && op != LOP_PLAIN) return cudaErrorInvalidConfiguration;
     if (lay == LAY_STRIDED && nf % inc != 0) return cudaErrorInvalidConfiguration;
+    const bool staged = op == LOP_DR_B || op == LOP_DR_B_FINAL, tout = op >= LOP_DRA;
     const long long pitch = (lay == LAY_CONTIG ? (long long)len : inc) * (long long)sizeof(T);
     if (pitch % 16 != 0 || ((uintptr_t)A & 15) || ((uintptr_t)X & 15) || (B && ((uintptr_t)B & 15)) || (C && ((uintptr_t)C & 15)))
         return cudaErrorInvalidConfiguration;
+    if (tout && (((long long)len * (long long)sizeof(T)) % 16 != 0 || (op == LOP_DRA && (!X2 || ((uintptr_t)X2 & 15))))) return cudaErrorInvalidConfiguration;
     LaneArgs<T> a;
     memset(&a, 0, sizeof(a));
-    a.A = A; a.B = B; a.C = C; a.X = X; a.lam = lam;
+    a.A = A; a.B = B; a.C = C; a.X = X; a.X2 = X2; a.lam = lam;
     const int BR = 128 / (int)sizeof(T);
     if (lay == LAY_CONTIG) {
         if (nf > 0x7fffffff) return cudaErrorInvalidConfiguration;
@@ -661,30 +679,34 @@ cudaError_t lane_prox(int op, const T* A, const T* B, const T* C, T* X, long lon
         const long long slabs = nf / inc;
         if (slabs > 0x7fffffff) return cudaErrorInvalidConfiguration;
         if (!make_map<T>(&a.tmA, A, inc, len, slabs, LANES, 8, CU_TENSOR_MAP_SWIZZLE_NONE)) return cudaErrorInvalidConfiguration;
-        if (op != LOP_PLAIN) {
+        if (staged) {
             if (!make_map<T>(&a.tmB, B, inc, len, slabs, LANES, 8, CU_TENSOR_MAP_SWIZZLE_NONE)) return cudaErrorInvalidConfiguration;
             if (!make_map<T>(&a.tmC, C, inc, len, slabs, LANES, 8, CU_TENSOR_MAP_SWIZZLE_NONE)) return cudaErrorInvalidConfiguration;
         }
         a.inc = inc; a.per_slab = inc; a.slabs = (int)slabs; a.gps = (int)((inc + LANES - 1) / LANES);
     }
-    // chunking: whole fibers when there are enough of them to fill the machine; else as many chunks as there are resident warp
-    // slots, so that the whole pass is ONE wave of warp tasks.  Chunk boundaries are multiples of 32 rows (TMA boxes).
+    // Chunking: whole fibers when there are enough of them to fill the machine; else exactly as many warp tasks as the device has
+    // resident warp slots -- ONE balanced wave: the first gfull groups get nmax chunks, the others nmax - 1 (TaskPlan), and the
+    // chunk boundaries balance owned rows + halo (ChunkPlan).  Boundaries fall on the feed's tile rows: 8 (STRIDED), 16 / 32 (CONTIG).
     const long long groups = (long long)a.slabs * a.gps;
     int slots = 0;
     cudaError_t e = launch_any<T>(lay, op, g_tune.variant, a, st, &slots);
     if (e != cudaSuccess) return e;
-    int clen = g_tune.clen, halo = g_tune.halo;
-    if (clen <= 0) {
-        long long c = groups >= slots ? 1 : slots / groups;
-        clen = (int)((len + c - 1) / c);
-        if (clen < 64) clen = 64;
+    const int gran = lay == LAY_CONTIG ? BR : 8;
+    const int halo = (g_tune.halo + gran - 1) / gran * gran;
+    const int cmax = ChunkPlan::fit(len, len / 64 > 0 ? len / 64 : 1, halo, gran);      // chunks own at least ~64 rows
+    a.plan.n = len; a.plan.halo = halo; a.plan.gran = gran;
+    if (g_tune.clen > 0) {                                       // tools: fixed chunk length
+        int nc = (len + g_tune.clen - 1) / g_tune.clen;
+        a.plan.nmax = nc < cmax ? nc : cmax; a.plan.gfull = groups;
+    } else if (groups >= slots || cmax == 1) { a.plan.nmax = 1; a.plan.gfull = groups; }
+    else {
+        long long nmax = (slots + groups - 1) / groups;
+        if (nmax > cmax) { a.plan.nmax = cmax; a.plan.gfull = groups; }
+        else { a.plan.nmax = (int)nmax; a.plan.gfull = slots - groups * (nmax - 1); }
     }
-    // boundaries on TMA box rows: 16 (float64) / 32 (float32) for the CONTIG layout, 8 for STRIDED; chunks on 32
-    const int hal = lay == LAY_CONTIG ? 128 / (int)sizeof(T) : 8;
-    clen = (clen + 31) / 32 * 32; halo = (halo + hal - 1) / hal * hal;
-    a.plan.n = len; a.plan.halo = halo;
-    if (clen >= len) { a.plan.clen = len; a.plan.nchunks = 1; } else { a.plan.clen = clen; a.plan.nchunks = (len + clen - 1) / clen; }
-    if (a.plan.nchunks > len / 64 + 2) return cudaErrorInvalidConfiguration;
+    if (a.plan.nmax <= 1) { a.plan.nmax = 1; a.plan.gfull = groups; }
+    if (a.plan.nmax > len / 64 + 2) return cudaErrorInvalidConfiguration;
     {
         int d = 0; cudaGetDevice(&d);
         if (d < 0 || d >= 64 || scratch != g_scr[d].p || groups > g_scr[d].cap_groups) return cudaErrorInvalidValue;      // not lane_scratch()'s buffer
@@ -692,7 +714,7 @@ cudaError_t lane_prox(int op, const T* A, const T* B, const T* C, T* X, long lon
         a.group_count = (int*)((char*)scratch + 64);
         a.rec = a.group_count + g_scr[d].cap_groups;
     }
-    a.ntasks = groups * a.plan.nchunks;
+    a.ntasks = a.plan.ntasks(groups);
     a.tlog = (g_tlog && a.ntasks <= g_tlog_cap) ? g_tlog : nullptr;
     return launch_any<T>(lay, op, g_tune.variant, a, st, nullptr);
 }
@@ -728,7 +750,7 @@ unsigned long long lane_read_stats(int reset) {
     return v;
 }
 
-template cudaError_t lane_prox<double>(int, const double*, const double*, const double*, double*, long long, int, long long, double, void*, cudaStream_t);
-template cudaError_t lane_prox<float>(int, const float*, const float*, const float*, float*, long long, int, long long, float, void*, cudaStream_t);
+template cudaError_t lane_prox<double>(int, const double*, const double*, const double*, double*, long long, int, long long, double, void*, cudaStream_t, double*);
+template cudaError_t lane_prox<float>(int, const float*, const float*, const float*, float*, long long, int, long long, float, void*, cudaStream_t, float*);
 
 }  // namespace ptvl

@@ -361,18 +361,47 @@ PTV_HD void warp_task(Env& env, Feed& feed, Drain& drain, const Window<T, W>& w,
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// Chunking of a fiber: nchunks chunks of `clen` rows (the last one takes the remainder), each entered `halo` rows early.
+// Chunking of the fibers of one group: nchunks chunks, each entered `halo` rows early, with balanced WORK -- a chunk scans its
+// owned rows plus its halo (the first one has none), so the boundaries are b_c = c w - (c - 1) halo with w = (n + (nchunks - 1)
+// halo) / nchunks, rounded down to multiples of `gran` (the feed's tile rows; a power of two, halo is a multiple of it).
 struct ChunkPlan {
-    int n, clen, nchunks, halo;
-    PTV_HD int cs(int c) const { return c * clen; }
-    PTV_HD int ce(int c) const { return c + 1 >= nchunks ? n : (c + 1) * clen; }
+    int n, nchunks, halo, gran;
+    PTV_HD int cs(int c) const {
+        if (c <= 0) return 0;
+        if (c >= nchunks) return n;
+        const long long b = ((long long)c * ((long long)n + (long long)(nchunks - 1) * halo)) / nchunks - (long long)(c - 1) * halo;
+        return (int)(b & ~(long long)(gran - 1));
+    }
+    PTV_HD int ce(int c) const { return c + 1 >= nchunks ? n : cs(c + 1); }
     PTV_HD TaskGeom geom(int c) const {
         TaskGeom g; g.n = n; g.cs = cs(c); g.ce = ce(c);
         g.p0 = g.cs - halo > 0 ? g.cs - halo : 0;
         return g;
     }
+    // largest chunk count <= want for which every chunk owns at least 2 gran rows more than its halo costs
+    static PTV_HD int fit(int n, int want, int halo, int gran) {
+        int nc = want < 1 ? 1 : want;
+        while (nc > 1 && ((long long)n + (long long)(nc - 1) * halo) / nc - halo < 2 * gran) nc--;
+        return nc;
+    }
 };
 
+// Tasks of one launch: `groups` fiber groups; the first gfull of them are cut into nmax chunks, the others into nmax - 1, so that
+// the number of warp tasks can equal the number of resident warp slots of the device exactly (one balanced wave).
+struct TaskPlan {
+    int n, halo, gran, nmax;
+    long long gfull;
+    PTV_HD long long ntasks(long long groups) const { return gfull * nmax + (groups - gfull) * (nmax - 1); }
+    PTV_HD void locate(long long task, long long* group, int* chunk, int* nc) const {
+        const long long tf = gfull * nmax;
+        if (task < tf) { *group = task / nmax; *chunk = (int)(task - *group * nmax); *nc = nmax; }
+        else { const long long t2 = task - tf; const long long g2 = t2 / (nmax - 1); *group = gfull + g2; *chunk = (int)(t2 - g2 * (nmax - 1)); *nc = nmax - 1; }
+    }
+    PTV_HD int chunks_of(long long group) const { return group < gfull ? nmax : nmax - 1; }
+    PTV_HD ChunkPlan plan(int nc) const { ChunkPlan p; p.n = n; p.nchunks = nc; p.halo = halo; p.gran = gran; return p; }
+};
+
+// ------------------------------------------------------------------------------------------------------------------
 // Verification and repair of ONE fiber after all its chunks have been scanned (run by the last warp of the fiber group to
 // finish).  rin/rout/rovf(c): the chunk's records for this fiber.  A chunk is exact on entry iff the (start, kind) of its
 // first emitted segment equals the predecessor's record of the segment that covers the chunk's first row (both scans are then

@@ -41,7 +41,7 @@ cudaError_t prox_fibers_ex(const T* A, const T* B, const T* C, InOp op, T* X, in
     // plain unweighted prox over many fibers: the lane-per-fiber streaming engine (kernels_lane.cu), when the shape suits TMA tiling
     // and there are enough fibers to fill the machine without cutting them (a single long fiber stays with the chunked kernels,
     // which are also the bit-faithful ones behind the 1D entry points)
-    if ((eng == ENGINE_AUTO || eng == ENGINE_LANE) && op == IN_A && out_op == OUT_X && !lamv && lam > T(0) && g.len >= 64 && g.nf >= 1024) {
+    if ((eng == ENGINE_AUTO || eng == ENGINE_LANE || eng == ENGINE_LANE_T) && op == IN_A && out_op == OUT_X && !lamv && lam > T(0) && g.len >= 64 && g.nf >= 1024) {
         const void* ptrs[2] = {A, X};
         if (ptvl::lane_shape_ok(g.nf, g.len, g.inc, sizeof(T), ptrs, 2)) {
             void* lscr = ptvl::lane_scratch(g.nf, g.len);

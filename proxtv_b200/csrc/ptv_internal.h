@@ -27,7 +27,8 @@ enum InOp { IN_A = 0, IN_A_MINUS_B = 1, IN_A_PLUS_B = 2 };
 
 // Which kernel family prox_fibers() may use.
 enum Engine { ENGINE_AUTO = 0, ENGINE_SEQ = 1, ENGINE_CHUNKED = 2, ENGINE_CHUNKED_STRIDED = 3, ENGINE_PIPELINED = 4, ENGINE_TSPACE = 5, ENGINE_TPOSE = 6,
-              ENGINE_LANE = 7 /* lane-per-fiber streaming engine (kernels_lane.cu); what AUTO uses when the shape suits TMA tiling */ };
+              ENGINE_LANE = 7 /* lane-per-fiber streaming engine (kernels_lane.cu); what AUTO uses when the shape suits TMA tiling */,
+              ENGINE_LANE_T = 8 /* DR2_TV only: lane engine, both passes strided with transposed results (dr2_lane_t_body) */ };
 
 struct ProxStats {           // filled asynchronously on the device; optional
     unsigned long long fallback_fibers;
@@ -82,6 +83,7 @@ template <typename T> cudaError_t ew_pd_combine(T* const* dp, T* const* dz, T* c
 template <typename T> cudaError_t ew_pdr_combine(T* const* dp, T* const* dz, T* const* hp, T* const* hz, int k, T* x, long long n,
                                                  double* scratch, double* result, cudaStream_t st);
 template <typename T> cudaError_t ew_div_scalar(const T* y, T* x, long long n, T k, cudaStream_t st);             // x = y / k
+template <typename T> cudaError_t ew_dr_first(const T* Y, const T* t, T* U, T* D, long long n, cudaStream_t st);  // D = t - t ; U = Y - (2 D - t)
 constexpr int REDUCE_BLOCKS = 1184;    // 148 SMs x 8; partial sums are combined in a fixed order (deterministic)
 
 // ---- device-resident solvers (solver.cu).  All arrays are device pointers; `ws` must hold ws_bytes_*() bytes. ----
@@ -104,11 +106,11 @@ template <typename T> int pdr_device(const T* y, const double* lambdas_scaled, c
 
 // ---- lane-per-fiber streaming engine (kernels_lane.cu): slope-form scan, TMA-tiled windows, no transposed copies ----
 namespace ptvl {
-enum { LANE_PLAIN = 0, LANE_DR_B = 1, LANE_DR_B_FINAL = 2 };      // fused pass arithmetic (PassOp in kernels_lane.cu)
+enum { LANE_PLAIN = 0, LANE_DR_B = 1, LANE_DR_B_FINAL = 2, LANE_DRA = 3, LANE_DRA_FINAL = 4, LANE_DRB = 5 };      // fused pass arithmetic (PassOp in kernels_lane.cu)
 // prox over the fibers (nf, len, inc); returns cudaErrorInvalidConfiguration when the shape does not suit (caller falls back)
 template <typename T>
 cudaError_t lane_prox(int op, const T* A, const T* B, const T* C, T* X, long long nf, int len, long long inc, T lam, void* scratch,
-                      cudaStream_t st);
+                      cudaStream_t st, T* X2 = nullptr);
 void* lane_scratch(long long nf, int len);          // per-device records / counters (allocates: call outside stream capture)
 bool lane_shape_ok(long long nf, int len, long long inc, size_t elem, const void* const* ptrs, int nptrs);
 void lane_set_tuning(int clen, int halo, int variant);

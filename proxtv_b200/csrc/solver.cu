@@ -158,6 +158,15 @@ static int dr2_piped_body(size_t M, size_t N, const T* Y, T w1, T w2, T* out, in
 // (src/TV2Dopt.cpp:403-423; the last form is the reference's :419-422 with tb substituted, equal up to rounding), and the
 // final projection pair (:427-430) s = t - x1 ; out = prox_rows(Y - s).  The first column pass sees the constant image
 // 2 * mean, whose prox is that constant.
+// ------------------------------------------------------------------------------------------------------------------
+// Douglas-Rachford on the lane-per-fiber engine (kernels_lane.cu): two kernels per iteration, no transposed copies, 6 array
+// sweeps per iteration (the algorithmic count).  With x1 = prox_cols(t), x2 = prox_rows(Y - s):
+//     columns   x1 = prox(t)                                    1 read + 1 write      CONTIG layout (TMA box in, TMA box out)
+//     rows      s = 2 (t - x1) - t ; in = Y - s                 3 reads               STRIDED layout, formed in the feeder
+//               t' = 0.5 (t + s + 2 x2) = (t - x1) + x2         1 write               formed in the drain
+// (src/TV2Dopt.cpp:403-423; the last form is the reference's :419-422 with tb substituted, equal up to rounding), and the
+// final projection pair (:427-430) s = t - x1 ; out = prox_rows(Y - s).  The first column pass sees the constant image
+// 2 * mean, whose prox is that constant.
 template <typename T>
 static int dr2_lane_body(size_t M, size_t N, int batch, const T* Y, T w1, T w2, T* out, int maxit, T* t, T* t2, T* x1, double* scratch,
                          void* lscr, cudaStream_t st) {
@@ -174,6 +183,40 @@ static int dr2_lane_body(size_t M, size_t N, int batch, const T* Y, T w1, T w2, 
           LTRY(ptvl::lane_prox<T>(final ? ptvl::LANE_DR_B_FINAL : ptvl::LANE_DR_B, Y, x1, t, final ? out : t2, (long long)M * batch, (int)N,
                                   (long long)M, w2, lscr, st)); }
         if (!final) { T* tmp = t; t = t2; t2 = tmp; }
+    }
+    return 0;
+#undef LTRY
+}
+
+template <typename T> cudaError_t gather_fibers(const T* A, const T* B, InOp op, T* out, FiberGeom g, cudaStream_t st);
+
+// Lane-engine schedule of DR2_TV for column-major images.  Both passes of an iteration are STRIDED lane passes (32 adjacent fibers
+// = one contiguous line per sample): the column pass runs over row-major copies, the row pass over column-major arrays, every
+// tile lands as it is, the Douglas-Rachford arithmetic sits in the drains and each pass writes its results transposed into the
+// other pass's layout (kernels_lane.cu: LOP_DRA / LOP_DRB):
+//     column pass (Tr, Yr row-major):   x1 = prox_cols(t) ; d = t - x1 ; u = Y - (2 d - t)   -> Uc, Dc (column-major)      (:405-411)
+//     row pass    (Uc, Dc col-major):   x2 = prox_rows(u) ; t' = d + x2                     -> Tr (row-major)             (:415-422)
+//     final:  u = Y - (t - x1) ; out = prox_rows(u)                                                                       (:427-430)
+// Same expressions, same association as the staged forms (t' = 0.5 (t + (2 (Y - (u - x2)) - s)) of the reference evaluates to
+// (t - x1) + x2 up to rounding).  The first column pass sees the constant image 2 * mean, whose prox is that constant.
+template <typename T>
+static int dr2_lane_t_body(size_t M, size_t N, int batch, const T* Y, T w1, T w2, T* out, int maxit, T* Tr, T* Yr, T* Uc, T* Dc, double* scratch,
+                         void* lscr, cudaStream_t st) {
+#define LTRY(expr) do { cudaError_t e__ = (expr); if (e__ == cudaErrorInvalidConfiguration) { cudaGetLastError(); return 2; } \
+    if (e__ != cudaSuccess) { fprintf(stderr, "proxtv_b200: CUDA error %s at %s:%d\n", cudaGetErrorString(e__), __FILE__, __LINE__); return 1; } } while (0)
+    const long long n = (long long)M * N * batch;
+    const long long nfc = (long long)N * batch, nfr = (long long)M * batch;           // column fibers (length M), row fibers (length N)
+    LTRY(ew_image_means_x2<T>(Y, (long long)M * N, batch, Tr, scratch, st));         // t = 2 mean (:390-395): constant, so layout-free
+    if (maxit > 0) LTRY(ew_dr_first<T>(Y, Tr, Uc, Dc, n, st));
+    { KernelSpan sp(KC_ELEMENTWISE, 1, st);                                          // Yr: every image transposed (rows contiguous)
+      LTRY(gather_fibers<T>(Y, nullptr, IN_A, Yr, FiberGeom{nfr, (int)N, (long long)M}, st)); }
+    for (int it = 0; it <= maxit; it++) {
+        const bool final = it == maxit;
+        if (it > 0 || maxit == 0) { KernelSpan sp(KC_PROX_CONTIG, 1, st);
+            LTRY(ptvl::lane_prox<T>(final ? ptvl::LANE_DRA_FINAL : ptvl::LANE_DRA, Tr, Yr, Tr, Uc, nfc, (int)M, (long long)N, w1, lscr, st, Dc)); }
+        { KernelSpan sp(KC_PROX_STRIDED, 1, st);
+          if (final) LTRY(ptvl::lane_prox<T>(ptvl::LANE_PLAIN, Uc, nullptr, nullptr, out, nfr, (int)N, (long long)M, w2, lscr, st));
+          else LTRY(ptvl::lane_prox<T>(ptvl::LANE_DRB, Uc, Dc, nullptr, Tr, nfr, (int)N, (long long)M, w2, lscr, st)); }
     }
     return 0;
 #undef LTRY
@@ -229,8 +272,9 @@ int dr2_device(size_t M, size_t N, int batch, int row_major, const T* Y, T w1, T
     // lane-per-fiber engine: column-major images whose row pitch suits TMA tiling, positive weights
     const void* lane_ptrs[3] = {Y, out, ws};
     void* lscr = nullptr;
-    bool lane = (eng == ENGINE_AUTO || eng == ENGINE_LANE) && !row_major && w1 > T(0) && w2 > T(0) && M >= 2 && N >= 2 && g_pipe.init() &&
-                ptvl::lane_shape_ok((long long)N * batch, (int)M, 1, sizeof(T), lane_ptrs, 3) &&
+    const bool lane_t = eng == ENGINE_LANE_T;       // both passes strided, results written transposed (see dr2_lane_t_body)
+    bool lane = (eng == ENGINE_AUTO || eng == ENGINE_LANE || lane_t) && !row_major && w1 > T(0) && w2 > T(0) && M >= 2 && N >= 2 && g_pipe.init() &&
+                ptvl::lane_shape_ok((long long)N * batch, (int)M, lane_t ? (long long)N : 1, sizeof(T), lane_ptrs, 3) &&
                 ptvl::lane_shape_ok((long long)M * batch, (int)N, (long long)M, sizeof(T), lane_ptrs, 3);
     if (lane) {
         void* a1 = ptvl::lane_scratch((long long)N * batch, (int)M); void* a2 = ptvl::lane_scratch((long long)M * batch, (int)N);
@@ -238,11 +282,12 @@ int dr2_device(size_t M, size_t N, int batch, int row_major, const T* Y, T w1, T
     }
     if (lane || tspace || piped) {
         auto body = [&](cudaStream_t bs) -> int {
-            if (lane) return dr2_lane_body<T>(M, N, batch, Y, w1, w2, out, maxit, t, s, x, scratch, lscr, bs);
+            if (lane) return lane_t ? dr2_lane_t_body<T>(M, N, batch, Y, w1, w2, out, maxit, t, s, x, scr, scratch, lscr, bs)
+                                   : dr2_lane_body<T>(M, N, batch, Y, w1, w2, out, maxit, t, s, x, scratch, lscr, bs);
             return tspace ? dr2_tspace_body<T>(M, N, batch, Y, w1, w2, out, maxit, ws, scratch, bs, tpose)
                           : dr2_piped_body<T>(M, N, Y, w1, w2, out, maxit, t, s, x, scr, scratch, gc, n, eng == ENGINE_AUTO && sizeof(T) == 8, bs);
         };
-        DrGraphKey key{sizeof(T) + (tspace ? 100u : 0u) + (tpose ? 200u : 0u) + (eng == ENGINE_AUTO ? 400u : 0u) + (lane ? 800u : 0u) + 1000u * (size_t)batch, M, N, (const void*)Y, (void*)out, ws, (double)w1,
+        DrGraphKey key{sizeof(T) + (tspace ? 100u : 0u) + (tpose ? 200u : 0u) + (eng == ENGINE_AUTO ? 400u : 0u) + (lane ? 800u : 0u) + (lane && lane_t ? 50u : 0u) + 1000u * (size_t)batch, M, N, (const void*)Y, (void*)out, ws, (double)w1,
                        (double)w2, maxit, lane ? lscr : nullptr};
         int rc = -1;
         if (!profile_is_enabled()) {

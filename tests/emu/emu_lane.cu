@@ -23,23 +23,32 @@ template <typename T> struct HostEnv {
     }
 };
 
-// fused input / output arithmetic of a pass (kernels_lane.cu has the same three forms)
-//   0  plain            in = A                          out = x
-//   1  DR second half   in = A - (2 (C - B) - C)        out = (C - B) + x        A = Y, B = x_cols, C = t   (src/TV2Dopt.cpp:411-422)
-//   2  DR final         in = A - (C - B)                out = x                                             (:427-430)
+// fused input / output arithmetic of a pass (kernels_lane.cu: PassOp has the same forms)
+//   0  plain              in = A                          out = x
+//   1  DR second half     in = A - (2 (C - B) - C)        out = (C - B) + x        A = Y, B = x_cols, C = t   (src/TV2Dopt.cpp:411-422)
+//   2  DR final           in = A - (C - B)                out = x                                             (:427-430)
+//   3  DR first half (T)  in = A     d = C - x ; out = B - (2 d - C) -> X (transposed), d -> X2 (transposed)   B = Y, C = t
+//   4  DR final (T)       in = A     out = B - (C - x) -> X (transposed)
+//   5  DR second half (T) in = A     out = B + x -> X (transposed)                                             B = d
 template <typename T> struct Op {
-    int kind; const T* A; const T* B; const T* C; T* X;
+    int kind; const T* A; const T* B; const T* C; T* X; T* X2;
     T in(long long g) const {
-        if (kind == 0) return A[g];
+        if (kind == 0 || kind >= 3) return A[g];
         const T d = C[g] - B[g];
         if (kind == 1) return A[g] - (T(2) * d - C[g]);
         return A[g] - d;
     }
-    void out(long long g, T x) const { X[g] = (kind == 1) ? (C[g] - B[g]) + x : x; }
+    // g: position in the pass's own layout; tg: position in the fiber-major (transposed) result arrays
+    void out(long long g, long long tg, T x) const {
+        if (kind == 3) { const T d = C[g] - x; X2[tg] = d; X[tg] = B[g] - (T(2) * d - C[g]); }
+        else if (kind == 4) X[tg] = B[g] - (C[g] - x);
+        else if (kind == 5) X[tg] = B[g] + x;
+        else X[g] = (kind == 1) ? (C[g] - B[g]) + x : x;
+    }
 };
 
 template <typename T> struct Fibers {          // 32 adjacent fibers of a group
-    long long base[LANES]; long long stride; bool valid[LANES];
+    long long base[LANES]; long long tbase[LANES]; long long stride; bool valid[LANES];      // tbase: fiber index * len
 };
 
 template <typename T, int W, int RT> struct HostFeed {
@@ -58,7 +67,7 @@ template <typename T, int W, int RT> struct HostFeed {
 template <typename T, int W> struct HostDrainDirect {
     const Op<T>* op; const Fibers<T>* fb;
     void rows8(const Window<T, W>&, int r0, int cnt, int lane, const T* xs, bool valid) {
-        if (valid) for (int u = 0; u < cnt; u++) op->out(fb->base[lane] + (long long)(r0 + u) * fb->stride, xs[u]);
+        if (valid) for (int u = 0; u < cnt; u++) op->out(fb->base[lane] + (long long)(r0 + u) * fb->stride, fb->tbase[lane] + r0 + u, xs[u]);
     }
     void prefetch(int, int, bool) {}
     template <class Env> void flush(Env&, const Window<T, W>&, int, bool) {}
@@ -74,7 +83,7 @@ template <typename T, int W, int BOX> struct HostDrainBoxed {
         while (stored + BOX <= upto || (final && stored < upto)) {
             const int b1 = stored + BOX < upto ? stored + BOX : upto;
             for (int r = stored; r < b1; r++)
-                for (int l = 0; l < LANES; l++) if (fb->valid[l]) op->out(fb->base[l] + (long long)r * fb->stride, w.ld(r, l));
+                for (int l = 0; l < LANES; l++) if (fb->valid[l]) op->out(fb->base[l] + (long long)r * fb->stride, fb->tbase[l] + r, w.ld(r, l));
             stored = b1;
         }
     }
@@ -84,12 +93,13 @@ template <typename T, int W, int BOX> struct HostDrainBoxed {
 struct EmuStats { long long tasks, epochs, retired_events, tails, rows_fed, repairs, retired_lanes, steps_max; };
 
 template <typename T, int W, int TITER, int RT>
-static int run_all(int opkind, const T* A, const T* B, const T* C, T* X, long long nf, int len, long long inc, T lam, int clen, int halo,
+static int run_all(int opkind, const T* A, const T* B, const T* C, T* X, T* X2, long long nf, int len, long long inc, T lam, int clen, int halo,
                    int boxed, EmuStats* es) {
     if (nf <= 0 || len <= 0) return 0;
-    Op<T> op{opkind, A, B, C, X};
-    ChunkPlan pl; pl.n = len; pl.halo = halo;
-    if (clen <= 0 || clen >= len) { pl.clen = len; pl.nchunks = 1; } else { pl.clen = clen; pl.nchunks = (len + clen - 1) / clen; }
+    Op<T> op{opkind, A, B, C, X, X2};
+    // the kernel's plan: chunk boundaries on the feed's tile rows, balanced owned rows + halo (ChunkPlan); clen only sets how many
+    ChunkPlan pl; pl.n = len; pl.gran = boxed ? 16 : 8; pl.halo = (halo + pl.gran - 1) / pl.gran * pl.gran;
+    pl.nchunks = (clen <= 0 || clen >= len) ? 1 : ChunkPlan::fit(len, (len + clen - 1) / clen, pl.halo, pl.gran);
     std::vector<T> win((size_t)W * LANES); std::vector<acc_t> rcp(W + 2);
     std::vector<unsigned long long> flg8((Window<T, W>::flag_bytes() + 7) / 8 + 1);
     uint8_t* flgp = reinterpret_cast<uint8_t*>(flg8.data());
@@ -103,8 +113,8 @@ static int run_all(int opkind, const T* A, const T* B, const T* C, T* X, long lo
             for (int l = 0; l < LANES; l++) {
                 const long long jj = gidx * LANES + l;
                 fb.valid[l] = jj < per_slab;
-                if (inc > 1) { fb.base[l] = s * inc * len + jj; fb.stride = inc; }
-                else { fb.base[l] = jj * (long long)len; fb.stride = 1; }
+                if (inc > 1) { fb.base[l] = s * inc * len + jj; fb.stride = inc; fb.tbase[l] = (s * inc + jj) * len; }
+                else { fb.base[l] = jj * (long long)len; fb.stride = 1; fb.tbase[l] = jj * (long long)len; }
             }
             for (int c = 0; c < pl.nchunks; c++) {
                 const TaskGeom g = pl.geom(c);
@@ -131,11 +141,11 @@ static int run_all(int opkind, const T* A, const T* B, const T* C, T* X, long lo
             }
             for (int l = 0; l < LANES; l++) {
                 if (!fb.valid[l]) continue;
-                const long long base = fb.base[l], st = fb.stride;
+                const long long base = fb.base[l], st = fb.stride, tb = fb.tbase[l];
                 es->repairs += verify_repair_fiber<T>(pl, lam,
                     [&](int c) { return rin[(size_t)c * LANES + l]; }, [&](int c) { return rout[(size_t)c * LANES + l]; },
                     [&](int c) { return rovf[(size_t)c * LANES + l]; }, [](int) {},
-                    [&](int r) { return op.in(base + (long long)r * st); }, [&](int r, T v) { op.out(base + (long long)r * st, v); });
+                    [&](int r) { return op.in(base + (long long)r * st); }, [&](int r, T v) { op.out(base + (long long)r * st, tb + r, v); });
             }
         }
     return 0;
@@ -143,22 +153,22 @@ static int run_all(int opkind, const T* A, const T* B, const T* C, T* X, long lo
 
 extern "C" {
 // config: 0 -> W=64,TITER=16,R=8 ; 1 -> W=32,TITER=8,R=8 ; 2 -> W=128,TITER=16,R=16 (float) ...
-int emu_lane_f64(int opkind, const double* A, const double* B, const double* C, double* X, long long nf, int len, long long inc,
+int emu_lane_f64(int opkind, const double* A, const double* B, const double* C, double* X, double* X2, long long nf, int len, long long inc,
                  double lam, int clen, int halo, int boxed, int config, long long* stats) {
     EmuStats es; memset(&es, 0, sizeof(es));
     int rc;
-    if (config == 0) rc = run_all<double, 64, 16, 8>(opkind, A, B, C, X, nf, len, inc, lam, clen, halo, boxed, &es);
-    else if (config == 1) rc = run_all<double, 32, 8, 8>(opkind, A, B, C, X, nf, len, inc, lam, clen, halo, boxed, &es);
-    else rc = run_all<double, 128, 16, 16>(opkind, A, B, C, X, nf, len, inc, lam, clen, halo, boxed, &es);
+    if (config == 0) rc = run_all<double, 64, 16, 8>(opkind, A, B, C, X, X2, nf, len, inc, lam, clen, halo, boxed, &es);
+    else if (config == 1) rc = run_all<double, 32, 8, 8>(opkind, A, B, C, X, X2, nf, len, inc, lam, clen, halo, boxed, &es);
+    else rc = run_all<double, 128, 16, 16>(opkind, A, B, C, X, X2, nf, len, inc, lam, clen, halo, boxed, &es);
     if (stats) memcpy(stats, &es, sizeof(es));
     return rc;
 }
-int emu_lane_f32(int opkind, const float* A, const float* B, const float* C, float* X, long long nf, int len, long long inc,
+int emu_lane_f32(int opkind, const float* A, const float* B, const float* C, float* X, float* X2, long long nf, int len, long long inc,
                  float lam, int clen, int halo, int boxed, int config, long long* stats) {
     EmuStats es; memset(&es, 0, sizeof(es));
     int rc;
-    if (config == 0) rc = run_all<float, 128, 16, 8>(opkind, A, B, C, X, nf, len, inc, lam, clen, halo, boxed, &es);
-    else rc = run_all<float, 32, 8, 8>(opkind, A, B, C, X, nf, len, inc, lam, clen, halo, boxed, &es);
+    if (config == 0) rc = run_all<float, 128, 16, 8>(opkind, A, B, C, X, X2, nf, len, inc, lam, clen, halo, boxed, &es);
+    else rc = run_all<float, 32, 8, 8>(opkind, A, B, C, X, X2, nf, len, inc, lam, clen, halo, boxed, &es);
     if (stats) memcpy(stats, &es, sizeof(es));
     return rc;
 }

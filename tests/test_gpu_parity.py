@@ -17,7 +17,7 @@ from conftest import jumps, relerr
 from oracle import oracle as O
 
 pytestmark = pytest.mark.gpu
-ENGINES = ["seq", "auto", "chunked", "chunked-strided", "lane"]
+ENGINES = ["seq", "auto", "chunked", "chunked-strided", "lane", "lane-t"]
 
 
 @pytest.fixture(params=ENGINES)

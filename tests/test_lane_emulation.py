@@ -33,9 +33,9 @@ def emu():
             pytest.skip("CUDA headers not available")
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-I" + cuda_inc, "-fPIC", "-ffp-contract=off", "-shared", "-x", "c++", src, "-o", so])
     lib = C.CDLL(so)
-    lib.emu_lane_f64.argtypes = [C.c_int, dp, dp, dp, dp, C.c_longlong, C.c_int, C.c_longlong, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int,
+    lib.emu_lane_f64.argtypes = [C.c_int, dp, dp, dp, dp, dp, C.c_longlong, C.c_int, C.c_longlong, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int,
                                  C.POINTER(C.c_longlong)]
-    lib.emu_lane_f32.argtypes = [C.c_int, fp, fp, fp, fp, C.c_longlong, C.c_int, C.c_longlong, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int,
+    lib.emu_lane_f32.argtypes = [C.c_int, fp, fp, fp, fp, fp, C.c_longlong, C.c_int, C.c_longlong, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int,
                                  C.POINTER(C.c_longlong)]
     lib.emu_slope_seq_f64.argtypes = [dp, C.c_int, C.c_double, dp, C.POINTER(C.c_longlong)]
     return lib
@@ -45,11 +45,11 @@ def _p(a, t=dp):
     return a.ctypes.data_as(t) if a is not None else None
 
 
-def lane(lib, op, A, B, Cc, nf, ln, inc, lam, clen=0, halo=32, boxed=0, config=0):
+def lane(lib, op, A, B, Cc, nf, ln, inc, lam, clen=0, halo=32, boxed=0, config=0, X2=None):
     f32 = A.dtype == np.float32
     X = np.full_like(A, np.nan); st = (C.c_longlong * 8)()
     t = fp if f32 else dp
-    (lib.emu_lane_f32 if f32 else lib.emu_lane_f64)(op, _p(A, t), _p(B, t), _p(Cc, t), _p(X, t), nf, ln, inc, lam, clen, halo, boxed, config, st)
+    (lib.emu_lane_f32 if f32 else lib.emu_lane_f64)(op, _p(A, t), _p(B, t), _p(Cc, t), _p(X, t), _p(X2, t), nf, ln, inc, lam, clen, halo, boxed, config, st)
     return X, dict(tasks=st[0], epochs=st[1], retire_events=st[2], tails=st[3], rows_fed=st[4], repairs=st[5], retired_lanes=st[6], iters=st[7])
 
 
@@ -142,8 +142,10 @@ def test_float32_storage(emu, port):
 
 
 def test_douglas_rachford_through_the_lane_passes(emu, port):
-    """A whole DR2_TV solve made of lane passes (column pass plain, row pass with the fused arithmetic, final projection pair),
-    exactly as solver.cu's dr2_lane_body issues them, against the oracle."""
+    """Whole DR2_TV solves made of lane passes, exactly as solver.cu issues them, against the oracle.
+    (a) the staged schedule: column pass plain (contiguous fibers), row pass with the three operands combined at landing;
+    (b) the transposed schedule (the default): BOTH passes strided, each over its own copy (columns over the row-major arrays, rows
+        over the column-major ones), arithmetic in the drain, results written transposed into the other layout."""
     from oracle import oracle as O
     M, N = 96, 80
     Y = O.gen_cfg2(M, N, seed=2, block=8)
@@ -159,3 +161,21 @@ def test_douglas_rachford_through_the_lane_passes(emu, port):
             t = out
     got = out.reshape(N, M).T
     assert np.abs(got - want).max() / np.abs(want).max() <= 1e-9
+    staged = got
+
+    Yr = np.ascontiguousarray(Y).ravel()                     # row-major copy: column fibers have stride N, adjacent columns are adjacent
+    t0 = 2 * Yf.mean()
+    Uc = Yf - (2.0 * (t0 - t0) - t0); Dc = np.zeros_like(Yf)   # first column pass: prox of the constant image is that constant
+    Tr = None
+    for it in range(36):
+        final = it == 35
+        if it > 0:                                           # column pass over the row-major copies -> u, d in column-major
+            Dc = np.full_like(Yf, np.nan)
+            Uc = lane(emu, 4 if final else 3, Tr, Yr, Tr, N, M, N, 0.2, clen=32, halo=16, X2=None if final else Dc)[0]
+        if final:
+            out = lane(emu, 0, Uc, None, None, M, N, M, 0.2, clen=32, halo=16)[0]
+        else:                                                # row pass over the column-major arrays -> t' in row-major
+            Tr = lane(emu, 5, Uc, Dc, None, M, N, M, 0.2, clen=32, halo=16)[0]
+    got = out.reshape(N, M).T
+    assert np.abs(got - want).max() / np.abs(want).max() <= 1e-9
+    assert np.array_equal(got, staged)                       # same arithmetic, other data movement: bit-identical

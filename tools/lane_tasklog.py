@@ -20,9 +20,13 @@ lib.proxtv_lane_tuning(clen, 32, variant)
 st = vp(torch.cuda.current_stream().cuda_stream)
 
 
+out2 = torch.empty_like(x)
+
+
 def run():
     if lay == "s":
-        ok = lib.proxtv_lane_prox_dev_f64(op, vp(x.data_ptr()), vp(xa.data_ptr()) if op else None, vp(t.data_ptr()) if op else None, vp(out.data_ptr()), M, N, M, 0.2, st)
+        ok = lib.proxtv_lane_prox2_dev_f64(op, vp(x.data_ptr()), vp(xa.data_ptr()) if op else None, vp(t.data_ptr()) if op else None, vp(out.data_ptr()),
+                                          vp(out2.data_ptr()), M, N, M, 0.2, st)
     else:
         ok = lib.proxtv_lane_prox_dev_f64(0, vp(x.data_ptr()), None, None, vp(out.data_ptr()), N, M, 1, 0.2, st)
     assert ok, lib.proxtv_last_error()
