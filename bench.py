@@ -395,14 +395,19 @@ def main():
     if rank == 0:
         peak, peak_src = peaks()
         names = ["prox_contiguous_fibers", "prox_strided_fibers", "elementwise"]
-        lane = args.engine in ("auto", "lane")
+        lane_t = args.engine == "lane-t"
+        lane = args.engine in ("auto", "lane") or lane_t
         # algorithmic bytes per launch of each kernel class for this workload (DESIGN.md "Kernels"), in f64 sweeps of the image.
         # lane engine: class 0 = k_lane CONTIG (column pass: 1R + 1W), class 1 = k_lane STRIDED with the fused Douglas-Rachford
         # arithmetic (row pass: reads Y, t, x_cols, writes t': 3R + 1W; the final projection pass has the same traffic).
         # chunked engines: both prox classes are the chunked scan (1R + 1W); gather (2R+1W) / scatter+combine (4R+1W) average 4.
-        sweeps = {0: 2.0, 1: 4.0 if lane else 2.0, 2: 4.0}
-        kname = {0: "k_lane<CONTIG, plain> (column pass)" if lane else "k_prox_chunked_contig",
-                 1: "k_lane<STRIDED, fused Douglas-Rachford> (row pass)" if lane else "k_prox_chunked_contig (on gathered rows)", 2: "elementwise"}
+        # engine lane-t: class 0 = k_lane STRIDED LOP_DRA over the row-major copies (reads t, Y; writes u, d transposed: 2R + 2W),
+        # class 1 = k_lane STRIDED LOP_DRB (reads u, d; writes t' transposed: 2R + 1W).
+        sweeps = {0: 4.0 if lane_t else 2.0, 1: (3.0 if lane_t else 4.0) if lane else 2.0, 2: 4.0}
+        kname = {0: ("k_lane<STRIDED, LOP_DRA> (column pass over row-major copies, results transposed)" if lane_t else
+                     "k_lane<CONTIG, plain> (column pass)") if lane else "k_prox_chunked_contig",
+                 1: ("k_lane<STRIDED, LOP_DRB> (row pass, result transposed)" if lane_t else
+                     "k_lane<STRIDED, fused Douglas-Rachford> (row pass)") if lane else "k_prox_chunked_contig (on gathered rows)", 2: "elementwise"}
         if lane:
             dom = max(range(3), key=lambda i: kms[i])
             avg_ms = kms[dom] / max(ks[dom], 1)

@@ -18,7 +18,7 @@ from . import _lib
 from ._lib import ProxTVError, load, require_device  # noqa: F401
 
 __all__ = ["tv1_1d", "tv1w_1d", "tv1_2d", "tv1w_2d", "tvgen", "tvgen_pdr", "tv1_1d_batched", "tv1w_1d_batched", "tv1_2d_batched",
-           "set_engine", "ProxTVError"]
+           "set_engine", "set_pinned_results", "ProxTVError"]
 
 _N_INFO = 3                      # prox_tv/__init__.py:67
 ENGINES = {"auto": 0, "seq": 1, "chunked": 2, "chunked-strided": 3, "pipelined": 4, "tspace": 5, "tpose": 6, "lane": 7, "lane-t": 8}
@@ -58,6 +58,66 @@ def _is_torch(x):
 def _check(ok, what):
     if not ok:
         raise ProxTVError("%s failed: %s" % (what, _lib.last_error()))
+
+
+# ---- result arrays in pooled page-locked memory ----
+# The reference returns a fresh ``np.zeros`` array.  For a 128 MiB image that costs more than the solve: 32768 page faults when the
+# device-to-host copy first touches the pages, and a pageable copy at a fraction of the PCIe rate.  Large results are therefore
+# carved out of a small pool of page-locked blocks (cudaHostAlloc through the library); a block returns to the pool when the last
+# array that refers to it -- the result or any view of it -- is garbage-collected.  ``set_pinned_results(False)`` switches it off.
+class _PinnedPool:
+    MIN_BYTES = 1 << 20          # smaller results: plain numpy memory
+    MAX_IDLE = 1 << 30           # idle blocks kept for reuse (bytes)
+
+    def __init__(self):
+        self.enabled = True
+        self.free = []           # (capacity, address)
+
+    def empty(self, shape, dtype, order):
+        import weakref
+        dtype = np.dtype(dtype)
+        nbytes = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
+        if not self.enabled or nbytes < self.MIN_BYTES:
+            return np.zeros(shape, dtype=dtype, order=order)
+        lib = load()
+        fit = [b for b in self.free if nbytes <= b[0] <= 2 * nbytes]
+        if fit:
+            blk = min(fit); self.free.remove(blk)
+        else:
+            addr = lib.proxtv_host_alloc(nbytes)
+            if not addr:
+                return np.zeros(shape, dtype=dtype, order=order)
+            blk = (nbytes, addr)
+        buf = (C.c_char * nbytes).from_address(blk[1])
+        weakref.finalize(buf, self._give, blk)
+        return np.frombuffer(buf, dtype=dtype).reshape(shape, order=order)
+
+    def _give(self, blk):
+        try:
+            if self.enabled and sum(b[0] for b in self.free) + blk[0] <= self.MAX_IDLE:
+                self.free.append(blk)
+            else:
+                load().proxtv_host_free(C.c_void_p(blk[1]))
+        except Exception:        # interpreter shutdown
+            pass
+
+    def clear(self):
+        lib = load()
+        for b in self.free:
+            lib.proxtv_host_free(C.c_void_p(b[1]))
+        self.free = []
+
+
+_pool = _PinnedPool()
+
+
+def set_pinned_results(on):
+    """Results of at least 1 MiB come from a pool of page-locked host blocks (default: on); returns the previous setting."""
+    prev = _pool.enabled
+    _pool.enabled = bool(on)
+    if not on:
+        _pool.clear()
+    return prev
 
 
 # ======================================================================================================================
@@ -184,9 +244,9 @@ def tv1_2d(x, w, n_threads=1, max_iters=0, method="dr"):
     x = np.asfortranarray(x, dtype="float64")
     assert x.ndim == 2
     w = force_float_scalar(w)
-    y = np.asfortranarray(np.zeros(x.shape))
-    info = np.zeros(_N_INFO)
     lib = require_device()
+    y = _pool.empty(x.shape, np.float64, "F")
+    info = np.zeros(_N_INFO)
     if method == "dr":
         lib.DR2_TV(x.shape[0], x.shape[1], _ptr(x), w, w, 1.0, 1.0, _ptr(y), int(n_threads), int(max_iters), _ptr(info))
         _check(info[2] != 3, "DR2_TV")
@@ -215,7 +275,7 @@ def tv1w_2d(x, w_col, w_row, max_iters=0, n_threads=1):
     assert np.shape(w_col) == (M - 1, N)
     assert np.shape(w_row) == (M, N - 1)
     x = np.asfortranarray(x, dtype="float64")
-    y = np.zeros(x.shape, order="F")
+    y = _pool.empty(x.shape, np.float64, "F")
     w_col = np.asfortranarray(w_col, dtype="float64")
     w_row = np.asfortranarray(w_row, dtype="float64")
     info = np.zeros(_N_INFO)
@@ -286,7 +346,7 @@ def tv1_2d_batched(x, w, max_iters=0):
     B, H, W = x.shape
     # device layout: column-major images back to back == C-ordered (B, W, H) array of transposed images
     xt = np.ascontiguousarray(np.transpose(x, (0, 2, 1)), dtype=np.float32 if f32 else np.float64)
-    out = np.empty_like(xt)
+    out = _pool.empty(xt.shape, xt.dtype, "C")
     info = np.zeros(_N_INFO)
     lib = require_device()
     fn = lib.proxtv_DR2_TV_batched_f32 if f32 else lib.proxtv_DR2_TV_batched_f64
@@ -316,7 +376,7 @@ def tvgen(x, ws, ds, ps, n_threads=1, max_iters=0):
     x = np.asfortranarray(x, dtype="float32" if f32 else "float64")
     ws = force_float_matrix(ws)
     ps = force_float_matrix(ps)
-    y = np.zeros(np.shape(x), order="F", dtype=x.dtype)
+    y = _pool.empty(np.shape(x), x.dtype, "F")
     if np.any(ps != 1):
         raise NotImplementedError("proxtv_b200 implements TV-L1 (p = 1) penalty terms only")
     lib = require_device()
@@ -357,7 +417,7 @@ def tvgen_pdr(x, ws, ds, ps, n_threads=1, max_iters=0):
     ps = force_float_matrix(ps)
     if np.any(ps != 1):
         raise NotImplementedError("proxtv_b200 implements TV-L1 (p = 1) penalty terms only")
-    y = np.zeros(np.shape(x), order="F", dtype=x.dtype)
+    y = _pool.empty(np.shape(x), x.dtype, "F")
     lib = require_device()
     dsa = np.array(ds, dtype=np.float64)
     ns = np.array(x.shape, dtype=np.int32)

@@ -330,10 +330,10 @@ template <typename T> cudaError_t ew_div_scalar(const T* y, T* x, long long n, T
 
 // first Douglas-Rachford half-iteration on the constant start image t (2 * mean): the column prox of a constant is that constant, so
 // d = t - x_cols and u = Y - (2 d - t) need no scan; written with the very expressions the lane drain uses (PassOp<LOP_DRA>)
-template <typename T> __global__ void k_dr_first(const T* __restrict__ Y, const T* __restrict__ t, T* __restrict__ U, T* __restrict__ D, long long n) {
+template <typename T> __global__ void k_dr_first(const T* Y, const T* __restrict__ t, T* __restrict__ U, T* D, long long n) {
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
-        const T c = t[e], d = c - c;
-        D[e] = d; U[e] = Y[e] - (T(2) * d - c);
+        const T c = t[e], d = c - c, y = Y[e];            // Y may be D (in place): read before the write
+        D[e] = d; U[e] = y - (T(2) * d - c);
     }
 }
 template <typename T> cudaError_t ew_dr_first(const T* Y, const T* t, T* U, T* D, long long n, cudaStream_t st) {

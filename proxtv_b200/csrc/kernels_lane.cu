@@ -14,6 +14,7 @@
 #include "lane_core.cuh"
 #include <cuda.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 namespace ptvl {
 
@@ -58,7 +59,7 @@ template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile
 //   LOP_DRA / _FINAL / LOP_DRB "transposed": every pass lands plain tiles, does its arithmetic in the DRAIN (operands read with
 //                              coalesced loads, one epoch ahead) and writes its results TRANSPOSED, so that both passes of an
 //                              iteration are strided passes -- one over the row-major copies, one over the column-major ones
-enum LaneOp { LOP_PLAIN = 0, LOP_DR_B = 1, LOP_DR_B_FINAL = 2, LOP_DRA = 3, LOP_DRA_FINAL = 4, LOP_DRB = 5 };
+enum LaneOp { LOP_PLAIN = 0, LOP_DR_B = 1, LOP_DR_B_FINAL = 2, LOP_DRA = 3, LOP_DRA_FINAL = 4, LOP_DRB = 5, LOP_PLAIN_T = 6 /* plain, result transposed */ };
 template <int OP> struct OpTraits {
     static constexpr bool staged = OP == LOP_DR_B || OP == LOP_DR_B_FINAL;           // B, C tiles combined at landing
     static constexpr bool tout = OP >= LOP_DRA;                                     // results written transposed (fiber-major)
@@ -75,6 +76,7 @@ template <typename T> struct LaneArgs {
     int slabs, gps;                 // groups of 32 fibers per slab
     TaskPlan plan;
     T lam;
+    acc_t lamc[2];                  // 2 lam, -2 lam (float64: what the scan adds / resets to)
     int* rec;                       // [3][plan.nmax][slabs*gps*32] chunk records (in, out, overflow)
     int* group_count;               // [slabs*gps] finished-task counters (self-resetting)
     unsigned long long* stats;      // [0] repair scans, [1] retired lanes
@@ -156,15 +158,14 @@ template <typename T, int W> struct DevWin {
 };
 
 template <bool PH1, typename T, int W>
-__device__ __forceinline__ void run_dev(Lane<T>& L, const DevWin<T, W> dw, const TaskGeom& g, acc_t lam2, int niter) {
+__device__ __forceinline__ void run_dev(Lane<T>& L, const DevWin<T, W> dw, const TaskGeom& g, const acc_t lam2, const acc_t nlam2, int niter) {
     using DW = DevWin<T, W>;
     constexpr int ROWB = DW::ROWB;
     acc_t Z = L.Z, lo = L.lo, hi = L.hi;
     int ia = L.i << DW::FSH, la = L.last << DW::FSH, bloa = L.blo << DW::FSH, bhia = L.bhi << DW::FSH, in_ = L.in_rec;
-    const int cea = g.ce << DW::FSH, csa = g.cs << DW::FSH;
-    acc_t nlam2 = -lam2;
-    opaque(nlam2);                                     // keep -2 lam in a register (else it is re-negated every iteration)
-#pragma unroll 1
+    const int csa = g.cs << DW::FSH;
+    // unrolled by two: the loop-carried registers swap roles instead of being copied; 2 lam / -2 lam come from the constant bank
+#pragma unroll 2
     for (int it = 0; it < niter; it++) {
         const acc_t y = (acc_t)SmemIO<T>::ld(dw.at(ia));
         const int ka = ia - la;
@@ -173,7 +174,7 @@ __device__ __forceinline__ void run_dev(Lane<T>& L, const DevWin<T, W> dw, const
         const acc_t cl = (Z + y) * r, ch = (Z + (y + lam2)) * r;
         Z += y;
         const bool first = (ka == ROWB);
-        const bool can = !first & (la < cea);
+        const bool can = !first;
         const bool craw = lo > ch, fraw = hi < cl;          // both compares issue back to back (neither waits for the other)
         const bool cbk = can & craw;
         const bool fbk = can & !craw & fraw;
@@ -207,14 +208,14 @@ __device__ __forceinline__ void run_dev(Lane<T>& L, const DevWin<T, W> dw, const
 }
 
 template <typename T, int W> struct DevEnv {
-    Lane<T> L; int lane; DevWin<T, W> dw;
+    Lane<T> L; int lane; DevWin<T, W> dw; const acc_t* lamc;      // lamc: {2 lam, -2 lam} in the kernel's parameter block (constant bank)
     template <class F> __device__ __forceinline__ void each(F f) { f(L, lane); }
     template <class F> __device__ __forceinline__ int rmin(F f) { return __reduce_min_sync(0xffffffffu, f(L, lane)); }
     template <class F> __device__ __forceinline__ int rmax(F f) { return __reduce_max_sync(0xffffffffu, f(L, lane)); }
     template <class F> __device__ __forceinline__ bool any(F f) { return __any_sync(0xffffffffu, f(L, lane)); }
     __device__ __forceinline__ void sync() { __syncwarp(); }
     __device__ __forceinline__ void scan(Lane<T>& l, const Window<T, W>&, int, const TaskGeom& g, const acc_t*, acc_t lam2, bool ph1, int niter) {
-        if (ph1) run_dev<true, T, W>(l, dw, g, lam2, niter); else run_dev<false, T, W>(l, dw, g, lam2, niter);
+        if (ph1) run_dev<true, T, W>(l, dw, g, lamc[0], lamc[1], niter); else run_dev<false, T, W>(l, dw, g, lamc[0], lamc[1], niter);
     }
 };
 
@@ -503,7 +504,7 @@ __global__ void __launch_bounds__(NW * 32, (12 + NW - 1) / NW) k_lane(const __gr
     const long long nfp = (long long)a.slabs * a.gps * LANES;
     const long long fiber = group * LANES + lane;
 
-    DevEnv<T, W> env; env.lane = lane;
+    DevEnv<T, W> env; env.lane = lane; env.lamc = a.lamc;
     env.dw.wbase = s32(win); env.dw.lane8 = lane * (uint32_t)sizeof(T); env.dw.flg = s32(flg) + lane * (uint32_t)Window<T, W>::FP; env.dw.rcp = s32(rcp);
     Window<T, W> w{win, flg};
     env.L.init(w, lane, g, a.lam, valid);
@@ -585,7 +586,8 @@ static bool make_map(CUtensorMap* m, const T* base, long long d0, long long d1, 
 }
 
 struct LaneTuning { int clen, halo, variant; };
-static LaneTuning g_tune = {0, 32, 0};        // chunk length (0 = one wave), halo rows, variant
+static int env_variant() { const char* e = getenv("PTV_LANE_VARIANT"); return e ? atoi(e) : -1; }
+static LaneTuning g_tune = {0, 32, env_variant()};        // chunk length (0 = one wave), halo rows, variant (-1: default per storage type; tools: PTV_LANE_VARIANT)
 static unsigned long long* g_tlog = nullptr; static long long g_tlog_cap = 0;
 void lane_set_tasklog(unsigned long long* dev, long long cap_tasks) { g_tlog = dev; g_tlog_cap = cap_tasks; }
 void lane_set_tuning(int clen, int halo, int variant) { g_tune.clen = clen; g_tune.halo = halo; g_tune.variant = variant; }
@@ -632,6 +634,8 @@ static cudaError_t launch_variant(int variant, LaneArgs<T>& a, cudaStream_t st, 
     switch (variant) {
         case 1: return launch_v<T, 64, 8, 16, OP, 1, LAY>(a, st, slots);
         case 5: return launch_v<T, 128, 8, 16, OP, 1, LAY>(a, st, slots);
+        case 6: if constexpr (sizeof(T) == 4) return launch_v<T, 128, 8, 32, OP, 4, LAY>(a, st, slots);      // float32: same bytes, twice the rows, half the epochs
+                else return launch_v<T, 64, 8, 16, OP, 4, LAY>(a, st, slots);
         default: return launch_v<T, 64, 8, 16, OP, 4, LAY>(a, st, slots);
     }
 }
@@ -644,20 +648,21 @@ static cudaError_t launch_any(int lay, int op, int variant, LaneArgs<T>& a, cuda
         case LOP_DRA: return launch_variant<T, LOP_DRA, LAY_STRIDED>(variant, a, st, slots);
         case LOP_DRA_FINAL: return launch_variant<T, LOP_DRA_FINAL, LAY_STRIDED>(variant, a, st, slots);
         case LOP_DRB: return launch_variant<T, LOP_DRB, LAY_STRIDED>(variant, a, st, slots);
+        case LOP_PLAIN_T: return launch_variant<T, LOP_PLAIN_T, LAY_STRIDED>(variant, a, st, slots);
         default: return launch_variant<T, LOP_PLAIN, LAY_STRIDED>(variant, a, st, slots);
     }
 }
 
 // x = prox_{lam TV}(in) over the fibers (nf, len, inc) of an array (the reference's slicing rule, src/TVNDopt.cpp:184-188).
 //   inc > 1: STRIDED layout, any op (PassOp);   inc == 1: CONTIG layout, plain op only.
-//   ops that write transposed (LANE_DRA, LANE_DRA_FINAL, LANE_DRB): X (and X2) are fiber-major arrays, element (fiber f, row r) at
+//   ops that write transposed (LANE_DRA, LANE_DRA_FINAL, LANE_DRB, LANE_PLAIN_T): X (and X2) are fiber-major arrays, element (fiber f, row r) at
 //   f * len + r -- for the fibers of a 2D image that is the transposed image.
 // scratch: lane_scratch() (records, group counters).  Returns cudaErrorInvalidConfiguration when the shape does not suit TMA
 // tiling (unaligned base, row pitch not a multiple of 16 bytes, tiny fibers) -- the caller then uses the chunked engine.
 template <typename T>
 cudaError_t lane_prox(int op, const T* A, const T* B, const T* C, T* X, long long nf, int len, long long inc, T lam, void* scratch,
                       cudaStream_t st, T* X2) {
-    if (nf <= 0 || len < 2 || !(lam > T(0)) || op < 0 || op > LOP_DRB) return cudaErrorInvalidConfiguration;
+    if (nf <= 0 || len < 2 || !(lam > T(0)) || op < 0 || op > LOP_PLAIN_T) return cudaErrorInvalidConfiguration;
     const int lay = inc == 1 ? LAY_CONTIG : LAY_STRIDED;
     if (lay == LAY_CONTIG && op != LOP_PLAIN) return cudaErrorInvalidConfiguration;
     if (lay == LAY_STRIDED && nf % inc != 0) return cudaErrorInvalidConfiguration;
@@ -668,7 +673,7 @@ cudaError_t lane_prox(int op, const T* A, const T* B, const T* C, T* X, long lon
     if (tout && (((long long)len * (long long)sizeof(T)) % 16 != 0 || (op == LOP_DRA && (!X2 || ((uintptr_t)X2 & 15))))) return cudaErrorInvalidConfiguration;
     LaneArgs<T> a;
     memset(&a, 0, sizeof(a));
-    a.A = A; a.B = B; a.C = C; a.X = X; a.X2 = X2; a.lam = lam;
+    a.A = A; a.B = B; a.C = C; a.X = X; a.X2 = X2; a.lam = lam; a.lamc[0] = 2.0 * (acc_t)lam; a.lamc[1] = -a.lamc[0];
     const int BR = 128 / (int)sizeof(T);
     if (lay == LAY_CONTIG) {
         if (nf > 0x7fffffff) return cudaErrorInvalidConfiguration;
@@ -685,27 +690,28 @@ cudaError_t lane_prox(int op, const T* A, const T* B, const T* C, T* X, long lon
         }
         a.inc = inc; a.per_slab = inc; a.slabs = (int)slabs; a.gps = (int)((inc + LANES - 1) / LANES);
     }
-    // Chunking: whole fibers when there are enough of them to fill the machine; else exactly as many warp tasks as the device has
-    // resident warp slots -- ONE balanced wave: the first gfull groups get nmax chunks, the others nmax - 1 (TaskPlan), and the
-    // chunk boundaries balance owned rows + halo (ChunkPlan).  Boundaries fall on the feed's tile rows: 8 (STRIDED), 16 / 32 (CONTIG).
+    // Chunking.  Enough fiber groups to fill the device's resident warp slots (a batch of images, a volume): whole fibers, one warp
+    // task per group -- measured on 32 images 2048 x 2048 f32 (2048 groups, 1776 slots): 87.5 ms per solve against 86-95 ms for
+    // 2..8 chunks per fiber; a partial second wave is cheap because the SMs it leaves half empty run their warps faster.  Fewer groups
+    // (one image: 128): as many chunks per fiber as fit ONE wave, floor(slots / groups), each scanned by its own warp from a cold
+    // start `halo` rows early; chunk boundaries balance owned rows + halo and fall on the feed's tile rows: 8 (STRIDED), 16 / 32
+    // (CONTIG) (ChunkPlan).  More chunks than that -- e.g. 14 x 128 = 1792 tasks for 1776 slots -- would put the excess into a
+    // second wave a whole task long.
     const long long groups = (long long)a.slabs * a.gps;
     int slots = 0;
-    cudaError_t e = launch_any<T>(lay, op, g_tune.variant, a, st, &slots);
+    const int variant = g_tune.variant >= 0 ? g_tune.variant : (sizeof(T) == 4 ? 6 : 0);      // float32: 128-row window, 32-step epochs
+    cudaError_t e = launch_any<T>(lay, op, variant, a, st, &slots);
     if (e != cudaSuccess) return e;
     const int gran = lay == LAY_CONTIG ? BR : 8;
     const int halo = (g_tune.halo + gran - 1) / gran * gran;
     const int cmax = ChunkPlan::fit(len, len / 64 > 0 ? len / 64 : 1, halo, gran);      // chunks own at least ~64 rows
-    a.plan.n = len; a.plan.halo = halo; a.plan.gran = gran;
+    a.plan.n = len; a.plan.halo = halo; a.plan.gran = gran; a.plan.gfull = groups;
     if (g_tune.clen > 0) {                                       // tools: fixed chunk length
-        int nc = (len + g_tune.clen - 1) / g_tune.clen;
-        a.plan.nmax = nc < cmax ? nc : cmax; a.plan.gfull = groups;
-    } else if (groups >= slots || cmax == 1) { a.plan.nmax = 1; a.plan.gfull = groups; }
-    else {
-        long long nmax = (slots + groups - 1) / groups;
-        if (nmax > cmax) { a.plan.nmax = cmax; a.plan.gfull = groups; }
-        else { a.plan.nmax = (int)nmax; a.plan.gfull = slots - groups * (nmax - 1); }
-    }
-    if (a.plan.nmax <= 1) { a.plan.nmax = 1; a.plan.gfull = groups; }
+        const int nc = (len + g_tune.clen - 1) / g_tune.clen;
+        a.plan.nmax = nc < cmax ? nc : cmax;
+    } else if (groups >= slots) a.plan.nmax = 1;
+    else { const long long c = slots / groups; a.plan.nmax = c < cmax ? (int)c : cmax; }
+    if (a.plan.nmax < 1) a.plan.nmax = 1;
     if (a.plan.nmax > len / 64 + 2) return cudaErrorInvalidConfiguration;
     {
         int d = 0; cudaGetDevice(&d);
@@ -716,7 +722,7 @@ cudaError_t lane_prox(int op, const T* A, const T* B, const T* C, T* X, long lon
     }
     a.ntasks = a.plan.ntasks(groups);
     a.tlog = (g_tlog && a.ntasks <= g_tlog_cap) ? g_tlog : nullptr;
-    return launch_any<T>(lay, op, g_tune.variant, a, st, nullptr);
+    return launch_any<T>(lay, op, variant, a, st, nullptr);
 }
 
 bool lane_shape_ok(long long nf, int len, long long inc, size_t elem, const void* const* ptrs, int nptrs) {

@@ -158,8 +158,8 @@ template <typename T> struct Lane {
     // `niter` scan steps, no bounds checks: the caller guarantees i + niter <= frontier (and <= n - 1: the last sample is never
     // processed here).  Straight-line and branch-free by design -- every lane of a warp executes the same instructions whether it
     // advances, touches or breaks (a break is a handful of selects plus predicated stores), so the lanes of a warp never diverge.
-    // Once the segment that covers row ce is finished (last >= ce) breaks are disabled and the lane only coasts; the epoch loop
-    // retires it.  PH1: the lane may still be in front of its first owned segment (clip to cs, record the entry state).
+    // Once the segment that covers row ce is finished (last >= ce) the epoch loop retires the lane (settle); whatever it did beyond
+    // that segment in the same call -- more breaks, more start marks, all above ce -- is never looked at.  PH1: the lane may still be in front of its first owned segment (clip to cs, record the entry state).
     template <bool PH1, int W>
     PTV_HD void run(const Window<T, W>& w, int lane, const TaskGeom& g, const acc_t* __restrict__ rcp, acc_t lam2, int niter) {
         acc_t Z_ = Z, lo_ = lo, hi_ = hi;
@@ -172,7 +172,7 @@ template <typename T> struct Lane {
             const acc_t cl = (Z_ + y) * r, ch = (Z_ + (y + lam2)) * r;      // slopes to the tube floor / ceiling at sample i
             Z_ += y;
             const bool first = (k == 1);
-            const bool can = !first & (last_ < g.ce);
+            const bool can = !first;
             const bool cbk = can & (lo_ > ch);
             const bool fbk = can & !cbk & (hi_ < cl);
             const bool brk = cbk | fbk;

@@ -106,7 +106,7 @@ template <typename T> int pdr_device(const T* y, const double* lambdas_scaled, c
 
 // ---- lane-per-fiber streaming engine (kernels_lane.cu): slope-form scan, TMA-tiled windows, no transposed copies ----
 namespace ptvl {
-enum { LANE_PLAIN = 0, LANE_DR_B = 1, LANE_DR_B_FINAL = 2, LANE_DRA = 3, LANE_DRA_FINAL = 4, LANE_DRB = 5 };      // fused pass arithmetic (PassOp in kernels_lane.cu)
+enum { LANE_PLAIN = 0, LANE_DR_B = 1, LANE_DR_B_FINAL = 2, LANE_DRA = 3, LANE_DRA_FINAL = 4, LANE_DRB = 5, LANE_PLAIN_T = 6 };      // fused pass arithmetic (PassOp in kernels_lane.cu)
 // prox over the fibers (nf, len, inc); returns cudaErrorInvalidConfiguration when the shape does not suit (caller falls back)
 template <typename T>
 cudaError_t lane_prox(int op, const T* A, const T* B, const T* C, T* X, long long nf, int len, long long inc, T lam, void* scratch,

@@ -190,33 +190,47 @@ static int dr2_lane_body(size_t M, size_t N, int batch, const T* Y, T w1, T w2, 
 
 template <typename T> cudaError_t gather_fibers(const T* A, const T* B, InOp op, T* out, FiberGeom g, cudaStream_t st);
 
-// Lane-engine schedule of DR2_TV for column-major images.  Both passes of an iteration are STRIDED lane passes (32 adjacent fibers
-// = one contiguous line per sample): the column pass runs over row-major copies, the row pass over column-major arrays, every
-// tile lands as it is, the Douglas-Rachford arithmetic sits in the drains and each pass writes its results transposed into the
-// other pass's layout (kernels_lane.cu: LOP_DRA / LOP_DRB):
-//     column pass (Tr, Yr row-major):   x1 = prox_cols(t) ; d = t - x1 ; u = Y - (2 d - t)   -> Uc, Dc (column-major)      (:405-411)
-//     row pass    (Uc, Dc col-major):   x2 = prox_rows(u) ; t' = d + x2                     -> Tr (row-major)             (:415-422)
-//     final:  u = Y - (t - x1) ; out = prox_rows(u)                                                                       (:427-430)
-// Same expressions, same association as the staged forms (t' = 0.5 (t + (2 (Y - (u - x2)) - s)) of the reference evaluates to
-// (t - x1) + x2 up to rounding).  The first column pass sees the constant image 2 * mean, whose prox is that constant.
+// Lane-engine schedule of DR2_TV with BOTH passes as STRIDED lane passes (32 adjacent fibers = one contiguous line per sample), for
+// either storage order: the pass along axis 0 (the reference's "columns", first) runs over row-major arrays, the pass along axis 1
+// over column-major arrays; every tile lands as it is, the Douglas-Rachford arithmetic sits in the drains, and each pass writes
+// its results transposed into the other pass's layout (kernels_lane.cu: LOP_DRA / LOP_DRB):
+//     axis-0 pass (Tr, Yr row-major):   x1 = prox(t) ; d = t - x1 ; u = Y - (2 d - t)   -> Uc, Dc (column-major)      (:405-411)
+//     axis-1 pass (Uc, Dc col-major):   x2 = prox(u) ; t' = d + x2                     -> Tr (row-major)             (:415-422)
+//     final:  u = Y - (t - x1) ; out = prox(u)                                                                       (:427-430)
+// Same expressions, same association as the staged forms above: the two schedules agree bit for bit.  A row-major image (torch
+// tensors, the batched entry points) needs no copy at all: Y is Yr and the last pass writes its result transposed; a column-major
+// image (the reference's layout) is transposed once into Yr, and its first half-iteration -- the prox of the constant start image
+// is that constant -- is a plain elementwise kernel.
 template <typename T>
-static int dr2_lane_t_body(size_t M, size_t N, int batch, const T* Y, T w1, T w2, T* out, int maxit, T* Tr, T* Yr, T* Uc, T* Dc, double* scratch,
-                         void* lscr, cudaStream_t st) {
+static int dr2_lane_t_body(size_t M, size_t N, int batch, int row_major, const T* Y, T w1, T w2, T* out, int maxit, T* Tr, T* Yr_buf, T* Uc, T* Dc,
+                           double* scratch, void* lscr, cudaStream_t st) {
 #define LTRY(expr) do { cudaError_t e__ = (expr); if (e__ == cudaErrorInvalidConfiguration) { cudaGetLastError(); return 2; } \
     if (e__ != cudaSuccess) { fprintf(stderr, "proxtv_b200: CUDA error %s at %s:%d\n", cudaGetErrorString(e__), __FILE__, __LINE__); return 1; } } while (0)
     const long long n = (long long)M * N * batch;
-    const long long nfc = (long long)N * batch, nfr = (long long)M * batch;           // column fibers (length M), row fibers (length N)
+    const long long nf0 = (long long)N * batch, nf1 = (long long)M * batch;           // fibers along axis 0 (length M), along axis 1 (length N)
+    const T* Yr = row_major ? Y : Yr_buf;
     LTRY(ew_image_means_x2<T>(Y, (long long)M * N, batch, Tr, scratch, st));         // t = 2 mean (:390-395): constant, so layout-free
-    if (maxit > 0) LTRY(ew_dr_first<T>(Y, Tr, Uc, Dc, n, st));
-    { KernelSpan sp(KC_ELEMENTWISE, 1, st);                                          // Yr: every image transposed (rows contiguous)
-      LTRY(gather_fibers<T>(Y, nullptr, IN_A, Yr, FiberGeom{nfr, (int)N, (long long)M}, st)); }
+    // One transposition per solve.  Column-major input: Yr = every image transposed.  Row-major input: the first half-iteration
+    // needs Y in column-major order once (u = Y - (2 (t - t) - t) with the constant start image t; a lane pass over constant fibers
+    // would be its worst case: not a single break, every fiber through the repair path); it is gathered into Dc and turned into
+    // (Uc, Dc) in place.
+    bool first_done = false;
+    if (!row_major) {
+        if (maxit > 0) { LTRY(ew_dr_first<T>(Y, Tr, Uc, Dc, n, st)); first_done = true; }
+        KernelSpan sp(KC_ELEMENTWISE, 1, st);
+        LTRY(gather_fibers<T>(Y, nullptr, IN_A, Yr_buf, FiberGeom{nf1, (int)N, (long long)M}, st));
+    } else if (maxit > 0) {
+        { KernelSpan sp(KC_ELEMENTWISE, 1, st);
+          LTRY(gather_fibers<T>(Y, nullptr, IN_A, Dc, FiberGeom{nf0, (int)M, (long long)N}, st)); }
+        LTRY(ew_dr_first<T>(Dc, Tr, Uc, Dc, n, st)); first_done = true;
+    }
     for (int it = 0; it <= maxit; it++) {
         const bool final = it == maxit;
-        if (it > 0 || maxit == 0) { KernelSpan sp(KC_PROX_CONTIG, 1, st);
-            LTRY(ptvl::lane_prox<T>(final ? ptvl::LANE_DRA_FINAL : ptvl::LANE_DRA, Tr, Yr, Tr, Uc, nfc, (int)M, (long long)N, w1, lscr, st, Dc)); }
+        if (!(it == 0 && first_done)) { KernelSpan sp(KC_PROX_CONTIG, 1, st);
+            LTRY(ptvl::lane_prox<T>(final ? ptvl::LANE_DRA_FINAL : ptvl::LANE_DRA, Tr, Yr, Tr, Uc, nf0, (int)M, (long long)N, w1, lscr, st, Dc)); }
         { KernelSpan sp(KC_PROX_STRIDED, 1, st);
-          if (final) LTRY(ptvl::lane_prox<T>(ptvl::LANE_PLAIN, Uc, nullptr, nullptr, out, nfr, (int)N, (long long)M, w2, lscr, st));
-          else LTRY(ptvl::lane_prox<T>(ptvl::LANE_DRB, Uc, Dc, nullptr, Tr, nfr, (int)N, (long long)M, w2, lscr, st)); }
+          if (final) LTRY(ptvl::lane_prox<T>(row_major ? ptvl::LANE_PLAIN_T : ptvl::LANE_PLAIN, Uc, nullptr, nullptr, out, nf1, (int)N, (long long)M, w2, lscr, st));
+          else LTRY(ptvl::lane_prox<T>(ptvl::LANE_DRB, Uc, Dc, nullptr, Tr, nf1, (int)N, (long long)M, w2, lscr, st)); }
     }
     return 0;
 #undef LTRY
@@ -269,25 +283,27 @@ int dr2_device(size_t M, size_t N, int batch, int row_major, const T* Y, T w1, T
     const bool tspace = (eng == ENGINE_TSPACE || tpose) && !row_major && M >= 64 && N >= 64 && g_pipe.init();
     const bool piped = (eng == ENGINE_AUTO || eng == ENGINE_PIPELINED) && !row_major && batch == 1 && M >= 1024 && N >= 1024 && M % 2 == 0 && N % 2 == 0 &&
                        (size_t)((M > N ? M : N) * sizeof(T)) <= 96 * 1024 && g_pipe.init();
-    // lane-per-fiber engine: column-major images whose row pitch suits TMA tiling, positive weights
+    // lane-per-fiber engine: images whose row pitch suits TMA tiling, positive weights.  Column-major: the staged schedule (column
+    // pass over contiguous fibers) or, engine lane-t, the transposed one; row-major: only the transposed schedule applies.
     const void* lane_ptrs[3] = {Y, out, ws};
     void* lscr = nullptr;
-    const bool lane_t = eng == ENGINE_LANE_T;       // both passes strided, results written transposed (see dr2_lane_t_body)
-    bool lane = (eng == ENGINE_AUTO || eng == ENGINE_LANE || lane_t) && !row_major && w1 > T(0) && w2 > T(0) && M >= 2 && N >= 2 && g_pipe.init() &&
+    const bool lane_t = eng == ENGINE_LANE_T || row_major;
+    bool lane = (eng == ENGINE_AUTO || eng == ENGINE_LANE || eng == ENGINE_LANE_T) && w1 > T(0) && w2 > T(0) && M >= 2 && N >= 2 && g_pipe.init() &&
                 ptvl::lane_shape_ok((long long)N * batch, (int)M, lane_t ? (long long)N : 1, sizeof(T), lane_ptrs, 3) &&
-                ptvl::lane_shape_ok((long long)M * batch, (int)N, (long long)M, sizeof(T), lane_ptrs, 3);
+                ptvl::lane_shape_ok((long long)M * batch, (int)N, (long long)M, sizeof(T), lane_ptrs, 3) &&
+                (!lane_t || (((long long)M * sizeof(T)) % 16 == 0 && ((long long)N * sizeof(T)) % 16 == 0));
     if (lane) {
         void* a1 = ptvl::lane_scratch((long long)N * batch, (int)M); void* a2 = ptvl::lane_scratch((long long)M * batch, (int)N);
         lscr = a2; lane = a1 && a2;                 // the second call returns the (possibly grown) buffer both passes use
     }
     if (lane || tspace || piped) {
         auto body = [&](cudaStream_t bs) -> int {
-            if (lane) return lane_t ? dr2_lane_t_body<T>(M, N, batch, Y, w1, w2, out, maxit, t, s, x, scr, scratch, lscr, bs)
+            if (lane) return lane_t ? dr2_lane_t_body<T>(M, N, batch, row_major, Y, w1, w2, out, maxit, t, s, x, scr, scratch, lscr, bs)
                                    : dr2_lane_body<T>(M, N, batch, Y, w1, w2, out, maxit, t, s, x, scratch, lscr, bs);
             return tspace ? dr2_tspace_body<T>(M, N, batch, Y, w1, w2, out, maxit, ws, scratch, bs, tpose)
                           : dr2_piped_body<T>(M, N, Y, w1, w2, out, maxit, t, s, x, scr, scratch, gc, n, eng == ENGINE_AUTO && sizeof(T) == 8, bs);
         };
-        DrGraphKey key{sizeof(T) + (tspace ? 100u : 0u) + (tpose ? 200u : 0u) + (eng == ENGINE_AUTO ? 400u : 0u) + (lane ? 800u : 0u) + (lane && lane_t ? 50u : 0u) + 1000u * (size_t)batch, M, N, (const void*)Y, (void*)out, ws, (double)w1,
+        DrGraphKey key{sizeof(T) + (tspace ? 100u : 0u) + (tpose ? 200u : 0u) + (eng == ENGINE_AUTO ? 400u : 0u) + (lane ? 800u : 0u) + (lane && lane_t ? 50u : 0u) + (row_major ? 25u : 0u) + 1000u * (size_t)batch, M, N, (const void*)Y, (void*)out, ws, (double)w1,
                        (double)w2, maxit, lane ? lscr : nullptr};
         int rc = -1;
         if (!profile_is_enabled()) {

@@ -30,6 +30,7 @@ template <typename T> struct HostEnv {
 //   3  DR first half (T)  in = A     d = C - x ; out = B - (2 d - C) -> X (transposed), d -> X2 (transposed)   B = Y, C = t
 //   4  DR final (T)       in = A     out = B - (C - x) -> X (transposed)
 //   5  DR second half (T) in = A     out = B + x -> X (transposed)                                             B = d
+//   6  plain (T)          in = A     out = x -> X (transposed)
 template <typename T> struct Op {
     int kind; const T* A; const T* B; const T* C; T* X; T* X2;
     T in(long long g) const {
@@ -43,6 +44,7 @@ template <typename T> struct Op {
         if (kind == 3) { const T d = C[g] - x; X2[tg] = d; X[tg] = B[g] - (T(2) * d - C[g]); }
         else if (kind == 4) X[tg] = B[g] - (C[g] - x);
         else if (kind == 5) X[tg] = B[g] + x;
+        else if (kind == 6) X[tg] = x;
         else X[g] = (kind == 1) ? (C[g] - B[g]) + x : x;
     }
 };

@@ -71,3 +71,17 @@ def test_cfg5_images_2048_f32(ptv, ref):
     for s in range(3):
         want = ref.dr2_tv(np.asfortranarray(imgs[s].astype(np.float64)), 0.2, n_threads=min(_threads(), 64))[0]
         assert relerr(got[s], want) <= 5e-5, s
+
+
+def test_cfg5_torch_row_major_equals_numpy_path(ptv):
+    """The batched entry point on row-major CUDA tensors (what bench.py --workload cfg5 and the multi-GPU driver use) runs the
+    transposed lane schedule on the tensors as they are; the numpy path solves column-major copies with the staged schedule.
+    Same arithmetic, other data movement; the only difference is the summation order of the start value 2 * mean (the reduction
+    runs over the array as it lies in memory), i.e. rounding level."""
+    import torch
+    for dt, npdt, tol in ((torch.float32, np.float32, 1e-6), (torch.float64, np.float64, 1e-12)):
+        imgs = np.stack([np.ascontiguousarray(O.gen_cfg2(1024, 2048, seed=10 + s)).astype(npdt) for s in range(2)])
+        a = ptv.tv1_2d_batched(imgs, 0.2)
+        b = ptv.tv1_2d_batched(torch.tensor(imgs, device="cuda"), 0.2)
+        assert b.dtype == dt and b.is_contiguous()
+        assert relerr(b.cpu().numpy(), a) <= tol

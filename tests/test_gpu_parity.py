@@ -386,3 +386,29 @@ def test_pdr_tv(ptv, port, eng):
     assert relerr(ptv.tvgen_pdr(V, [0.2, 0.2, 0.2], [1, 2, 3], [1, 1, 1]), want) <= 1e-9
     with pytest.raises(NotImplementedError):
         ptv.tvgen_pdr(V, [0.2, 0.2], [1, 2], [2, 1])
+
+
+def test_pinned_result_pool(ptv, port):
+    """Large numpy results live in pooled page-locked blocks: two live results never share memory, a block is reused only after
+    every array referring to it (views included) is gone, and switching the pool off gives plain numpy memory."""
+    import gc
+    Y = O.gen_cfg2(512, 512, seed=41, block=16)
+    want = port.dr2_tv(Y, 0.2)[0]
+    a = ptv.tv1_2d(Y, 0.2)
+    b = ptv.tv1_2d(2 * Y, 0.2)
+    assert a.flags.f_contiguous and relerr(a, want) <= 1e-9
+    assert not np.shares_memory(a, b) and relerr(b, port.dr2_tv(2 * Y, 0.2)[0]) <= 1e-9
+    addr = a.ctypes.data
+    view = a[::2, ::2]
+    del a; gc.collect()
+    c = ptv.tv1_2d(Y, 0.2)                       # the view keeps the block alive: c must not land on it
+    assert c.ctypes.data != addr and relerr(view, want[::2, ::2]) <= 1e-9
+    del view, c; gc.collect()
+    d = ptv.tv1_2d(Y, 0.2)                       # now a block is free again
+    assert relerr(d, want) <= 1e-9
+    prev = ptv.set_pinned_results(False)
+    try:
+        e = ptv.tv1_2d(Y, 0.2)
+        assert e.flags.owndata or e.base is not None and relerr(e, want) <= 1e-9
+    finally:
+        ptv.set_pinned_results(prev)

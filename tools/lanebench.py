@@ -10,6 +10,7 @@ lib = ptv.require_device()
 vp = C.c_void_p
 lib.proxtv_lane_prox_dev_f64.argtypes = [C.c_int, vp, vp, vp, vp, C.c_longlong, C.c_int, C.c_longlong, C.c_double, vp]
 lib.proxtv_lane_prox_dev_f32.argtypes = [C.c_int, vp, vp, vp, vp, C.c_longlong, C.c_int, C.c_longlong, C.c_float, vp]
+lib.proxtv_lane_prox2_dev_f64.argtypes = [C.c_int, vp, vp, vp, vp, vp, C.c_longlong, C.c_int, C.c_longlong, C.c_double, vp]
 lib.proxtv_lane_tuning.argtypes = [C.c_int, C.c_int, C.c_int]
 lib.proxtv_lane_stats.argtypes = [C.c_int]; lib.proxtv_lane_stats.restype = C.c_ulonglong
 OUT = {}
@@ -54,7 +55,7 @@ def check_small():
         Y = O.gen_cfg2(M, N, seed=int(rng.integers(100)), block=16)          # F-order M x N
         x = torch.tensor(np.ascontiguousarray(Y.T), device="cuda")           # (N, M) row-major == column-major M x N
         want = old_prox(x, M, N, M, lam)
-        for variant in (0, 2):
+        for variant in (0, 1):
             lib.proxtv_lane_tuning(clen, halo, variant)
             got = lane(0, x, None, None, M, N, M, lam)
             err = (got - want).abs().max().item()
@@ -73,11 +74,31 @@ def check_small():
             err = (got2 - want2).abs().max().item()
             print(f"   op={op}: max|diff| {err:.2e} repairs {lib.proxtv_lane_stats(1)}", flush=True)
             ok &= err < 1e-9
+        # drain-side forms with transposed results (the lane-t schedule): fibers = rows of the M x N column-major image x
+        if N % 2 == 0:
+            px = old_prox(x, M, N, M, lam)                          # prox of every row, (N, M) layout
+            lib.proxtv_lane_tuning(clen, halo, 0)
+            T_ = lambda a: a.t().contiguous()                       # fiber-major = the transposed image
+            u = torch.full_like(x, float("nan")).view(M, N); d2 = torch.full_like(x, float("nan")).view(M, N)
+            assert lib.proxtv_lane_prox2_dev_f64(3, vp(x.data_ptr()), vp(xa.data_ptr()), vp(x.data_ptr()), vp(u.data_ptr()), vp(d2.data_ptr()), M, N, M, lam, stream())
+            dd = x - px
+            e1 = (d2 - T_(dd)).abs().max().item(); e2 = (u - T_(xa - (2 * dd - x))).abs().max().item()
+            g4 = torch.full_like(x, float("nan")).view(M, N)
+            assert lib.proxtv_lane_prox2_dev_f64(4, vp(x.data_ptr()), vp(xa.data_ptr()), vp(x.data_ptr()), vp(g4.data_ptr()), None, M, N, M, lam, stream())
+            e3 = (g4 - T_(xa - (x - px))).abs().max().item()
+            g5 = torch.full_like(x, float("nan")).view(M, N)
+            assert lib.proxtv_lane_prox2_dev_f64(5, vp(x.data_ptr()), vp(xa.data_ptr()), None, vp(g5.data_ptr()), None, M, N, M, lam, stream())
+            e4 = (g5 - T_(xa + px)).abs().max().item()
+            g6 = torch.full_like(x, float("nan")).view(M, N)
+            assert lib.proxtv_lane_prox2_dev_f64(6, vp(x.data_ptr()), None, None, vp(g6.data_ptr()), None, M, N, M, lam, stream())
+            e5 = (g6 - T_(px)).abs().max().item()
+            print(f"   ops 3..6 (transposed results): d {e1:.1e} u {e2:.1e} final-u {e3:.1e} t' {e4:.1e} plain {e5:.1e} repairs {lib.proxtv_lane_stats(1)}", flush=True)
+            ok &= max(e1, e2, e3, e4, e5) < 1e-9
     # contiguous fibers (CONTIG layout: TMA box + in-place transpose in, swizzled staging + TMA store out)
     for (nf, ln, lam, clen) in [(64, 256, 0.2, 0), (100, 300, 0.2, 128), (33, 1000, 1.0, 256), (256, 4096, 0.2, 0), (7, 64, 0.1, 0), (40, 130, 0.2, 64)]:
         x = torch.tensor(np.ascontiguousarray(O.gen_cfg2(nf, ln, seed=5, block=16)), device="cuda")     # (nf, ln) row-major: fibers contiguous
         want = old_prox(x, nf, ln, 1, lam)
-        for variant in (0, 2):
+        for variant in (0, 1):
             lib.proxtv_lane_tuning(clen, 32, variant)
             got = lane(0, x, None, None, nf, ln, 1, lam)
             err = (got - want).abs().max().item()
@@ -117,7 +138,7 @@ def bench_big(quick):
     out = torch.empty_like(x)
     res = []
     configs = [(0, 32)]
-    variants = [0, 1, 2, 3, 4]
+    variants = [0, 1]        # 0: 4-warp CTAs (default), 1: single-warp CTAs
     if quick: configs = configs[:2]; variants = [0, 1]
     for variant in variants:
         for clen, halo in configs:
@@ -131,18 +152,25 @@ def bench_big(quick):
     OUT["plain_f64_4096"] = res
     # fused DR second half
     t = torch.tensor(np.random.default_rng(1).normal(0, 1, (N, M)), device="cuda"); xa = t * 0.5
-    for variant in (0, 1, 2, 3, 4):
+    for variant in (0, 1):
         for clen in (0,):
             lib.proxtv_lane_tuning(clen, 32, variant)
             us = timeit(lambda: lane(1, x, xa, t, M, N, M, lam, out))
             print(f"lane DR_B v={variant} clen={clen}: {us:8.1f} us  ({4*M*N*8/us/1e3:7.1f} GB/s over 3R+1W)", flush=True)
             res.append(dict(op=1, variant=variant, clen=clen, us=us))
+    o2 = torch.empty_like(x)
+    for op, name, nb in ((3, "DRA (2R+2W, both results transposed)", 4), (4, "DRA final (2R+1W)", 3), (5, "DRB (2R+1W)", 3), (6, "plain, transposed result", 2)):
+        lib.proxtv_lane_tuning(0, 32, 0)
+        f = lambda: lib.proxtv_lane_prox2_dev_f64(op, vp(x.data_ptr()), vp(xa.data_ptr()), vp(x.data_ptr()), vp(out.data_ptr()), vp(o2.data_ptr()), M, N, M, lam, stream())
+        us = timeit(f)
+        print(f"lane {name}: {us:8.1f} us  ({nb*M*N*8/us/1e3:7.1f} GB/s)", flush=True)
+        res.append(dict(op=op, us=us))
     # contiguous pass (columns of the image)
     wantc = old_prox(x, N, M, 1, lam)
     t_oldc = timeit(lambda: old_prox(x, N, M, 1, lam), 10)
     print(f"old engine contiguous pass: {t_oldc:.1f} us", flush=True)
     OUT["old_contig_us"] = t_oldc
-    for variant in (0, 1, 2, 3, 4):
+    for variant in (0, 1):
         lib.proxtv_lane_tuning(0, 32, variant)
         got = lane(0, x, None, None, N, M, 1, lam, out)
         err = (got - wantc).abs().max().item()
