@@ -77,7 +77,7 @@ template <typename T> struct LaneArgs {
     TaskPlan plan;
     T lam;
     acc_t lamc[2];                  // 2 lam, -2 lam (float64: what the scan adds / resets to)
-    int* rec;                       // [3][plan.nmax][slabs*gps*32] chunk records (in, out, overflow)
+    int* rec;                       // [5][plan.nmax][slabs*gps*32] chunk records (in, out, overflow, in2, in3)
     int* group_count;               // [slabs*gps] finished-task counters (self-resetting)
     unsigned long long* stats;      // [0] repair scans, [1] retired lanes
     unsigned long long* tlog;       // optional (tools): per task {start ns, scan end ns, end ns, SM id}
@@ -437,29 +437,36 @@ template <typename T, int W, int RT, int OP, int LAY, int NW> struct LaneSmem {
 // each repair scan the lanes copy the next NB rows of the fiber -- with the pass's input arithmetic applied -- into the warp's
 // window memory, and the scan reads them from there (a dependent global load per step would cost ~1 us each); rows beyond the
 // staged range fall back to global memory.  Lane 0 writes the results.  Rare: a handful of fibers per solve.
-template <typename T, int OP, int NB>
+template <typename T, int OP, int NB, int W>
 __device__ __noinline__ int repair_fiber(const LaneArgs<T>* a, const ChunkPlan pl, long long fiber, long long gbase, long long stride, long long tfib,
-                                         long long nfp, T* buf, int lane) {
+                                         long long nfp, T* buf, const acc_t* rcp, int lane) {
     const int* rec = a->rec;
     const long long cstride = (long long)a->plan.nmax;
     const T* A = a->A; const T* B = a->B; const T* C = a->C; T* X = a->X; T* X2 = a->X2;
     int buf_lo = 0, buf_n = 0;
     auto in_at = [&](int r) { const long long g = gbase + (long long)r * stride;
                               return OpTraits<OP>::staged ? PassOp<T, OP>::in(A[g], B[g], C[g]) : A[g]; };
+    // 256 rows are staged at a time (a repair usually merges after a few rows; staging costs up to three dependent global loads per row)
+    constexpr int NBS = NB < 256 ? NB : 256;
+    auto stage = [&](int pos) { __syncwarp();
+                                buf_lo = pos; buf_n = pl.n - pos < NBS ? pl.n - pos : NBS;
+                                for (int j = lane; j < buf_n; j += 32) buf[j] = in_at(pos + j);
+                                __syncwarp(); };
     return verify_repair_fiber<T>(pl, a->lam,
         [&](int c) { return rec[(0 * cstride + c) * nfp + fiber]; },
+        [&](int c) { return rec[(3 * cstride + c) * nfp + fiber]; },
+        [&](int c) { return rec[(4 * cstride + c) * nfp + fiber]; },
         [&](int c) { return rec[(1 * cstride + c) * nfp + fiber]; },
         [&](int c) { return rec[(2 * cstride + c) * nfp + fiber]; },
-        [&](int pos) { __syncwarp();
-                       buf_lo = pos; buf_n = pl.n - pos < NB ? pl.n - pos : NB;
-                       for (int j = lane; j < buf_n; j += 32) buf[j] = in_at(pos + j);
-                       __syncwarp(); },
-        [&](int r) { const int j = r - buf_lo; return (j >= 0 && j < buf_n) ? buf[j] : in_at(r); },
+        [&](int pos) { stage(pos); },
+        [&](int r) { if (r < buf_lo || r >= buf_lo + buf_n) stage(r);        // warp-uniform: all lanes run the same scan
+                     return buf[r - buf_lo]; },
         [&](int r, T v) { if (lane == 0) { const long long g = gbase + (long long)r * stride;
                                            T o1, o2;
                                            PassOp<T, OP>::out(v, OpTraits<OP>::drain_reads > 0 ? B[g] : T(0), OpTraits<OP>::drain_reads > 1 ? C[g] : T(0), o1, o2);
                                            if (OpTraits<OP>::tout) { X[tfib + r] = o1; if (OpTraits<OP>::two_out) X2[tfib + r] = o2; }
-                                           else X[g] = o1; } });
+                                           else X[g] = o1; } },
+        rcp, W + 2);
 }
 
 __device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
@@ -526,6 +533,8 @@ __global__ void __launch_bounds__(NW * 32, (12 + NW - 1) / NW) k_lane(const __gr
     rec[(0 * cstride + chunk) * nfp + fiber] = env.L.in_rec;
     rec[(1 * cstride + chunk) * nfp + fiber] = env.L.out_rec;
     rec[(2 * cstride + chunk) * nfp + fiber] = env.L.retired ? env.L.ovf_rec : REC_NONE;
+    rec[(3 * cstride + chunk) * nfp + fiber] = env.L.in_rec2;
+    rec[(4 * cstride + chunk) * nfp + fiber] = env.L.in_rec3;
     const bool any_retired = __any_sync(0xffffffffu, env.L.retired);
     if (nc == 1 && !any_retired) return;
     __threadfence();
@@ -552,7 +561,7 @@ __global__ void __launch_bounds__(NW * 32, (12 + NW - 1) / NW) k_lane(const __gr
     while (m) {
         const int src = __ffs(m) - 1; m &= m - 1;
         const long long gb = __shfl_sync(0xffffffffu, gbase, src);
-        nrep += repair_fiber<T, OP, W * LANES>(&a, pl, group * LANES + src, gb, gstride, tgroup + (long long)src * pl.n, nfp, win, lane);
+        nrep += repair_fiber<T, OP, W * LANES, W>(&a, pl, group * LANES + src, gb, gstride, tgroup + (long long)src * pl.n, nfp, win, rcp, lane);
     }
     if (nrep && lane == 0) atomicAdd(a.stats, (unsigned long long)nrep);
 }
@@ -593,7 +602,7 @@ void lane_set_tasklog(unsigned long long* dev, long long cap_tasks) { g_tlog = d
 void lane_set_tuning(int clen, int halo, int variant) { g_tune.clen = clen; g_tune.halo = halo; g_tune.variant = variant; }
 
 // Scratch of the lane engine, one buffer per device (grow-only, zero-initialised when (re)allocated):
-//     [stats 64 B][group counters: cap_groups ints][chunk records]
+//     [stats 64 B][group counters: cap_groups ints][chunk records: 5 per (chunk, fiber)]
 // The counters must be zero between launches (the last warp of a group resets its counter), so their region has a FIXED size per
 // allocation -- it must never overlap what an earlier launch with fewer groups used for records.
 struct LaneScratch { void* p = nullptr; size_t cap = 0; long long cap_groups = 0; };
@@ -601,7 +610,7 @@ static LaneScratch g_scr[64];
 static long long lane_scratch_bytes(long long groups_cap, long long nf, int len) {
     const long long nfp = (nf + 31) / 32 * 32 + 32 * 64;
     const long long maxchunks = len / 64 + 2;
-    return 64 + groups_cap * 4 + 3 * maxchunks * nfp * 4 + 256;
+    return 64 + groups_cap * 4 + 5 * maxchunks * nfp * 4 + 256;
 }
 
 // launch one instantiation; with `slots` only report how many warp tasks the device can hold at once

@@ -55,16 +55,17 @@ PTV_HD acc_t z_of_kind(int kind, acc_t lam) { return kind == LK_CEIL ? 0.0 : (ki
 // Used by the repair path of the kernel (global memory), the tail of a fiber (window) and the CPU tests.
 //   ld(i)              sample i of the fiber
 //   seg(f, e, v, kind) called for every finished segment [f, e] with value v whose start has `kind`; returns true to stop
+//   rcp[0 .. nrcp)     optional table of reciprocals 1 / k (the kernel's shared-memory table)
 // Starts at position `pos` with a segment of kind `kind` beginning there; runs to the end of the fiber (n) unless stopped.
 template <typename T, class Ld, class Seg>
-PTV_HD void slope_seq(int n, T lam_, int pos, int kind, Ld ld, Seg seg) {
+PTV_HD void slope_seq(int n, T lam_, int pos, int kind, Ld ld, Seg seg, const acc_t* rcp = nullptr, int nrcp = 0) {
     const acc_t lam = (acc_t)lam_, lam2 = 2.0 * lam, eps = 1e-10;      // src/general.h:64
     int last = pos - 1, i = pos, blo = pos, bhi = pos, kcur = kind;
     acc_t Z = z_of_kind(kind, lam), lo = 0.0, hi = 0.0;
     while (i < n) {
         const acc_t y = (acc_t)ld(i);
         const int k = i - last;
-        const acc_t r = 1.0 / (acc_t)k;
+        const acc_t r = k < nrcp ? rcp[k] : 1.0 / (acc_t)k;      // the table holds the correctly rounded quotients: same value
         // same expressions, same association as the lanes' loop (Lane::run): identical decisions and values bit for bit
         const acc_t cl = (Z + y) * r, ch = (Z + (y + lam2)) * r;
         Z += y;
@@ -140,6 +141,8 @@ template <typename T> struct Lane {
     acc_t Z, lo, hi;
     int i, last, blo, bhi;
     int in_rec, out_rec;  // (start, kind) of the first emitted segment / of the finished segment that covers row ce
+    int in_rec2, in_rec3; // (start, kind) of the next two segment starts after the first emitted one (found by the sweep): merge points
+                          // that let a repair stop after a few rows instead of a whole chunk
     bool done;            // finished (or retired); nothing more to scan
     bool valid;           // the lane has a fiber
     bool retired;         // gave up: a segment did not fit the window; ovf_rec = renewal state to continue from
@@ -150,7 +153,7 @@ template <typename T> struct Lane {
     PTV_HD void init(const Window<T, W>& w, int lane, const TaskGeom& g, T lam, bool is_valid) {
         i = g.p0; last = g.p0 - 1; blo = bhi = g.p0;
         Z = -(acc_t)lam; lo = hi = 0.0;
-        in_rec = out_rec = ovf_rec = REC_NONE;
+        in_rec = out_rec = ovf_rec = in_rec2 = in_rec3 = REC_NONE;
         valid = is_valid; done = !is_valid; retired = false; xcur = T(0);
         w.set_flag(g.p0, lane, LK_BEGIN + 1);           // the (cold) start of the scan is a segment start of kind BEGIN
     }
@@ -254,6 +257,7 @@ PTV_HD void warp_task(Env& env, Feed& feed, Drain& drain, const Window<T, W>& w,
     int row_hi = g.p0;                // rows below are in the window, ready for the scan
     int fill_pos = g.cs;              // next owned row to sweep (multiple of 8)
     bool ph1 = true;                  // some lane has not emitted its first owned segment yet
+    bool recs_open = true;            // some lane may still lack its second / third start record
     const int BIG = 0x3fffffff;
     // One epoch = sweep what is final, slide the window, ask for more rows, take over what has landed, run as many scan steps as
     // every participating lane can take without a bounds check.  Three warp reductions and one barrier poll in the steady state.
@@ -268,6 +272,8 @@ PTV_HD void warp_task(Env& env, Feed& feed, Drain& drain, const Window<T, W>& w,
             if (upto < g.ce) upto &= ~7;               // whole groups only, except at the very end of the chunk
             if (upto > fill_pos) {
                 const int a = fill_pos;
+                const bool need_recs = recs_open && env.any([&](Lane<T>& L, int) { return L.valid && L.in_rec3 == REC_NONE; });
+                if (!need_recs) recs_open = false;
                 env.each([&](Lane<T>& L, int lane) {
                     for (int r = a; r < upto; r += 8) {
                         T xs[8];
@@ -275,6 +281,16 @@ PTV_HD void warp_task(Env& env, Feed& feed, Drain& drain, const Window<T, W>& w,
                         const unsigned long long fl = w.flags8(r, lane);
                         T t[8];
                         w.ld8(r, lane, t);                                          // unconditional: straight-line, loads overlap
+                        if (need_recs && L.in_rec3 == REC_NONE && fl != 0ull) {     // first groups of a chunk only
+                            const int base = rec_pos(L.in_rec) > g.cs ? rec_pos(L.in_rec) : g.cs;
+                            for (int u = 0; u < 8; u++) {
+                                const int f8 = (int)((fl >> (8 * u)) & 0xffull);
+                                if (f8 && r + u > base && r + u < g.ce) {
+                                    if (L.in_rec2 == REC_NONE) L.in_rec2 = rec_pack(r + u, f8 - 1);
+                                    else if (L.in_rec3 == REC_NONE) L.in_rec3 = rec_pack(r + u, f8 - 1);
+                                }
+                            }
+                        }
 #pragma unroll
                         for (int u = 0; u < 8; u++) {
                             L.xcur = ((fl >> (8 * u)) & 0xffull) ? t[u] : L.xcur;
@@ -407,10 +423,12 @@ struct TaskPlan {
 // first emitted segment equals the predecessor's record of the segment that covers the chunk's first row (both scans are then
 // in the identical renewal state from that start on).  Otherwise -- or when a lane retired inside the chunk -- the exact
 // sequential scan continues from the last verified renewal state, writing results directly, until one of its finished
-// segments coincides with the first segment of a later chunk (merge) or the fiber ends.  Returns the number of repair scans.
+// segments coincides with one of the recorded segment starts of a later chunk (its first, or the two after it) or the fiber ends.
+// Returns the number of repair scans.
 // prep(pos): called before every repair scan with its start row (the kernel stages the fiber's rows from there into shared memory).
-template <typename T, class RecIn, class RecOut, class RecOvf, class Prep, class Ld, class St>
-PTV_HD int verify_repair_fiber(const ChunkPlan& pl, T lam, RecIn rin, RecOut rout, RecOvf rovf, Prep prep, Ld ld, St st) {
+template <typename T, class RecIn, class RecIn2, class RecIn3, class RecOut, class RecOvf, class Prep, class Ld, class St>
+PTV_HD int verify_repair_fiber(const ChunkPlan& pl, T lam, RecIn rin, RecIn2 rin2, RecIn3 rin3, RecOut rout, RecOvf rovf, Prep prep, Ld ld, St st,
+                               const acc_t* rcp = nullptr, int nrcp = 0) {
     int repairs = 0, c = 0;
     bool entry_ok = true;                 // chunk c is known to be exact on entry (chunk 0; or established by a merge)
     while (c < pl.nchunks) {
@@ -421,16 +439,24 @@ PTV_HD int verify_repair_fiber(const ChunkPlan& pl, T lam, RecIn rin, RecOut rou
         if (cur == REC_NONE) { c++; entry_ok = false; continue; }
         repairs++;
         int resume = pl.nchunks;
+        int cs_next = pl.cs(cnext), cs_own = cnext > 0 ? pl.cs(cnext - 1) : 0;     // first rows of chunk cnext / of the chunk before it
         prep(rec_pos(cur));
         slope_seq<T>(pl.n, lam, rec_pos(cur), rec_kind(cur), ld,
                      [&](int f, int e, T v, int kind) {
                          for (int r = f; r <= e; r++) st(r, v);
-                         while (cnext < pl.nchunks && pl.cs(cnext) <= e) {     // chunk starts covered by this segment
-                             if (pl.cs(cnext) >= f && rin(cnext) == rec_pack(f, kind)) { resume = cnext; return true; }
-                             cnext++;
+                         const int rp = rec_pack(f, kind);
+                         while (cnext < pl.nchunks && cs_next <= e) {          // chunk starts covered by this segment
+                             if (cs_next >= f && rin(cnext) == rp) { resume = cnext; return true; }
+                             cs_own = cs_next; cnext++; cs_next = pl.cs(cnext);
                          }
+                         // the segment starts inside chunk cnext - 1: the same (start, kind) among that chunk's recorded starts means
+                         // its lane was in this very renewal state -- everything it wrote from row f on is exact
+                         const int co = cnext - 1;
+                         // (a lane that retired at row p scanned nothing from p on: its marks there do not count)
+                         if (co >= 0 && cs_own < f && (rin2(co) == rp || rin3(co) == rp) &&
+                             (rovf(co) == REC_NONE || f < rec_pos(rovf(co)))) { resume = co; return true; }
                          return false;
-                     });
+                     }, rcp, nrcp);
         c = resume; entry_ok = true;      // merged into chunk `resume` (or reached the end of the fiber)
     }
     return repairs;

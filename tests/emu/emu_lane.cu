@@ -109,6 +109,7 @@ static int run_all(int opkind, const T* A, const T* B, const T* C, T* X, T* X2, 
     const long long slabs = inc > 1 ? nf / inc : 1, per_slab = inc > 1 ? inc : nf;
     const long long gps = (per_slab + LANES - 1) / LANES;
     std::vector<int> rin((size_t)pl.nchunks * LANES), rout((size_t)pl.nchunks * LANES), rovf((size_t)pl.nchunks * LANES);
+    std::vector<int> rin2((size_t)pl.nchunks * LANES), rin3((size_t)pl.nchunks * LANES);
     for (long long s = 0; s < slabs; s++)
         for (long long gidx = 0; gidx < gps; gidx++) {
             Fibers<T> fb;
@@ -137,6 +138,7 @@ static int run_all(int opkind, const T* A, const T* B, const T* C, T* X, T* X2, 
                 for (int l = 0; l < LANES; l++) {
                     rin[(size_t)c * LANES + l] = env.L[l].in_rec; rout[(size_t)c * LANES + l] = env.L[l].out_rec;
                     rovf[(size_t)c * LANES + l] = env.L[l].retired ? env.L[l].ovf_rec : REC_NONE;
+                    rin2[(size_t)c * LANES + l] = env.L[l].in_rec2; rin3[(size_t)c * LANES + l] = env.L[l].in_rec3;
                     if (env.L[l].retired) es->retired_lanes++;
                 }
                 es->tasks++; es->steps_max += ts.iters; es->epochs += ts.epochs; es->retired_events += ts.retired; es->tails += ts.tail; es->rows_fed += fed;
@@ -145,7 +147,8 @@ static int run_all(int opkind, const T* A, const T* B, const T* C, T* X, T* X2, 
                 if (!fb.valid[l]) continue;
                 const long long base = fb.base[l], st = fb.stride, tb = fb.tbase[l];
                 es->repairs += verify_repair_fiber<T>(pl, lam,
-                    [&](int c) { return rin[(size_t)c * LANES + l]; }, [&](int c) { return rout[(size_t)c * LANES + l]; },
+                    [&](int c) { return rin[(size_t)c * LANES + l]; }, [&](int c) { return rin2[(size_t)c * LANES + l]; },
+                    [&](int c) { return rin3[(size_t)c * LANES + l]; }, [&](int c) { return rout[(size_t)c * LANES + l]; },
                     [&](int c) { return rovf[(size_t)c * LANES + l]; }, [](int) {},
                     [&](int r) { return op.in(base + (long long)r * st); }, [&](int r, T v) { op.out(base + (long long)r * st, tb + r, v); });
             }

@@ -1,4 +1,5 @@
-"""Experiment: strided plain pass writing its result transposed (fiber-major, 16-byte scattered stores) vs in place."""
+"""Strided plain pass writing its result in place (op 0) vs transposed, fiber-major (op 6).  Measured: +3.7 us per 134 MB array with the
+warp-cooperative in-place exchange, +10 us with naive 16-byte scattered stores (the first version of this experiment)."""
 import ctypes as C, os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -12,8 +13,9 @@ st = vp(torch.cuda.current_stream().cuda_stream)
 
 
 def run(variant, out):
-    lib.proxtv_lane_tuning(0, 32, variant)
-    assert lib.proxtv_lane_prox_dev_f64(0, vp(x.data_ptr()), None, None, vp(out.data_ptr()), M, N, M, 0.2, st), lib.proxtv_last_error()
+    lib.proxtv_lane_tuning(0, 32, variant & 0xffff)
+    op = 6 if variant & 0x10000 else 0            # 6 = plain pass, result transposed (in-place warp-cooperative exchange, store8_transposed)
+    assert lib.proxtv_lane_prox2_dev_f64(op, vp(x.data_ptr()), None, None, vp(out.data_ptr()), None, M, N, M, 0.2, st), lib.proxtv_last_error()
 
 
 def timeit(variant, out, reps=20):
