@@ -34,12 +34,12 @@ B_PER_PIXEL_SOLVE = lambda b, maxit=35: b * (1 + 6 * maxit + 5)      # noqa: E73
 LAM = 0.2
 
 
-def ncu_traffic(cls=-1):
+def ncu_traffic(cls=-1, lane_t=False):
     """dram__bytes_read + dram__bytes_write per launch of the dominant kernel from the committed ncu --set full capture.
-    cls 0 / 1: the lane engine's column / row pass (profiles/r2_lane_ncu_full.csv, columns launch0 / launch1);
-    -1: round 1's chunked scan (mean of its two captured launches)."""
+    cls 0 / 1: the lane engine's column / row pass (profiles/r2_lane_staged_ncu_full.csv, or r2_lane_t_ncu_full.csv for the transposed
+    schedule; columns launch0 = row pass, launch1 = column pass); -1: round 1's chunked scan (mean of its two captured launches)."""
     try:
-        path = "r1_contig_kernel_ncu_full.csv" if cls < 0 else "r2_lane_ncu_full.csv"
+        path = "r1_contig_kernel_ncu_full.csv" if cls < 0 else ("r2_lane_t_ncu_full.csv" if lane_t else "r2_lane_staged_ncu_full.csv")
         r = w = None
         for line in open(os.path.join(ROOT, "profiles", path)):
             p = line.strip().split(",")
@@ -430,8 +430,8 @@ def main():
                                    % (M, M, LAM), "engine": args.engine + (" (lane-per-fiber slope-form engine, kernels_lane.cu)" if lane else ""),
                        "l2": "working set 4 x %d MiB > 126 MB L2 (inputs larger than L2, no flush)" % (nbytes >> 20)},
             "roofline": {"bound": "hbm", "kernel": kname[dom], "achieved": ach, "peak": peak, "unit": "GB/s",
-                         "frac": ach / peak, "traffic": ncu_traffic(dom if lane else -1) if M == 4096 else None,
-                         "traffic_source": "profiles/r2_lane_ncu_full.csv (ncu --set full, same kernels and shape)" if lane else "profiles/r1_contig_kernel_ncu_full.csv",
+                         "frac": ach / peak, "traffic": ncu_traffic(dom if lane else -1, lane_t) if M == 4096 else None,
+                         "traffic_source": ("profiles/r2_lane_t_ncu_full.csv" if lane_t else "profiles/r2_lane_staged_ncu_full.csv") + " (ncu --set full, same kernels and shape)" if lane else "profiles/r1_contig_kernel_ncu_full.csv",
                          "algorithmic_bytes_per_launch": sweeps[dom] * M * M * 8, "peak_source": peak_src,
                          "avg_launch_ms": avg_ms, "launches_timed": int(ks[dom]),
                          "timing_region": "%d additional steps right after the timed region, same kernels launched one by one (no graph replay), CUDA events around every launch" % args.steps,
