@@ -219,6 +219,23 @@ def run_other_workload(args, rank, world, local):
         alg_bytes = None                 # needs the iteration count: filled in after the run
         workload = "tvgen PD_TV %dx%dx%d f32, ws=(.2,.2,.2), ds=(1,2,3)" % shp; dtype = "f32 storage, f64 scan arithmetic"
         h2d = d2h = units * 4
+    elif wl == "split":                 # ONE image split over all ranks: column / row slabs, two all-to-alls per iteration
+        from proxtv_b200.distributed import tv1_2d_single_sharded
+        H = args.size
+        x = None
+        if rank == 0:
+            g = torch.Generator(device="cuda"); g.manual_seed(0)
+            lv = torch.randn((H // 64, H // 64), device="cuda", dtype=torch.float64, generator=g).repeat_interleave(64, dim=0).repeat_interleave(64, dim=1)
+            x = (lv + torch.randn((H, H), device="cuda", dtype=torch.float64, generator=g) * 0.3).t()      # column-major view, like the reference's arrays
+        tm = {}
+        step = (lambda: tv1_2d_single_sharded(x, LAM, timings=tm)) if world > 1 else (lambda: ptv.tv1_2d(x, LAM))  # noqa: E731
+        units, unit, metric = H * H, "Mpixels/s", "tv1_2d single image Mpixels/s"
+        alg_bytes = units * B_PER_PIXEL_SOLVE(8)
+        workload = "tv1_2d DR2_TV ONE %dx%d f64 image over %d GPU(s), lambda=%.1f; %s" % (
+            H, H, world, LAM, "column / row slabs, 2 NCCL all-to-alls per iteration, scatter + gather from/to rank 0 inside the timed region" if world > 1 else "single GPU")
+        dtype = "f64"
+        h2d = d2h = 0
+        extra["timings_rank0"] = tm
     else:                               # cfg5: tv1_2d on a batch of 2048 x 2048 f32 images, 128 per GPU, NCCL scatter / gather of images
         from proxtv_b200.distributed import tv1_2d_batched_sharded
         per_gpu = args.batch or 128; H = 2048; B = per_gpu * world
@@ -257,17 +274,17 @@ def run_other_workload(args, rank, world, local):
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     ms_step = float(tmax.item()) / args.steps
-    total_units = units if wl == "cfg5" else units * world
+    total_units = units if wl in ("cfg5", "split") else units * world
     if wl == "cfg4":
         iters = int(inf[0]); extra["iterations"] = iters; extra["stop"] = float(inf[1])
         alg_bytes = units * 4 * ((k + 1) + iters * (5 * k + 2))
     if rank == 0:
-        ach = alg_bytes * (1 if wl == "cfg5" else world) / (ms_step * 1e-3) / 1e9 / world
+        ach = alg_bytes * (1 if wl in ("cfg5", "split") else world) / (ms_step * 1e-3) / 1e9 / world
         line = {"metric": metric, "value": total_units / (ms_step * 1e-3) / 1e6, "unit": unit, "n_gpus": world, "steps": args.steps,
-                "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if wl == "split" else "weak", "vs_baseline": None,
                 "dtype": dtype, "data": "synthetic", "config": dict({"workload": workload}, **extra),
                 "roofline": {"bound": "hbm", "kernel": "whole step (all kernels of the workload)", "achieved": ach, "peak": peak, "unit": "GB/s per GPU",
-                             "frac": ach / peak, "algorithmic_bytes_per_step_per_gpu": alg_bytes / (world if wl == "cfg5" else 1), "peak_source": peak_src, "traffic": None},
+                             "frac": ach / peak, "algorithmic_bytes_per_step_per_gpu": alg_bytes / (world if wl in ("cfg5", "split") else 1), "peak_source": peak_src, "traffic": None},
                 "gpu_launches": int(sum(kl[i] for i in range(3))), "clocks": clk,
                 "e2e": {"value": None, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "note": "device-resident workload (inputs generated on the GPU); the headline e2e number is config 2's"}}
@@ -285,7 +302,7 @@ def main():
     ap.add_argument("--size", type=int, default=4096)
     ap.add_argument("--engine", default="auto")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4", "cfg5"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4", "cfg5", "split"])
     ap.add_argument("--batch", type=int, default=0, help="cfg3: signals; cfg5: images per GPU (0 = BASELINE.json's)")
     ap.add_argument("--pieces", type=int, default=4, help="cfg5: pipelined transfer pieces per GPU slab")
     args = ap.parse_args()
