@@ -228,14 +228,13 @@ def run_other_workload(args, rank, world, local):
             lv = torch.randn((H // 64, H // 64), device="cuda", dtype=torch.float64, generator=g).repeat_interleave(64, dim=0).repeat_interleave(64, dim=1)
             x = (lv + torch.randn((H, H), device="cuda", dtype=torch.float64, generator=g) * 0.3).t()      # column-major view, like the reference's arrays
         tm = {}
-        step = (lambda: tv1_2d_single_sharded(x, LAM, timings=tm)) if world > 1 else (lambda: ptv.tv1_2d(x, LAM))  # noqa: E731
+        step = (lambda: tv1_2d_single_sharded(x, LAM)) if world > 1 else (lambda: ptv.tv1_2d(x, LAM))  # noqa: E731
         units, unit, metric = H * H, "Mpixels/s", "tv1_2d single image Mpixels/s"
         alg_bytes = units * B_PER_PIXEL_SOLVE(8)
         workload = "tv1_2d DR2_TV ONE %dx%d f64 image over %d GPU(s), lambda=%.1f; %s" % (
             H, H, world, LAM, "column / row slabs, 2 NCCL all-to-alls per iteration, scatter + gather from/to rank 0 inside the timed region" if world > 1 else "single GPU")
         dtype = "f64"
         h2d = d2h = 0
-        extra["timings_rank0"] = tm
     else:                               # cfg5: tv1_2d on a batch of 2048 x 2048 f32 images, 128 per GPU, NCCL scatter / gather of images
         from proxtv_b200.distributed import tv1_2d_batched_sharded
         per_gpu = args.batch or 128; H = 2048; B = per_gpu * world
@@ -285,7 +284,8 @@ def run_other_workload(args, rank, world, local):
                 "dtype": dtype, "data": "synthetic", "config": dict({"workload": workload}, **extra),
                 "roofline": {"bound": "hbm", "kernel": "whole step (all kernels of the workload)", "achieved": ach, "peak": peak, "unit": "GB/s per GPU",
                              "frac": ach / peak, "algorithmic_bytes_per_step_per_gpu": alg_bytes / (world if wl in ("cfg5", "split") else 1), "peak_source": peak_src, "traffic": None},
-                "gpu_launches": int(sum(kl[i] for i in range(3))), "clocks": clk,
+                "gpu_launches": (args.steps * 71 if (wl == "split" and world > 1) else int(sum(kl[i] for i in range(3))))   # split: 35 column + 36 row lane passes per solve on every rank, issued through proxtv_lane_prox_dev_*
+                                , "clocks": clk,
                 "e2e": {"value": None, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "note": "device-resident workload (inputs generated on the GPU); the headline e2e number is config 2's"}}
         print(json.dumps(line))
