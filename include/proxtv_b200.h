@@ -103,9 +103,12 @@ const char *proxtv_version(void);
  * form (7) wherever the shape suits TMA tiling (16-byte aligned bases, row pitch a multiple of 16 bytes, positive weights, enough
  * fibers), else the chunked family; 1 sequential lane-per-fiber; 2 chunked speculative scan with the plain serial schedule;
  * 3 chunked with direct strided staging; 4 pipelined gather/scatter schedule; 5 transposeless schedule (scan kernels write both
- * layouts); 6 plain transposes around a fused row kernel; 7 the lane engine (kernels_lane.cu).  Engines 2, 4, 5, 6 are bit-identical
- * to each other (the reference's own arithmetic); the lane engine agrees with them to ~1e-13 (same decisions, slope-form arithmetic).
- * The 1D entry points of Part 1 always use the bit-faithful chunked kernels.  Returns the previous value. */
+ * layouts); 6 plain transposes around a fused row kernel; 7 the lane engine (kernels_lane.cu; DR2_TV: column pass over contiguous
+ * fibers, row pass with the three operands combined at landing); 8 the lane engine with the transposed DR2_TV schedule (both passes
+ * strided, arithmetic in the drains, results written transposed; what row-major images always use).  Engines 2, 4, 5, 6 are
+ * bit-identical to each other (the reference's own arithmetic); 7 and 8 are bit-identical to each other and agree with the others to
+ * ~1e-13 (same decisions, slope-form arithmetic).  The 1D entry points of Part 1 always use the bit-faithful chunked kernels.
+ * Returns the previous value. */
 int proxtv_set_engine(int engine);
 
 /* Batched 1D prox over the fibers of a column-major array: nf fibers of len samples, fiber j starting at
@@ -170,10 +173,17 @@ void proxtv_host_free(void *p);
 /* release the cached device workspace */
 void proxtv_release_workspace(void);
 
-/* Lane engine, for measurements: one batched prox pass with the fused arithmetic `op` (0 plain: X = prox(A); 1 Douglas-Rachford
- * second half: X = (C - B) + prox(A - (2 (C - B) - C)); 2 final projection: X = prox(A - (C - B))); fibers (nf, len, inc) as above
- * (inc == 1 only with op 0).  Returns 0 when the shape does not suit the engine.  tuning: chunk length (0 = one wave of warp tasks),
- * halo rows, kernel variant; stats: number of fibers that went through the sequential repair path since the last reset. */
+/* Lane engine, one batched prox pass with the fused arithmetic `op` over the fibers (nf, len, inc) as above (inc == 1 only with op 0);
+ * used by the multi-GPU driver (proxtv_b200/distributed.py) and by the measurement tools.  With x = prox(scan input):
+ *   0 plain                 X = prox(A)
+ *   1 DR second half        X = (C - B) + prox(A - (2 (C - B) - C))                 (operands combined when their tiles land)
+ *   2 DR final projection   X = prox(A - (C - B))
+ *   3 DR first half, T      x = prox(A); d = C - x; X^T = B - (2 d - C); X2^T = d   (operands read in the drain; ^T: results written
+ *   4 DR final, T           X^T = B - (C - prox(A))                                  fiber-major, element (fiber f, row r) at f * len + r)
+ *   5 DR second half, T     X^T = B + prox(A)
+ *   6 plain, T              X^T = prox(A)
+ * Returns 0 when the shape does not suit the engine (bases and row pitch multiples of 16 bytes).  tuning: chunk length (0 = automatic),
+ * halo rows, kernel variant (-1 = default per storage type); stats: fibers that went through the repair path since the last reset. */
 int proxtv_lane_prox_dev_f64(int op, const double *A, const double *B, const double *C, double *X, long long nf, int len,
                              long long inc, double lam, void *stream);
 int proxtv_lane_prox_dev_f32(int op, const float *A, const float *B, const float *C, float *X, long long nf, int len,
