@@ -645,6 +645,7 @@ static cudaError_t launch_variant(int variant, LaneArgs<T>& a, cudaStream_t st, 
         case 5: return launch_v<T, 128, 8, 16, OP, 1, LAY>(a, st, slots);
         case 6: if constexpr (sizeof(T) == 4) return launch_v<T, 128, 8, 32, OP, 4, LAY>(a, st, slots);      // float32: same bytes, twice the rows, half the epochs
                 else return launch_v<T, 64, 8, 16, OP, 4, LAY>(a, st, slots);
+        case 7: return launch_v<T, 64, 8, 24, OP, 4, LAY>(a, st, slots);      // 24-step epochs: -1 % on config 2, but only 20 window rows of slack
         default: return launch_v<T, 64, 8, 16, OP, 4, LAY>(a, st, slots);
     }
 }
