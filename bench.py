@@ -174,7 +174,7 @@ def run_other_workload(args, rank, world, local):
     import torch
     import torch.distributed as dist
     import proxtv_b200 as ptv
-    from oracle import oracle as O
+    import synth_inputs as S
 
     torch.cuda.set_device(local)
     if world > 1:
@@ -206,7 +206,7 @@ def run_other_workload(args, rank, world, local):
         h2d, d2h = B * (2 * L - 1) * 8, B * L * 8
     elif wl == "cfg4":                  # tvgen 3D anisotropic TV (PD_TV), 512 x 512 x 256 f32
         shp = (512, 512, 256)
-        V = O.gen_cfg4(shp, seed=rank)
+        V = S.gen_cfg4(shp, seed=rank)
         Vd = torch.from_numpy(np.ascontiguousarray(V.astype(np.float32).transpose(2, 1, 0))).cuda(); outd = torch.empty_like(Vd)
         ns = np.array(shp, dtype=np.int32); dims = np.array([1.0, 2.0, 3.0]); inf = np.zeros(3)
 
@@ -318,7 +318,7 @@ def main():
     import torch
     import torch.distributed as dist
     import proxtv_b200 as ptv
-    from oracle import oracle as O          # input generators + the cpu_baseline leg only
+    import synth_inputs as S               # seeded input generators; oracle/ is imported by the cpu_baseline leg only
 
     torch.cuda.set_device(local)
     if world > 1:
@@ -326,7 +326,7 @@ def main():
     lib = ptv.require_device()
     ptv.set_engine(args.engine)
     M = args.size
-    Yh = O.gen_cfg2(M, M, seed=rank)                                     # F-ordered float64, one image per rank
+    Yh = S.gen_cfg2(M, M, seed=rank)                                     # F-ordered float64, one image per rank
     Yd = torch.from_numpy(np.ascontiguousarray(Yh.T)).cuda()             # device copy, column-major image
     out = torch.empty_like(Yd)
     info = np.zeros(3)
@@ -462,6 +462,7 @@ def main():
             "clocks": clk,
         }
         if world == 1 and not args.no_cpu_baseline:
+            from oracle import oracle as O          # the cpu_baseline leg: the one place the measured arm's process touches oracle/
             try:
                 R = O.Ref(); kind = "reference"
             except Exception:  # noqa: BLE001

@@ -3,7 +3,7 @@ libraries of older revisions work).  usage: python tools/bisect_bench.py lib1.so
 import ctypes as C, os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from oracle import oracle as O
+import synth_inputs as O
 
 def ev(fn, reps=5):
     for _ in range(2): fn()

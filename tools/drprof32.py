@@ -3,7 +3,7 @@ import ctypes as C, os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import proxtv_b200 as ptv
-from oracle import oracle as O
+import synth_inputs as O
 lib = ptv.require_device()
 H = int(sys.argv[1]) if len(sys.argv) > 1 else 2048; Bn = int(sys.argv[2]) if len(sys.argv) > 2 else 8
 imgs = torch.stack([torch.from_numpy(np.ascontiguousarray(O.gen_cfg2(H, H, seed=s).astype(np.float32))) for s in range(Bn)]).cuda()

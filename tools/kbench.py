@@ -4,7 +4,7 @@ import ctypes as C, sys, os
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import proxtv_b200 as ptv
-from oracle import oracle as O
+import synth_inputs as O
 
 def timeit(fn, reps=10):
     for _ in range(3): fn()

@@ -3,7 +3,7 @@ import ctypes as C, os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import proxtv_b200 as ptv
-from oracle import oracle as O
+import synth_inputs as O
 lib = ptv.require_device(); vp = C.c_void_p
 lib.proxtv_lane_prox_dev_f64.argtypes = [C.c_int, vp, vp, vp, vp, C.c_longlong, C.c_int, C.c_longlong, C.c_double, vp]
 lib.proxtv_lane_tuning.argtypes = [C.c_int, C.c_int, C.c_int]

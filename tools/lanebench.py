@@ -4,7 +4,7 @@ import ctypes as C, json, os, sys, time
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import proxtv_b200 as ptv
-from oracle import oracle as O
+import synth_inputs as O
 
 lib = ptv.require_device()
 vp = C.c_void_p

@@ -3,7 +3,7 @@ import ctypes as C, os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import proxtv_b200 as ptv
-from oracle import oracle as O
+import synth_inputs as O
 lib = ptv.require_device()
 shp = tuple(int(v) for v in sys.argv[1].split("x")) if len(sys.argv) > 1 else (512, 512, 256)
 V = O.gen_cfg4(shp, seed=0).astype(np.float32)
