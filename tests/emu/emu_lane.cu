@@ -177,6 +177,27 @@ int emu_lane_f32(int opkind, const float* A, const float* B, const float* C, flo
     if (stats) memcpy(stats, &es, sizeof(es));
     return rc;
 }
+// the chunk plan: chunk count after fit(), boundaries cs(0..nchunks) and cold-start rows p0(0..nchunks-1)
+int emu_plan(int n, int want, int halo, int gran, int* cs_out, int* p0_out) {
+    ChunkPlan pl; pl.n = n; pl.halo = halo; pl.gran = gran; pl.nchunks = ChunkPlan::fit(n, want, halo, gran);
+    for (int c = 0; c <= pl.nchunks; c++) cs_out[c] = pl.cs(c);
+    for (int c = 0; c < pl.nchunks; c++) { const TaskGeom g = pl.geom(c); p0_out[c] = g.p0; if (g.cs != pl.cs(c) || g.ce != pl.cs(c + 1)) return -1; }
+    return pl.nchunks;
+}
+// the task plan: every task index maps to a distinct (group, chunk) with chunk < chunks_of(group); returns the task count or -1
+long long emu_taskplan(int nmax, long long gfull, long long groups) {
+    TaskPlan tp; tp.n = 4096; tp.halo = 32; tp.gran = 8; tp.nmax = nmax; tp.gfull = gfull;
+    const long long nt = tp.ntasks(groups);
+    std::vector<char> seen((size_t)groups * nmax, 0);
+    for (long long t = 0; t < nt; t++) {
+        long long g; int c, nc;
+        tp.locate(t, &g, &c, &nc);
+        if (g < 0 || g >= groups || c < 0 || c >= nc || nc != tp.chunks_of(g) || seen[(size_t)g * nmax + c]) return -1;
+        seen[(size_t)g * nmax + c] = 1;
+    }
+    long long cnt = 0; for (char v : seen) cnt += v;
+    return cnt == nt ? nt : -1;
+}
 // plain sequential slope-form scan of one fiber (the arithmetic the lanes use, without any window / chunk machinery)
 void emu_slope_seq_f64(const double* y, int n, double lam, double* x, long long* steps) {
     long long st = 0;

@@ -38,6 +38,8 @@ def emu():
     lib.emu_lane_f32.argtypes = [C.c_int, fp, fp, fp, fp, fp, C.c_longlong, C.c_int, C.c_longlong, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int,
                                  C.POINTER(C.c_longlong)]
     lib.emu_slope_seq_f64.argtypes = [dp, C.c_int, C.c_double, dp, C.POINTER(C.c_longlong)]
+    lib.emu_plan.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.emu_taskplan.argtypes = [C.c_int, C.c_longlong, C.c_longlong]; lib.emu_taskplan.restype = C.c_longlong
     return lib
 
 
@@ -179,3 +181,27 @@ def test_douglas_rachford_through_the_lane_passes(emu, port):
     got = out.reshape(N, M).T
     assert np.abs(got - want).max() / np.abs(want).max() <= 1e-9
     assert np.array_equal(got, staged)                       # same arithmetic, other data movement: bit-identical
+
+
+def test_chunk_and_task_plans(emu):
+    """ChunkPlan: boundaries start at 0, end at n, strictly increase, fall on the feed's tile rows, every chunk owns at least two tile
+    rows more than its halo costs, cold starts are aligned and never negative, and the work (owned rows + halo) is balanced to within
+    one tile row.  TaskPlan: task index -> (group, chunk) is a bijection, also when the last groups have one chunk fewer."""
+    rng = np.random.default_rng(11)
+    for _ in range(3000):
+        gran = int(rng.choice([8, 16, 32])); halo = gran * int(rng.integers(0, 5)); n = int(rng.integers(1, 20000)); want = int(rng.integers(1, 80))
+        cs = (C.c_int * 128)(); p0 = (C.c_int * 128)()
+        nc = emu.emu_plan(n, want, halo, gran, cs, p0)
+        assert 1 <= nc <= want, (n, want, halo, gran, nc)
+        b = [cs[c] for c in range(nc + 1)]
+        assert b[0] == 0 and b[-1] == n and all(x < y for x, y in zip(b, b[1:])), (n, want, halo, gran, b)
+        assert all(x % gran == 0 for x in b[:-1])
+        if nc > 1:
+            work = [b[1]] + [b[c + 1] - b[c] + halo for c in range(1, nc)]
+            assert max(work) - min(work) <= 2 * gran, (n, nc, halo, gran, work)      # rounding moves a boundary by less than one tile row
+            assert min(b[c + 1] - b[c] for c in range(nc)) >= gran
+        for c in range(nc):
+            assert p0[c] == max(0, b[c] - halo) and p0[c] % gran == 0
+    for nmax, gfull, groups in ((1, 7, 7), (14, 112, 128), (13, 128, 128), (2, 0, 5), (3, 5, 5), (9, 1, 1000)):
+        want = gfull * nmax + (groups - gfull) * (nmax - 1)
+        assert emu.emu_taskplan(nmax, gfull, groups) == want
