@@ -2,14 +2,19 @@
 //
 // One warp = 32 adjacent fibers x one chunk of rows.  Rows enter the warp's circular shared-memory window as TMA tiles
 // (cp.async.bulk.tensor, one mbarrier per tile slot; SASS: UTMALDG), the 32 lanes scan their own window column (bank-conflict
-// free), and finished rows leave through the drain, which also applies the fused Douglas-Rachford arithmetic:
+// free), and finished rows leave through the drain:
 //     STRIDED layout (fibers adjacent in memory: every dimension but the first of a column-major array)
 //         a window row IS one contiguous 32-sample line of the array: the tile lands in place, rows are drained with one
 //         coalesced store each -- no transposed copy of anything (this replaces the gather / scatter kernels of transpose.cu)
 //     CONTIG layout (fibers contiguous: the first dimension)
 //         a TMA box of 16 rows x 32 fibers lands fiber-major with the 128-byte hardware swizzle and is transposed into the window
 //         by the warp; finished boxes are transposed back and leave with a TMA store (UTMASTG)
-// No CTA-wide barrier anywhere: warps are independent (a CTA is just NW of them sharing the reciprocal table).
+// Fused Douglas-Rachford arithmetic (PassOp) sits either at the landing (staged ops: three operand tiles combined into the scan's
+// input) or in the drain (operands fetched with coalesced loads one epoch ahead); drain-side ops can write their results TRANSPOSED
+// -- fiber-major -- through an in-place exchange of the 32 x 8 block just swept (store8_transposed), which is what lets both passes of
+// a 2D iteration be STRIDED passes over two copies in opposite layouts (solver.cu: dr2_lane_t_body).
+// No CTA-wide barrier after the prologue: warps are independent (a CTA is NW of them sharing the reciprocal table; NW = 4, one per SM
+// sub-partition, three CTAs per SM when the pass needs no staging).
 #include "ptv_internal.h"
 #include "lane_core.cuh"
 #include <cuda.h>

@@ -26,7 +26,8 @@
 // and hands finished rows to the drain.  Long fibers (one image = only 4096 fibers) are cut into chunks of a few hundred
 // samples that start cold `halo` samples early; a chunk is exact iff the (start, kind) of its segment covering its first row
 // equals the predecessor's record of the same segment, which the last warp of a fiber group to finish verifies; a mismatch
-// (or a segment too long for the window) is repaired by an exact sequential continuation from the last verified renewal state.
+// (or a segment too long for the window) is repaired by an exact sequential continuation from the last verified renewal state,
+// which stops as soon as it reproduces one of the chunk's recorded segment starts (its first three): a few rows, as a rule.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
