@@ -49,6 +49,12 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, i
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
                  ::"r"(s32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(s32(bar)) : "memory");
 }
+__device__ __forceinline__ uint64_t policy_evict_first() { uint64_t p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p; }
+// same with an L2 cache policy (createpolicy) for the lines the load brings in
+__device__ __forceinline__ void tma_load_3d_hint(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar, uint64_t pol) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4}], [%5], %6;"
+                 ::"r"(s32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(s32(bar)), "l"(pol) : "memory");
+}
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* src, int c0, int c1, int c2) {
     asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
                  ::"l"(map), "r"(s32(src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
@@ -238,7 +244,10 @@ template <typename T, int W, int RT, int OP> struct FeedStrided {
             const int q = (int)((unsigned)row0 / (unsigned)R) - q0;
             uint64_t* b = bar + ((unsigned)q % (unsigned)NBAR);
             mbar_expect_tx(b, (uint32_t)(R * LANES * sizeof(T) * (OpTraits<OP>::staged ? 3 : 1)));
-            tma_load_3d(win + ((row0 & (W - 1)) << 5), &a->tmA, x0, row0, z, b);
+            // the scan's input is read again by the drain only in the LOP_DRA forms (C == A); everywhere else its lines are dead once
+            // they have landed: evict-first, so that what L2 keeps are the operand tiles the drain will come back for
+            if (OP == LOP_DRA || OP == LOP_DRA_FINAL) tma_load_3d(win + ((row0 & (W - 1)) << 5), &a->tmA, x0, row0, z, b);
+            else tma_load_3d_hint(win + ((row0 & (W - 1)) << 5), &a->tmA, x0, row0, z, b, policy_evict_first());
             if (OpTraits<OP>::staged) {
                 tma_load_3d(stB + (q % NST) * R * LANES, &a->tmB, x0, row0, z, b);
                 tma_load_3d(stC + (q % NST) * R * LANES, &a->tmC, x0, row0, z, b);
@@ -276,8 +285,15 @@ template <> struct Vec16<float> {
 };
 
 
-__device__ __forceinline__ void st_global_v16(double* p, const double* v) { asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v[0]), "d"(v[1]) : "memory"); }
-__device__ __forceinline__ void st_global_v16(float* p, const float* v) { asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory"); }
+// L2 eviction priorities of the drain: everything the drain touches is a LAST use inside this kernel -- results are written once and
+// not read again here, operands are read once (or re-read: the scan's own input, landed by TMA a window earlier) -- so its loads and
+// stores are marked evict-first; what stays in L2 are the tiles that were landed but not yet drained, i.e. exactly the re-reads.
+__device__ __forceinline__ void st_global_v16(double* p, const double* v, uint64_t pol) { asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(p), "d"(v[0]), "d"(v[1]), "l"(pol) : "memory"); }
+__device__ __forceinline__ void st_global_v16(float* p, const float* v, uint64_t pol) { asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "l"(pol) : "memory"); }
+__device__ __forceinline__ void st_stream(double* p, double v, uint64_t pol) { asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(pol) : "memory"); }
+__device__ __forceinline__ void st_stream(float* p, float v, uint64_t pol) { asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(pol) : "memory"); }
+__device__ __forceinline__ double ld_last(const double* p, uint64_t pol) { double v; asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol)); return v; }
+__device__ __forceinline__ float ld_last(const float* p, uint64_t pol) { float v; asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol)); return v; }
 
 // 8 results per lane (rows r0 .. r0+7 of 32 adjacent fibers) written TRANSPOSED -- dst[f * n + r], fiber-major -- without any extra
 // shared memory: the window rows just swept are dead, so their 32 x 8 block is rewritten fiber-major in place (16-byte chunks,
@@ -285,7 +301,7 @@ __device__ __forceinline__ void st_global_v16(float* p, const float* v) { asm vo
 // consecutive results of ONE fiber; a store instruction then covers 32 / NCH fibers x one full 64-byte (f64) / 32-byte (f32) run instead
 // of 32 scattered 16-byte pieces.  dst points at (fiber 0 of the group, row r0); fibers >= nvalid are not written.
 template <typename T, int W>
-__device__ __forceinline__ void store8_transposed(const Window<T, W>& w, int r0, int lane, const T* xs, T* dst, long long n, int nvalid) {
+__device__ __forceinline__ void store8_transposed(const Window<T, W>& w, int r0, int lane, const T* xs, T* dst, long long n, int nvalid, uint64_t pol) {
     constexpr int EPC = 16 / (int)sizeof(T), NCH = 8 / EPC, FB = 8 * (int)sizeof(T), FPI = LANES / NCH, SG = 8 / NCH;
     const uint32_t reg = s32(w.win) + (uint32_t)(((r0 & (W - 1)) << 5) * (int)sizeof(T));
     __syncwarp();                                        // every lane has read its column of these rows
@@ -298,7 +314,7 @@ __device__ __forceinline__ void store8_transposed(const Window<T, W>& w, int r0,
         const int f = lane / NCH + FPI * k;
         T v[EPC];
         Vec16<T>::ld(reg + (uint32_t)(f * FB + ((cc ^ ((f / SG) & (NCH - 1))) << 4)), v);
-        if (f < nvalid) st_global_v16(dst + (long long)f * n + cc * EPC, v);
+        if (f < nvalid) st_global_v16(dst + (long long)f * n + cc * EPC, v, pol);
     }
     __syncwarp();                                        // the block may be rewritten (second output, next tile)
 }
@@ -311,12 +327,12 @@ template <typename T, int W, int OP> struct DrainStrided {
     long long tbase, n; int nvalid;   // transposed results: element (fiber 0 of the group, row 0) of the fiber-major array; fibers in the group
     // operands of the fused drain arithmetic for the group of rows that will be swept next, fetched one epoch ahead (coalesced: a
     // window row is one contiguous line of every operand array)
-    T pb[8], pc[8]; int pf_row;
+    T pb[8], pc[8]; int pf_row; uint64_t pol;     // pol: L2 evict-first policy of the drain's loads and stores
     __device__ __forceinline__ void fetch(int r0) {
         const long long g0 = gbase + (long long)r0 * stride;
         const T* __restrict__ qb = B + g0; const T* __restrict__ qc = C + g0;
 #pragma unroll
-        for (int u = 0; u < 8; u++) { pb[u] = __ldg(qb); qb += stride; if (TR::drain_reads > 1) { pc[u] = __ldg(qc); qc += stride; } }
+        for (int u = 0; u < 8; u++) { pb[u] = ld_last(qb, pol); qb += stride; if (TR::drain_reads > 1) { pc[u] = ld_last(qc, pol); qc += stride; } }
     }
     __device__ __forceinline__ void prefetch(int r0, int ce, bool valid) {
         if (TR::drain_reads == 0 || !valid || r0 + 8 > ce || r0 == pf_row) return;
@@ -332,12 +348,12 @@ template <typename T, int W, int OP> struct DrainStrided {
             for (int u = 0; u < 8; u++) PassOp<T, OP>::out(xs[u], pb[u], pc[u], o1[u], o2[u]);
             pf_row = -1;
             if (TR::tout) {
-                store8_transposed<T, W>(w, r0, lane, o1, X + tbase + r0, n, nvalid);
-                if (TR::two_out) store8_transposed<T, W>(w, r0, lane, o2, X2 + tbase + r0, n, nvalid);
+                store8_transposed<T, W>(w, r0, lane, o1, X + tbase + r0, n, nvalid, pol);
+                if (TR::two_out) store8_transposed<T, W>(w, r0, lane, o2, X2 + tbase + r0, n, nvalid, pol);
             } else {
                 T* __restrict__ px = X + g0;                // one pointer, bumped by the row stride
 #pragma unroll
-                for (int u = 0; u < 8; u++) { *px = o1[u]; px += stride; }
+                for (int u = 0; u < 8; u++) { st_stream(px, o1[u], pol); px += stride; }
             }
             return;
         }
@@ -527,7 +543,7 @@ __global__ void __launch_bounds__(NW * 32, (12 + NW - 1) / NW) k_lane(const __gr
     } else {
         FeedStrided<T, W, RT, OP> feed{&a, win, stB, stC, bar, x0, z, g.p0 / RT, lane};
         DrainStrided<T, W, OP> drain; drain.B = a.B; drain.C = a.C; drain.X = a.X; drain.X2 = a.X2; drain.gbase = gbase; drain.stride = a.inc;
-        drain.pf_row = -1; drain.ce = g.ce; drain.tbase = tgroup; drain.n = pl.n; drain.nvalid = (int)(a.per_slab - x0 < LANES ? a.per_slab - x0 : LANES);
+        drain.pf_row = -1; drain.pol = policy_evict_first(); drain.ce = g.ce; drain.tbase = tgroup; drain.n = pl.n; drain.nvalid = (int)(a.per_slab - x0 < LANES ? a.per_slab - x0 : LANES);
         warp_task<T, W, TITER>(env, feed, drain, w, rcp, g, a.lam, TITER + TITER / 2 + RT, (TaskStats*)nullptr);
     }
     if (a.tlog && lane == 0) a.tlog[task * 4 + 1] = gtimer();
