@@ -205,3 +205,20 @@ def test_chunk_and_task_plans(emu):
     for nmax, gfull, groups in ((1, 7, 7), (14, 112, 128), (13, 128, 128), (2, 0, 5), (3, 5, 5), (9, 1, 1000)):
         want = gfull * nmax + (groups - gfull) * (nmax - 1)
         assert emu.emu_taskplan(nmax, gfull, groups) == want
+
+
+def test_transposed_result_ops(emu, port):
+    """Ops that write fiber-major (transposed) results, one by one against the plain pass: 6 (plain), 5 (B + x), 4 (B - (C - x)),
+    3 (two results), on strided fibers with a partial last group and chunked fibers."""
+    rng = np.random.default_rng(8)
+    M, N = 72, 90                                            # fibers = rows of the column-major M x N image: nf = M, len = N, inc = M
+    A = np.asfortranarray(rng.normal(0, 1, (M, N))).ravel("F"); Bv = rng.normal(0, 1, M * N); Cv = rng.normal(0, 1, M * N)
+    x = lane(emu, 0, A, None, None, M, N, M, 0.3, clen=32, halo=16)[0]
+    T = lambda v: v.reshape(N, M).T.copy().ravel()           # position (row r of fiber f) -> f * N + r
+    assert np.array_equal(lane(emu, 6, A, None, None, M, N, M, 0.3, clen=32, halo=16)[0], T(x))
+    assert np.array_equal(lane(emu, 5, A, Bv, None, M, N, M, 0.3, clen=32, halo=16)[0], T(Bv + x))
+    assert np.array_equal(lane(emu, 4, A, Bv, Cv, M, N, M, 0.3, clen=32, halo=16)[0], T(Bv - (Cv - x)))
+    X2 = np.full_like(A, np.nan)
+    u = lane(emu, 3, A, Bv, Cv, M, N, M, 0.3, clen=32, halo=16, X2=X2)[0]
+    d = Cv - x
+    assert np.array_equal(X2, T(d)) and np.array_equal(u, T(Bv - (2.0 * d - Cv)))
