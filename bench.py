@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of proxtv_b200:  tv1_2d (DR2_TV) Mpixels/s on 4096 x 4096 float64 images, lambda = 0.2.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--size M] [--engine auto|seq|chunked]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--size M] [--engine auto|lane|lane-t|chunked|seq]
+                    [--workload cfg2|cfg3|cfg4|cfg5|split] [--batch B] [--pieces P]
 
 One "step" = one complete solve (35 Douglas-Rachford iterations + the final projection pair, 72 fiber passes) of one
 4096 x 4096 image per GPU (BASELINE.json configs[1]; synthetic piecewise-constant + Gaussian-noise input).
@@ -14,8 +15,10 @@ Rank 0 prints ONE JSON line.  Keys beyond the base contract:
   roofline_solve  the north-star figure: whole-solve algorithmic bytes (1728 B/pixel) / solve time.
   e2e           same metric through the reference-facing C ABI call DR2_TV() with pinned HOST buffers (H2D + D2H inside).
   cpu_baseline  the reference's own OpenMP DR2_TV (oracle/_ref, compiled from the unmodified sources) on this box's host
-                cores, N = 1 only, on a bounded sample.
+                cores (thread count from a short sweep), N = 1 only, one solve of the FULL image.
 --impl reference times only that CPU implementation (rank 0 alone), same metric/config.
+--workload cfg3 | cfg4 | cfg5: the other BASELINE.json configurations (cfg5 over N GPUs: NCCL scatter / gather of image slabs,
+pipelined); --workload split: ONE image over all N ranks (strong scaling; two all-to-alls per iteration).
 """
 import argparse
 import ctypes as C
