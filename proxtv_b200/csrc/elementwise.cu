@@ -343,7 +343,23 @@ template <typename T> cudaError_t ew_dr_first(const T* Y, const T* t, T* U, T* D
     return cudaGetLastError();
 }
 
+// mean |y[e + 1] - y[e]| over n consecutive elements: one block, fixed summation order (the lane-engine suitability test, solver.cu)
+template <typename T> __global__ void k_mean_abs_step(const T* __restrict__ y, long long n, double* __restrict__ out) {
+    __shared__ double sh[256];
+    double s = 0.0;
+    for (long long e = threadIdx.x; e + 1 < n; e += blockDim.x) s += fabs((double)y[e + 1] - (double)y[e]);
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int k = 128; k > 0; k >>= 1) { if ((int)threadIdx.x < k) sh[threadIdx.x] += sh[threadIdx.x + k]; __syncthreads(); }
+    if (threadIdx.x == 0) out[0] = n > 1 ? sh[0] / (double)(n - 1) : 0.0;
+}
+template <typename T> cudaError_t ew_mean_abs_step(const T* y, long long n, double* out, cudaStream_t st) {
+    k_mean_abs_step<T><<<1, 256, 0, st>>>(y, n, out);
+    return cudaGetLastError();
+}
+
 #define INST(T) \
+    template cudaError_t ew_mean_abs_step<T>(const T*, long long, double*, cudaStream_t); \
     template cudaError_t ew_dr_first<T>(const T*, const T*, T*, T*, long long, cudaStream_t); \
     template cudaError_t ew_image_means_x2<T>(const T*, long long, int, T*, double*, cudaStream_t); \
     template cudaError_t ew_dr_reflect_cols<T>(const T*, const T*, T*, long long, cudaStream_t); \

@@ -83,6 +83,7 @@ template <typename T> cudaError_t ew_pd_combine(T* const* dp, T* const* dz, T* c
 template <typename T> cudaError_t ew_pdr_combine(T* const* dp, T* const* dz, T* const* hp, T* const* hz, int k, T* x, long long n,
                                                  double* scratch, double* result, cudaStream_t st);
 template <typename T> cudaError_t ew_div_scalar(const T* y, T* x, long long n, T k, cudaStream_t st);             // x = y / k
+template <typename T> cudaError_t ew_mean_abs_step(const T* y, long long n, double* out, cudaStream_t st);       // out[0] = mean |y[e+1] - y[e]|
 template <typename T> cudaError_t ew_dr_first(const T* Y, const T* t, T* U, T* D, long long n, cudaStream_t st);  // D = t - t ; U = Y - (2 D - t)
 constexpr int REDUCE_BLOCKS = 1184;    // 148 SMs x 8; partial sums are combined in a fixed order (deterministic)
 
@@ -98,6 +99,15 @@ template <typename T> int pd2_device(const T* y, const double* lambdas, const do
                                      int nds, int npen, int maxIters, void* ws, Engine eng, cudaStream_t st);
 template <typename T> int pd_device(const T* y, const double* lambdas_scaled, const double* dims, T* x, double* info,
                                     const int* ns, int nds, int npen, int maxIters, void* ws, Engine eng, cudaStream_t st);
+// Engine choice under ENGINE_AUTO for data y (device pointer, n elements) and penalty lam: the lane engine keeps every open segment of
+// a fiber inside a 64-row (float64) / 128-row (float32) shared-memory window and sends fibers whose segments outgrow it through a
+// slow exact repair path, so it only pays while segments are short -- lam not larger than about the mean step |y[i+1] - y[i]| of the
+// data (measured: the repair count of a 4096 x 4096 solve explodes from 13 to 1.9 million between lam = 0.57 and 2.9 mean steps,
+// 12 ms -> 4.4 s, where the chunked engine needs 70 ms).  Returns ENGINE_CHUNKED when eng is AUTO and the data does not suit the
+// lane engine, else eng.  Synchronises the stream once per new (y, n, lam) -- the decision is cached per device.
+template <typename T> Engine lane_guard(Engine eng, const T* y, long long n, double lam, cudaStream_t st);
+int lane_guard_last();           // tools / tests: last decision on this device (1 lane suits, 0 it does not, -1 none taken)
+
 // PDR_TV (src/TVNDopt.cpp:280-500): parallel Douglas-Rachford, fixed iteration count; same workspace as pd_device
 template <typename T> int pdr_device(const T* y, const double* lambdas_scaled, const double* dims, T* x, double* info,
                                      const int* ns, int nds, int npen, int maxIters, void* ws, Engine eng, cudaStream_t st);

@@ -150,6 +150,33 @@ static int dr2_piped_body(size_t M, size_t N, const T* Y, T w1, T w2, T* out, in
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// lane_guard (declared in ptv_internal.h): is the lane engine a good choice for this data?
+struct LaneGuardState { const void* y = nullptr; long long n = 0; double lam = 0.0; size_t ts = 0; int ok = -1; double* dev = nullptr; };
+static LaneGuardState g_guard_d[MAX_DEV];
+int lane_guard_last() { return g_guard_d[cur_dev()].ok; }
+template <typename T>
+Engine lane_guard(Engine eng, const T* y, long long n, double lam, cudaStream_t st) {
+    if (eng != ENGINE_AUTO || n < 2 || !(lam > 0.0)) return eng;
+    LaneGuardState& G = g_guard_d[cur_dev()];
+    if (!(G.ok >= 0 && G.y == (const void*)y && G.n == n && G.lam == lam && G.ts == sizeof(T))) {
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(st, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) { cudaGetLastError(); return eng; }
+        if (!G.dev && cudaMalloc(&G.dev, sizeof(double)) != cudaSuccess) { cudaGetLastError(); G.dev = nullptr; return ENGINE_CHUNKED; }
+        double step = 0.0;
+        const long long ns = n < (1LL << 18) ? n : (1LL << 18);               // the first 256k elements: a few fibers' worth
+        if (ew_mean_abs_step<T>(y, ns, G.dev, st) != cudaSuccess ||
+            cudaMemcpyAsync(&step, G.dev, sizeof(double), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+            cudaStreamSynchronize(st) != cudaSuccess) { cudaGetLastError(); return ENGINE_CHUNKED; }
+        const double kappa = sizeof(T) == 8 ? 1.0 : 2.0;                      // float32 windows hold twice the rows
+        G.y = (const void*)y; G.n = n; G.lam = lam; G.ts = sizeof(T);
+        G.ok = (step > 0.0 && lam <= kappa * step) ? 1 : 0;                   // a constant array (step == 0) is the lane engine's worst case
+    }
+    return G.ok ? eng : ENGINE_CHUNKED;
+}
+template Engine lane_guard<double>(Engine, const double*, long long, double, cudaStream_t);
+template Engine lane_guard<float>(Engine, const float*, long long, double, cudaStream_t);
+
+// ------------------------------------------------------------------------------------------------------------------
 // Douglas-Rachford on the lane-per-fiber engine (kernels_lane.cu): two kernels per iteration, no transposed copies, 6 array
 // sweeps per iteration (the algorithmic count).  With x1 = prox_cols(t), x2 = prox_rows(Y - s):
 //     columns   x1 = prox(t)                                    1 read + 1 write      CONTIG layout (TMA box in, TMA box out)
@@ -269,6 +296,7 @@ int dr2_device(size_t M, size_t N, int batch, int row_major, const T* Y, T w1, T
     T* scr = (T*)w; w += 4 * align256(n * sizeof(T));      // gather/scatter staging of the strided pass (+2 arrays of the T-space schedule)
     double* scratch = (double*)w;
     if (maxit <= 0) maxit = MAX_ITERS_DR;                                     // TV2Dopt.cpp:387
+    eng = lane_guard<T>(eng, Y, n, (double)(w1 > w2 ? w1 : w2), st);        // AUTO: the lane engine only while segments stay short
     // first pass: fibers along axis 0 (length M); second pass: along axis 1 (length N) -- the order is part of the contract.
     // column-major: axis-0 fibers are contiguous, axis-1 fibers have stride M; row-major storage swaps the two roles.
     const FiberGeom gc = row_major ? FiberGeom{(long long)N * batch, (int)M, (long long)N} : FiberGeom{(long long)N * batch, (int)M, 1};
@@ -452,6 +480,7 @@ int pd2_device(const T* y, const double* lambdas, const double* dims, T* x, doub
                     if (info) info[INFO_RC] = RC_ERROR; return 0; }
     long long n = 1; for (int i = 0; i < nds; i++) n *= ns[i];
     if (maxIters <= 0) maxIters = MAX_ITERS_PD;
+    if (npen >= 1) eng = lane_guard<T>(eng, y, n, npen >= 2 && lambdas[1] > lambdas[0] ? lambdas[1] : lambdas[0], st);
     FiberGeom g0{0, 0, 1}, g1{0, 0, 1};
     if (npen < 1 || !geom_of(ns, nds, dims[0], n, &g0) || (npen >= 2 && !geom_of(ns, nds, dims[1], n, &g1))) {
         printf("PD2_TV: invalid penalty dimensions\n"); if (info) info[INFO_RC] = RC_ERROR; return 0; }
@@ -490,6 +519,8 @@ int pd_device(const T* y, const double* lam, const double* dims, T* x, double* i
     long long n = 1; for (int i = 0; i < nds; i++) n *= ns[i];
     if (maxIters <= 0) maxIters = MAX_ITERS_PD;
     if (npen > 64) { printf("PD_TV: more than 64 penalty terms are not supported\n"); if (info) info[INFO_RC] = RC_ERROR; return 0; }
+    { double lmax = 0.0; for (int i = 0; i < npen; i++) if (lam[i] > lmax) lmax = lam[i];
+      eng = lane_guard<T>(eng, y, n, lmax, st); }
     FiberGeom g[64];
     for (int i = 0; i < npen; i++)
         if (!geom_of(ns, nds, dims[i], n, &g[i])) { printf("PD_TV: invalid penalty dimensions\n");
@@ -534,6 +565,8 @@ int pdr_device(const T* y, const double* lam, const double* dims, T* x, double* 
     long long n = 1; for (int i = 0; i < nds; i++) n *= ns[i];
     if (maxIters <= 0) maxIters = MAX_ITERS_DR;                                                       // :320
     if (npen > 64) { printf("PDR_TV: more than 64 penalty terms are not supported\n"); if (info) info[INFO_RC] = RC_ERROR; return 0; }
+    { double lmax = 0.0; for (int i = 0; i < npen; i++) if (lam[i] > lmax) lmax = lam[i];
+      eng = lane_guard<T>(eng, y, n, lmax, st); }
     FiberGeom g[64];
     for (int i = 0; i < npen; i++)
         if (!geom_of(ns, nds, dims[i], n, &g[i])) { printf("PDR_TV: invalid penalty dimensions\n");

@@ -412,3 +412,22 @@ def test_pinned_result_pool(ptv, port):
         assert e.flags.owndata or e.base is not None and relerr(e, want) <= 1e-9
     finally:
         ptv.set_pinned_results(prev)
+
+
+def test_auto_engine_guard(ptv, port):
+    """Engine 'auto' takes the lane engine only while the data keeps segments short (penalty <= about the mean step of the input);
+    a large penalty -- long segments, which the lane engine would send through its slow repair path -- goes to the chunked engine.
+    Either way, and with the lane engine forced, the result is the oracle's."""
+    lib = ptv.load()
+    Y = O.gen_cfg2(256, 256, seed=3, block=16)
+    prev = ptv.set_engine("auto")
+    try:
+        a = ptv.tv1_2d(Y, 0.2)
+        assert lib.proxtv_lane_guard_last() == 1
+        b = ptv.tv1_2d(Y, 5.0)
+        assert lib.proxtv_lane_guard_last() == 0
+        assert relerr(a, port.dr2_tv(Y, 0.2)[0]) <= 1e-9 and relerr(b, port.dr2_tv(Y, 5.0)[0]) <= 1e-9
+        ptv.set_engine("lane")                                   # forced: no guard, the repair path does the work
+        assert relerr(ptv.tv1_2d(Y, 5.0), port.dr2_tv(Y, 5.0)[0]) <= 1e-9
+    finally:
+        ptv.set_engine(prev)
