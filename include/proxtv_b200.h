@@ -194,8 +194,8 @@ int proxtv_lane_prox2_dev_f64(int op, const double *A, const double *B, const do
 void proxtv_lane_tuning(int clen, int halo, int variant);
 unsigned long long proxtv_lane_stats(int reset);
 /* Under engine 0 (auto) the solvers use the lane engine only while the data keeps segments short -- penalty not larger than about the
- * mean step |y[i+1] - y[i]| of (a sample of) the input, measured with one small kernel and one stream synchronisation per new
- * (input, size, penalty) -- and the chunked engine otherwise.  Last decision on the current device: 1 lane, 0 chunked, -1 none taken. */
+ * mean step |y[i+1] - y[i]| of (a sample of) the input, measured with one small kernel and one stream synchronisation per call --
+ * and the chunked engine otherwise.  Last decision on the current device: 1 lane, 0 chunked, -1 none taken. */
 int proxtv_lane_guard_last(void);
 /* tools: device buffer of 4 x cap_tasks uint64 that receives, per warp task of the next launches, {start ns, scan end ns, end ns, SM id}
  * (globaltimer); NULL switches the log off. */

@@ -104,7 +104,7 @@ template <typename T> int pd_device(const T* y, const double* lambdas_scaled, co
 // slow exact repair path, so it only pays while segments are short -- lam not larger than about the mean step |y[i+1] - y[i]| of the
 // data (measured: the repair count of a 4096 x 4096 solve explodes from 13 to 1.9 million between lam = 0.57 and 2.9 mean steps,
 // 12 ms -> 4.4 s, where the chunked engine needs 70 ms).  Returns ENGINE_CHUNKED when eng is AUTO and the data does not suit the
-// lane engine, else eng.  Synchronises the stream once per new (y, n, lam) -- the decision is cached per device.
+// lane engine, else eng.  One small kernel and one stream synchronisation per call (the data behind a pointer changes between calls).
 template <typename T> Engine lane_guard(Engine eng, const T* y, long long n, double lam, cudaStream_t st);
 int lane_guard_last();           // tools / tests: last decision on this device (1 lane suits, 0 it does not, -1 none taken)
 

@@ -158,7 +158,7 @@ template <typename T>
 Engine lane_guard(Engine eng, const T* y, long long n, double lam, cudaStream_t st) {
     if (eng != ENGINE_AUTO || n < 2 || !(lam > 0.0)) return eng;
     LaneGuardState& G = g_guard_d[cur_dev()];
-    if (!(G.ok >= 0 && G.y == (const void*)y && G.n == n && G.lam == lam && G.ts == sizeof(T))) {
+    {   // evaluated on every call: the same buffer (the C ABI's own staging area, a caller's frame buffer) holds different data each time
         cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
         if (cudaStreamIsCapturing(st, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) { cudaGetLastError(); return eng; }
         if (!G.dev && cudaMalloc(&G.dev, sizeof(double)) != cudaSuccess) { cudaGetLastError(); G.dev = nullptr; return ENGINE_CHUNKED; }
